@@ -1,0 +1,197 @@
+/*
+ * tqdne_b200.h -- C-ABI of the B200-native EDM sampling engine (libtqdne_b200.so).
+ *
+ * The reference (highfem/tqdne) has no FFI layer: its "operator API" is the Python module
+ * surface.  This header is the boundary a maintainer binds from Python with
+ * ctypes (INTEGRATION.md shows the stub); every entry point cites the reference call it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers are raw CUDA addresses owned by the caller
+ *     (PyTorch in the shipped host code); the library never allocates activation memory
+ *   - every function returns 0 on success, non-zero on failure; tq_last_error() describes it
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - activations are channels-last: [N, H, W, C] (2D) or [N, 1, L, C] (1D), dense
+ *   - `dtype`: TQ_BF16 -> tcgen05/TMEM/TMA tensor path, TQ_F32 -> FFMA parity path
+ *   - an op is appended to a `tq_plan` once (tensor maps are encoded then) and replayed with
+ *     tq_plan_run(); a plan is a straight-line list of kernel launches, CUDA-graph capturable
+ */
+#ifndef TQDNE_B200_H
+#define TQDNE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQ_ABI_VERSION 1
+
+enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         tq_abi_version(void);
+const char* tq_last_error(void);
+/* number of kernels launched by this library in this process since load / since last reset */
+int64_t     tq_launch_count(void);
+void        tq_launch_count_reset(void);
+
+/* ---- plan (straight-line launch list) ------------------------------------------------------ */
+typedef struct tq_plan tq_plan;
+tq_plan* tq_plan_create(void);
+void     tq_plan_destroy(tq_plan* p);
+int      tq_plan_num_ops(const tq_plan* p);
+/* launch ops [first, last) on `stream`; last < 0 means "to the end" */
+int      tq_plan_run(tq_plan* p, void* stream);
+int      tq_plan_run_range(tq_plan* p, int first, int last, void* stream);
+/* capture the whole plan into a CUDA graph once; later tq_plan_run() replays the graph */
+int      tq_plan_enable_graph(tq_plan* p, int enable);
+/* name of the kernel behind op i (for profiles and tests) */
+const char* tq_plan_op_name(const tq_plan* p, int i);
+
+/* ---- implicit-GEMM convolution / linear  -------------------------------------------------- *
+ * Replaces: nn.Conv1d/Conv2d built by conv_nd (tqdne/nn.py:16-24) at every call site of the
+ * denoiser and decoder (tqdne/unet.py:88,102,108-112,233,357; tqdne/blocks.py:56,94,128,134,
+ * 241,249,253,316,348,387,430), the nearest-upsample + conv pair (blocks.py:59-65), the skip
+ * concat feeding a conv (unet.py:396) and nn.Linear of emb_layers (unet.py:93-99).
+ *
+ * The reduction is described as a list of 64-channel K-slices.  Slice s multiplies the input box
+ * of source `src` shifted by (dx, dy) at channels [c0, c0+64) with weight columns
+ * [kb*64, kb*64+64).  A 3x3 "same" conv is 9*Cin/64 slices; a stride-2 conv reads four parity
+ * views of its input; a fused nearest-upsample conv runs 4 output-parity classes over the
+ * low-resolution grid; a skip concat or a fused 1x1 shortcut is just more slices / sources.    */
+typedef struct {
+    const void* ptr;      /* element (n=0,y=0,x=0,c=0) of the view                              */
+    int32_t N, H, W, C;   /* extent of the view (OOB reads are zero)                            */
+    int64_t sn, sy, sx;   /* element strides of n, y, x (channel stride is 1)                   */
+} tq_src;
+
+typedef struct {
+    int16_t src, dx, dy, rsv;
+    int32_t c0;           /* first channel of the slice inside the source                        */
+    int32_t kb;           /* weight K block (64 columns each)                                    */
+} tq_slice;
+
+typedef struct {
+    int32_t dtype;            /* TQ_BF16 | TQ_F32 : type of sources, weights, residual           */
+    int32_t N, H, W;          /* grid the 128-row tiles walk (output grid of one parity class)   */
+    int32_t cout;             /* real output channels                                            */
+    int32_t cout_pad;         /* rows of the weight matrix (multiple of 64)                      */
+    int32_t ktot;             /* columns of the weight matrix (multiple of 64)                   */
+    int32_t num_srcs;         /* 1..4                                                            */
+    int32_t num_classes;      /* 1, or 4 for the fused nearest-upsample conv                     */
+    int32_t num_slices;       /* slices per class                                                */
+    tq_src  srcs[4];
+    const tq_slice* slices;   /* HOST array [num_classes][num_slices], copied by the call        */
+    const void*  weights;     /* device [cout_pad][ktot], K contiguous                           */
+    const float* bias;        /* device [cout_pad] or NULL                                       */
+    const float* emb;         /* device: per-sample channel add emb[n*emb_ld + c] or NULL        */
+    int32_t emb_ld;
+    const void* residual;     /* device, same layout as out, dtype = `dtype`, or NULL            */
+    void*   out;
+    int32_t out_dtype;        /* TQ_BF16 | TQ_F32                                                */
+    int64_t out_sn, out_sy, out_sx;   /* element strides of the output                           */
+    int64_t out_class_off[4];         /* element offset of each parity class                     */
+    int32_t block_n;          /* 0 = auto, else 64 / 128 / 256                                   */
+} tq_conv_desc;
+int tq_plan_add_conv(tq_plan* p, const tq_conv_desc* d);
+
+/* ---- GroupNorm(32) [+ SiLU] over a (virtual) channel concat -------------------------------- *
+ * Replaces: GroupNorm32 / normalization (tqdne/nn.py:11-13,90-105) + nn.SiLU in in_layers /
+ * out_layers (unet.py:85-103, blocks.py:238-250), attention norm (blocks.py:126), `out`
+ * (unet.py:354-356), fed by th.cat([h, hs.pop()], dim=1) (unet.py:396) without materialising it.
+ * x0:[N,P,C0] (+ x1:[N,P,C1]) -> y:[N,P,C0+C1]; stats in fp32; eps as given; 32 groups.
+ * `ws` is a caller-provided fp32 scratch of 2*N*(C0+C1) floats.                                 */
+typedef struct {
+    int32_t dtype;         /* TQ_BF16 | TQ_F32 for x0, x1, y                                      */
+    int32_t N, P, C0, C1;  /* P = H*W positions                                                   */
+    const void* x0; const void* x1;
+    const float* gamma; const float* beta;   /* [C0+C1]                                           */
+    float   eps;
+    int32_t silu;          /* apply x*sigmoid(x) after the affine                                  */
+    void*   y;
+    float*  ws;
+} tq_gn_desc;
+int tq_plan_add_groupnorm(tq_plan* p, const tq_gn_desc* d);
+
+/* ---- attention core -------------------------------------------------------------------------- *
+ * Replaces: QKVAttention.forward (tqdne/blocks.py:156-190).  qkv:[N,T,3*heads*d] channels-last
+ * with channel = third*(heads*d) + head*d + c, out:[N,T,heads*d];
+ * w = softmax_fp32((q*s)^T (k*s)), s = d^-1/4, out = w v.                                         */
+typedef struct {
+    int32_t dtype; int32_t N, T, heads, d;
+    const void* qkv; void* out;
+} tq_attn_desc;
+int tq_plan_add_attention(tq_plan* p, const tq_attn_desc* d);
+
+/* ---- small dense layers in fp32 (embedding MLPs) ---------------------------------------------- *
+ * Replaces: nn.Linear / nn.SiLU of time_mlp, cond_mlp (tqdne/unet.py:210-227), their sum
+ * (unet.py:383-388) and the SiLU in front of every emb_layers Linear (unet.py:92).
+ *   v[m][j]      = sum_k act_in(x[m or 0][k]) * W[j][k] + b[j] (+ add[m or 0][j])
+ *   y[m][j]      = v                          (fp32, optional)
+ *   y_act[m][j]  = SiLU(v)                    (optional, stored as y_act_dtype: TQ_F32 | TQ_BF16)
+ * act_in: 0 none, 1 SiLU.  x_rows / add_rows == 1 broadcasts a single row to all M outputs.        */
+typedef struct {
+    int32_t M, K, Nout, x_rows;
+    const float* x; const float* W; const float* b;
+    int32_t act_in;
+    const float* add; int32_t add_rows;
+    float* y;
+    void*  y_act; int32_t y_act_dtype;
+} tq_linear_desc;
+int tq_plan_add_linear(tq_plan* p, const tq_linear_desc* d);
+/* feat[M, 2*half] = [sin(2*pi*t*W), cos(2*pi*t*W)],  t:[M] read from device                      */
+int tq_plan_add_fourier(tq_plan* p, const float* t, const float* W, int32_t M, int32_t half, float* feat);
+
+/* ---- sampler element-wise steps ------------------------------------------------------------------ *
+ * Replaces: LightningEDM.forward pre/post scaling (tqdne/edm.py:105-113) and the Heun/Euler
+ * state update of sample_deterministically / sample_stochastically (edm.py:171-230).
+ * State x is fp64 channels-last [N,P,C]; the denoiser input is written with C padded to Cpad.
+ * All scalars are passed by value per call (they are not part of a plan).
+ *
+ *   tq_edm_precondition : xin = dtype( float(x) * c_in )            (pad channels = 0)
+ *   tq_edm_euler        : D = F*c_out + c_skip*float(x);  d = (x - D)/sigma;  x1 = x + d*dt
+ *                         optionally xin = dtype(float(x1) * c_in_next)
+ *   tq_edm_heun         : D' = F*c_out' + c_skip'*float(x1); d' = (x1 - D')/sigma';
+ *                         x = x + dt*(0.5*d + 0.5*d');  optionally xin = dtype(float(x)*c_in_next)
+ * F is the fp32 channels-last network output [N,P,Cf] (row stride Cf >= C).                        */
+int tq_edm_precondition(const double* x, void* xin, int32_t dtype, int64_t NP, int32_t C, int32_t Cpad,
+                        float c_in, void* stream);
+int tq_edm_euler(const double* x, const float* F, int32_t Cf, double* d, double* x1,
+                 void* xin, int32_t dtype, int64_t NP, int32_t C, int32_t Cpad,
+                 float c_out, float c_skip, float sigma, float dt, float c_in_next, int32_t write_xin,
+                 void* stream);
+int tq_edm_heun(double* x, const double* x1, const double* d, const float* F, int32_t Cf,
+                void* xin, int32_t dtype, int64_t NP, int32_t C, int32_t Cpad,
+                float c_out, float c_skip, float sigma_next, float dt, float c_in_next, int32_t write_xin,
+                void* stream);
+/* x += noise * scale  (stochastic sampler churn, edm.py:205-207), fp64 */
+int tq_edm_add_noise(double* x, const double* noise, double scale, int64_t n, void* stream);
+
+/* ---- layout ------------------------------------------------------------------------------------- *
+ * [N,C,P] (reference NCHW/NCL, dtype_in) <-> [N,P,Cpad] channels-last (dtype_out), pad = 0.         */
+int tq_nchw_to_nhwc(const void* src, int32_t dtype_in, void* dst, int32_t dtype_out,
+                    int32_t N, int32_t C, int64_t P, int32_t Cpad, void* stream);
+int tq_nhwc_to_nchw(const void* src, int32_t dtype_in, int32_t Cld, void* dst, int32_t dtype_out,
+                    int32_t N, int32_t C, int64_t P, void* stream);
+
+/* ---- representation inverses ----------------------------------------------------------------------- *
+ * tq_logspec_griffinlim replaces LogSpectrogram.invert_representation (tqdne/representation.py:
+ * 152-175) with librosa 0.11 griffinlim(n_iter, hop, n_fft, random_state=0) semantics:
+ * rep:[items, n_fft/2, frames] in [-1,1] (reference NCHW order, any float dtype cast to fp32 by the
+ * caller) -> wave:[items, hop*(frames-1)].  phase0:[n_fft/2+1, frames] are the initial phase angles
+ * in radians (2*pi*RandomState(0).random()), shared by all items.  ws: fp32 scratch, size from
+ * tq_griffinlim_ws_bytes().  precision: TQ_F32 or TQ_F64 arithmetic.                                   */
+int64_t tq_griffinlim_ws_bytes(int32_t items, int32_t n_fft, int32_t frames, int32_t precision);
+int tq_logspec_griffinlim(const float* rep, const double* phase0, void* wave, int32_t items,
+                          int32_t n_fft, int32_t hop, int32_t frames, int32_t n_iter,
+                          double log_clip, double log_max, double momentum, int32_t precision,
+                          void* ws, void* stream);
+/* tq_mavg_envelope_inverse replaces MovingAverageEnvelope.invert_representation
+ * (representation.py:57-60): rep:[N,2*Cw,L] fp32 -> wave:[N,Cw,L] fp32.                                */
+int tq_mavg_envelope_inverse(const float* rep, float* wave, int32_t N, int32_t Cw, int64_t L,
+                             double log_eps, double eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TQDNE_B200_H */

@@ -1,0 +1,33 @@
+"""Shared fixtures: named architectures, seeded weights, golden vectors."""
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from oracle.weights import seeded_state_dict, shapes_of
+from tests.conftest import GOLDEN
+
+FEATURES = ("hypocentral_distance", "magnitude", "vs30", "hypocentre_depth", "azimuthal_gap")
+CFG = SimpleNamespace(features_keys=FEATURES, channels=3, latent_channels=8)
+
+
+def golden(name):
+    z = np.load(GOLDEN / f"{name}.npz")
+    return {k: (torch.from_numpy(z[k]) if z[k].ndim else z[k].item()) for k in z.files}
+
+
+def arch():
+    import tqdne_b200.architectures as a
+
+    return a
+
+
+def unet_cfg(kind):
+    a = arch()
+    return {"latent2d": a.get_2d_unet_config(CFG, 8, 8), "1d": a.get_1d_unet_config(CFG, 6, 6),
+            "pixel2d": a.get_2d_unet_config(CFG, 3, 3)}[kind]
+
+
+def seeded(module, seed):
+    module.load_state_dict(seeded_state_dict(shapes_of(module), seed))
+    return module.eval()

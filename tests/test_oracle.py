@@ -1,0 +1,151 @@
+"""CPU: the oracle restatement against the golden vectors produced by the reference itself."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import griffinlim_ref, torch_ref
+from oracle.weights import seeded_state_dict, shapes_of
+from tests.conftest import rel_l2
+from tests.helpers import CFG, arch, golden, unet_cfg
+
+TOL = 2e-5  # fp32 CPU restatement vs fp32 CPU reference: same ops, possibly different summation order
+
+
+def _sd(module, seed):
+    return seeded_state_dict(shapes_of(module), seed)
+
+
+@pytest.mark.parametrize("kind,name", [("latent2d", "unet_latent2d"), ("1d", "unet_1d"), ("pixel2d", "unet_pixel2d")])
+def test_unet_restatement_matches_reference(kind, name):
+    import tqdne_b200 as tq
+
+    g = golden(name)
+    cfg = unet_cfg(kind)
+    sd = _sd(tq.UNetModel(**cfg), g["seed"])
+    with torch.no_grad():
+        y = torch_ref.unet_forward(sd, cfg, g["x"], g["t"], g["cond"])
+    assert rel_l2(y, g["y"]) < TOL
+
+
+def test_decoder_encoder_restatement():
+    import tqdne_b200 as tq
+
+    enc_cfg, dec_cfg = arch().get_2d_autoencoder_configs(CFG)
+    g = golden("decoder2d")
+    with torch.no_grad():
+        y = torch_ref.decoder_forward(_sd(tq.Decoder(**dec_cfg), g["seed"]), dec_cfg, g["z"])
+    assert rel_l2(y, g["y"]) < TOL
+    g = golden("encoder2d")
+    with torch.no_grad():
+        y = torch_ref.encoder_forward(_sd(tq.Encoder(**enc_cfg), g["seed"]), enc_cfg, g["x"])
+    assert rel_l2(y, g["y"]) < TOL
+
+
+def _latent_edm():
+    import tqdne_b200 as tq
+
+    enc_cfg, dec_cfg = arch().get_2d_autoencoder_configs(CFG)
+    ae = tq.LightningAutoencoder(enc_cfg, dec_cfg, {})
+    edm = tq.LightningEDM(unet_cfg("latent2d"), {}, num_sampling_steps=4, autoencoder=ae)
+    return edm, dec_cfg
+
+
+def test_sampling_sigmas_match_reference_schedule():
+    g = golden("edm_heun4_latent")
+    assert torch.equal(torch_ref.sampling_sigmas(4), g["sigmas"])
+    import tqdne_b200 as tq
+
+    assert torch.equal(tq.EDM().sampling_sigmas(4), g["sigmas"])
+    s25 = tq.EDM().sampling_sigmas(25)
+    assert s25.dtype == torch.float32 and len(s25) == 26 and abs(float(s25[0]) - 80.0) < 1e-3 and s25[-1] == 0.0
+    assert abs(float(s25[-2]) - 0.002) < 1e-8
+
+
+def test_denoiser_and_heun_restatement():
+    edm, dec_cfg = _latent_edm()
+    g = golden("edm_denoiser")
+    sd = _sd(edm, g["seed"])
+    cfg = unet_cfg("latent2d")
+    with torch.no_grad():
+        D = torch_ref.denoise(sd, cfg, g["x"], g["sigma"], g["cond"])
+    assert rel_l2(D, g["D"]) < TOL
+    g = golden("edm_heun4_latent")
+    with torch.no_grad():
+        lat = torch_ref.heun_sample(sd, cfg, g["eps"], g["sigmas"], g["cond"])
+        dec = torch_ref.decoder_forward(sd, dec_cfg, lat.float(), prefix="autoencoder.decoder.")
+    assert lat.dtype == torch.float64
+    assert rel_l2(lat, g["latent"]) < 1e-4
+    assert rel_l2(dec, g["decoded"]) < 1e-4
+
+
+def test_reference_rng_draw_order_is_known():
+    """sample() draws randn_like(mean) (fp32) for the dummy encode, then the fp64 sampler noise (edm.py:155-160)."""
+    edm, dec_cfg = _latent_edm()
+    g = golden("edm_sample_seed1234")
+    sd = _sd(edm, g["seed"])
+    torch.manual_seed(int(g["torch_seed"]))
+    torch.randn((2, 8, 32, 32), dtype=torch.float32)
+    sig = torch_ref.sampling_sigmas(4)
+    eps = torch.randn((2, 8, 32, 32), dtype=torch.float64) * sig[0]
+    with torch.no_grad():
+        lat = torch_ref.heun_sample(sd, unet_cfg("latent2d"), eps, sig, g["cond"])
+        dec = torch_ref.decoder_forward(sd, dec_cfg, lat.float(), prefix="autoencoder.decoder.")
+    assert rel_l2(dec, g["decoded"]) < 1e-4
+
+
+def test_1d_heun_and_envelope_inverse():
+    import tqdne_b200 as tq
+
+    g = golden("edm_heun3_1d")
+    cfg = unet_cfg("1d")
+    edm = tq.LightningEDM(cfg, {}, num_sampling_steps=3)
+    sd = _sd(edm, g["seed"])
+    with torch.no_grad():
+        out = torch_ref.heun_sample(sd, cfg, g["eps"], g["sigmas"], g["cond"])
+    assert rel_l2(out, g["sample"]) < 1e-4
+    wave = torch_ref.mavg_envelope_inverse(g["sample"].float().numpy())
+    assert rel_l2(wave, g["waveform"]) < 1e-6
+    g = golden("mavg_inverse")
+    assert rel_l2(torch_ref.mavg_envelope_inverse(g["rep"].numpy()), g["wave"]) < 1e-7
+
+
+def test_stft_pair_pinned_against_torch():
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(4064)
+    S = griffinlim_ref.stft(y)
+    win = torch.hann_window(256, periodic=True, dtype=torch.float64)
+    St = torch.stft(torch.from_numpy(y), 256, 32, window=win, center=True, pad_mode="constant", return_complex=True)
+    assert S.shape == (129, 128)
+    assert np.abs(S - St.numpy()).max() < 1e-10
+    yi = griffinlim_ref.istft(S)
+    yt = torch.istft(St, 256, 32, window=win, center=True, length=4064).numpy()
+    assert np.abs(yi - yt).max() < 1e-12 and np.abs(yi - y).max() < 1e-12
+
+
+def test_logspec_inverse_wrapper_matches_reference_code():
+    """Reference un-normalise / exp / Nyquist / reshape code (representation.py:152-175) around the same GL."""
+    g = golden("logspec_inverse_iter8")
+    w = griffinlim_ref.logspec_inverse(g["rep"].numpy(), n_iter=int(g["n_iter"]), precision="fp64")
+    assert w.shape == (1, 3, 4064)
+    assert rel_l2(w, g["wave"]) < 1e-9
+
+
+def test_griffinlim_properties():
+    """Unpinned boundary: check what the domain offers -- GL keeps a consistent spectrogram fixed (up to phase)
+    and reduces spectral inconsistency; the kernel's FFT decomposition model equals numpy's rfft/irfft."""
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(256)
+    assert np.abs(griffinlim_ref.kernel_model_rfft256(x) - np.fft.rfft(x)).max() < 1e-12
+    X = np.fft.rfft(x) + 0j
+    X[0] += 0.3j
+    X[128] -= 0.2j
+    assert np.abs(griffinlim_ref.kernel_model_irfft256(X) - np.fft.irfft(X, n=256)).max() < 1e-12
+    y = rng.standard_normal(4064)
+    S = np.abs(griffinlim_ref.stft(y))
+
+    def inconsistency(wave):
+        return np.linalg.norm(np.abs(griffinlim_ref.stft(wave)) - S) / np.linalg.norm(S)
+
+    e4 = inconsistency(griffinlim_ref.griffinlim(S, n_iter=4))
+    e32 = inconsistency(griffinlim_ref.griffinlim(S, n_iter=32))
+    assert e32 < e4 < 1.0

@@ -1,0 +1,140 @@
+// tq_api.cu -- C-ABI glue: error state, launch accounting, the straight-line plan and its CUDA graph.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "tq_common.h"
+
+namespace tq {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            sms <= 0)
+            sms = 148;  // B200
+    }
+    return sms;
+}
+
+static void drop_graph(tq_plan* p) {
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    if (p->graph) cudaGraphDestroy(p->graph);
+    p->graph_exec = nullptr;
+    p->graph = nullptr;
+    p->graph_ops = 0;
+}
+
+static int run_ops(tq_plan* p, int first, int last, cudaStream_t st) {
+    for (int i = first; i < last; ++i) {
+        if (p->ops[i].launch(st)) return 1;
+    }
+    return 0;
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" {
+
+int tq_abi_version(void) { return TQ_ABI_VERSION; }
+const char* tq_last_error(void) { return g_err; }
+int64_t tq_launch_count(void) { return g_launches.load(); }
+void tq_launch_count_reset(void) { g_launches.store(0); }
+
+tq_plan* tq_plan_create(void) { return new tq_plan(); }
+void tq_plan_destroy(tq_plan* p) {
+    if (!p) return;
+    drop_graph(p);
+    delete p;
+}
+int tq_plan_num_ops(const tq_plan* p) { return p ? (int)p->ops.size() : 0; }
+const char* tq_plan_op_name(const tq_plan* p, int i) {
+    if (!p || i < 0 || i >= (int)p->ops.size()) return "";
+    return p->ops[i].name.c_str();
+}
+
+int tq_plan_run_range(tq_plan* p, int first, int last, void* stream) {
+    TQ_CHECK(p != nullptr, "plan is null");
+    const int n = (int)p->ops.size();
+    if (last < 0 || last > n) last = n;
+    TQ_CHECK(first >= 0 && first <= last, "bad op range");
+    return run_ops(p, first, last, static_cast<cudaStream_t>(stream));
+}
+
+int tq_plan_run(tq_plan* p, void* stream) {
+    TQ_CHECK(p != nullptr, "plan is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n = (int)p->ops.size();
+    if (!p->use_graph) return run_ops(p, 0, n, st);
+    if (p->graph_exec == nullptr || p->graph_ops != p->ops.size()) {
+        drop_graph(p);
+        // one eager pass first: cudaFuncSetAttribute calls are not capturable
+        if (run_ops(p, 0, n, st)) return 1;
+        TQ_CUDA(cudaStreamSynchronize(st));
+        TQ_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = g_launches.load();
+        const int rc = run_ops(p, 0, n, st);
+        cudaError_t e = cudaStreamEndCapture(st, &p->graph);
+        g_launches.store(before);  // captured launches did not execute
+        TQ_CHECK(rc == 0, "capture failed: %s", g_err);
+        TQ_CHECK(e == cudaSuccess, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        TQ_CUDA(cudaGraphInstantiate(&p->graph_exec, p->graph, 0));
+        p->graph_ops = p->ops.size();
+    }
+    TQ_CUDA(cudaGraphLaunch(p->graph_exec, st));
+    count_launch(n);
+    return 0;
+}
+
+int tq_plan_enable_graph(tq_plan* p, int enable) {
+    TQ_CHECK(p != nullptr, "plan is null");
+    p->use_graph = enable != 0;
+    if (!enable) drop_graph(p);
+    return 0;
+}
+
+int tq_plan_add_conv(tq_plan* p, const tq_conv_desc* d) {
+    TQ_CHECK(p && d, "null argument");
+    TQ_CHECK(d->slices != nullptr && d->weights != nullptr && d->out != nullptr, "conv: null pointer");
+    TQ_CHECK(d->N > 0 && d->H > 0 && d->W > 0, "conv: empty grid");
+    drop_graph(p);
+    const char* force = getenv("TQ_FORCE_SIMT");
+    if (d->dtype == TQ_BF16 && !(force && force[0] == '1')) return build_conv_sm100(p->ops, *d);
+    return build_conv_simt(p->ops, *d);
+}
+int tq_plan_add_groupnorm(tq_plan* p, const tq_gn_desc* d) {
+    TQ_CHECK(p && d, "null argument");
+    drop_graph(p);
+    return build_groupnorm(p->ops, *d);
+}
+int tq_plan_add_attention(tq_plan* p, const tq_attn_desc* d) {
+    TQ_CHECK(p && d, "null argument");
+    drop_graph(p);
+    return build_attention(p->ops, *d);
+}
+int tq_plan_add_linear(tq_plan* p, const tq_linear_desc* d) {
+    TQ_CHECK(p && d, "null argument");
+    drop_graph(p);
+    return build_linear(p->ops, *d);
+}
+int tq_plan_add_fourier(tq_plan* p, const float* t, const float* W, int32_t M, int32_t half, float* feat) {
+    TQ_CHECK(p != nullptr, "null argument");
+    drop_graph(p);
+    return build_fourier(p->ops, t, W, M, half, feat);
+}
+
+}  // extern "C"

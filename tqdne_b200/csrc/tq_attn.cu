@@ -1,0 +1,176 @@
+// tq_attn.cu -- attention core, channels-last, fp32 math with online softmax.
+// Reference: QKVAttention.forward (tqdne/blocks.py:156-190): q,k,v = qkv.chunk(3, dim=1), heads split
+// inside each third, w = softmax_fp32((q*s)^T (k*s)) with s = d^-1/4, a = w v.  No mask (use_causal_mask is
+// off in every shipped config, tqdne/architectures.py:35,76).
+//
+// One CTA = (sample, head, 16 queries); 4 warps x 4 queries.  K/V are staged in shared memory in
+// 64-key blocks (row pitch d+1 floats: conflict-free both for "lane = key" score dots and
+// "lane = channel" PV accumulation).  The latent config has T=16, d=128 (0.02 % of FLOPs); T=256/508
+// (pixel / 1D configs) run through the same kernel.
+#include <cuda_bf16.h>
+
+#include <memory>
+
+#include "tq_common.h"
+
+namespace tq {
+namespace {
+
+constexpr int QB = 16;   // queries per CTA
+constexpr int KBLK = 64;  // keys per smem block
+
+struct AttnParams {
+    const void* qkv;
+    void* out;
+    int N, T, heads, d;
+};
+
+__device__ __forceinline__ float ld_f(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_f(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_f(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_f(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename T, int D>
+__global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
+    extern __shared__ float sm[];
+    constexpr int PITCH = D + 1;
+    float* Ks = sm;                       // [KBLK][PITCH]
+    float* Vs = Ks + KBLK * PITCH;        // [KBLK][PITCH]
+    float* Qs = Vs + KBLK * PITCH;        // [QB][D]
+    float* Ps = Qs + QB * D;              // [4 warps][KBLK]
+    const int C = p.heads * D;
+    const int ld = 3 * C;
+    const int qblocks = (p.T + QB - 1) / QB;
+    const int qb = blockIdx.x % qblocks;
+    const int h = (blockIdx.x / qblocks) % p.heads;
+    const int n = blockIdx.x / (qblocks * p.heads);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float scale = 1.f / sqrtf(sqrtf((float)D));
+    const T* base = static_cast<const T*>(p.qkv) + (long long)n * p.T * ld + h * D;
+
+    for (int i = tid; i < QB * D; i += 128) {
+        const int qi = i / D, c = i % D;
+        const int t = qb * QB + qi;
+        Qs[i] = t < p.T ? ld_f(base + (long long)t * ld + c) * scale : 0.f;
+    }
+    constexpr int DPL = D / 32;  // channels per lane
+    float m_run[4], l_run[4], acc[4][DPL];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m_run[i] = -INFINITY;
+        l_run[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) acc[i][j] = 0.f;
+    }
+
+    for (int k0 = 0; k0 < p.T; k0 += KBLK) {
+        __syncthreads();
+        for (int i = tid; i < KBLK * D; i += 128) {
+            const int s = i / D, c = i % D;
+            const int t = k0 + s;
+            float kv = 0.f, vv = 0.f;
+            if (t < p.T) {
+                kv = ld_f(base + (long long)t * ld + C + c) * scale;
+                vv = ld_f(base + (long long)t * ld + 2 * C + c);
+            }
+            Ks[s * PITCH + c] = kv;
+            Vs[s * PITCH + c] = vv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) {
+            const float* q = Qs + (warp * 4 + qi) * D;
+            float sc[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int s = lane + 32 * j;
+                float a = 0.f;
+                const float* kr = Ks + s * PITCH;
+#pragma unroll 8
+                for (int c = 0; c < D; ++c) a = fmaf(q[c], kr[c], a);
+                sc[j] = (k0 + s < p.T) ? a : -INFINITY;
+            }
+            float bm = fmaxf(sc[0], sc[1]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+            const float m_new = fmaxf(m_run[qi], bm);
+            const float corr = expf(m_run[qi] - m_new);  // exp(-inf) = 0 on the first block
+            float ps = 0.f;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float e = expf(sc[j] - m_new);
+                Ps[warp * KBLK + lane + 32 * j] = e;
+                ps += e;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+            l_run[qi] = l_run[qi] * corr + ps;
+            m_run[qi] = m_new;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) acc[qi][j] *= corr;
+            const float* pw = Ps + warp * KBLK;
+#pragma unroll 4
+            for (int s = 0; s < KBLK; ++s) {
+                const float pv = pw[s];
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) acc[qi][j] = fmaf(pv, Vs[s * PITCH + lane + 32 * j], acc[qi][j]);
+            }
+            __syncwarp();
+        }
+    }
+    T* ob = static_cast<T*>(p.out) + (long long)n * p.T * C + h * D;
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+        const int t = qb * QB + warp * 4 + qi;
+        if (t >= p.T) continue;
+        const float inv = 1.f / l_run[qi];
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) st_f(ob + (long long)t * C + lane + 32 * j, acc[qi][j] * inv);
+    }
+}
+
+template <typename T, int D>
+int launch_attn(const AttnParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)(2 * KBLK * (D + 1) + QB * D + 4 * KBLK) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TQ_CUDA(cudaFuncSetAttribute(attention_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int qblocks = (p.T + QB - 1) / QB;
+    attention_kernel<T, D><<<p.N * p.heads * qblocks, 128, smem, st>>>(p);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace
+
+int build_attention(std::vector<Op>& ops, const tq_attn_desc& d) {
+    TQ_CHECK(d.dtype == TQ_BF16 || d.dtype == TQ_F32, "attention: bad dtype");
+    TQ_CHECK(d.d == 64 || d.d == 128 || d.d == 32, "attention: head dim must be 32, 64 or 128 (got %d)", d.d);
+    TQ_CHECK(d.N > 0 && d.T > 0 && d.heads > 0 && d.qkv && d.out, "attention: bad arguments");
+    auto p = std::make_shared<AttnParams>();
+    p->qkv = d.qkv; p->out = d.out; p->N = d.N; p->T = d.T; p->heads = d.heads; p->d = d.d;
+    const bool f32 = d.dtype == TQ_F32;
+    const int dd = d.d;
+    Op op;
+    char nm[64];
+    snprintf(nm, sizeof nm, "attention<%s,d=%d> T=%d", f32 ? "f32" : "bf16", dd, d.T);
+    op.name = nm;
+    op.launch = [p, f32, dd](cudaStream_t st) -> int {
+        if (f32) {
+            if (dd == 128) return launch_attn<float, 128>(*p, st);
+            if (dd == 64) return launch_attn<float, 64>(*p, st);
+            return launch_attn<float, 32>(*p, st);
+        }
+        if (dd == 128) return launch_attn<__nv_bfloat16, 128>(*p, st);
+        if (dd == 64) return launch_attn<__nv_bfloat16, 64>(*p, st);
+        return launch_attn<__nv_bfloat16, 32>(*p, st);
+    };
+    ops.push_back(std::move(op));
+    return 0;
+}
+
+}  // namespace tq

@@ -1,0 +1,59 @@
+// tq_common.h -- host-side internals shared by the translation units of libtqdne_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../include/tqdne_b200.h"
+
+namespace tq {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define TQ_CHECK(cond, ...)          \
+    do {                             \
+        if (!(cond)) {               \
+            tq::set_error(__VA_ARGS__); \
+            return 1;                \
+        }                            \
+    } while (0)
+
+#define TQ_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            tq::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+struct Op {
+    std::string name;
+    std::function<int(cudaStream_t)> launch;
+};
+
+int device_sm_count();
+
+// builders implemented in the kernel translation units; each appends >= 1 Op
+int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d);
+int build_conv_simt(std::vector<Op>& ops, const tq_conv_desc& d);
+int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d);
+int build_attention(std::vector<Op>& ops, const tq_attn_desc& d);
+int build_linear(std::vector<Op>& ops, const tq_linear_desc& d);
+int build_fourier(std::vector<Op>& ops, const float* t, const float* W, int M, int half, float* feat);
+
+}  // namespace tq
+
+struct tq_plan {
+    std::vector<tq::Op> ops;
+    bool use_graph = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    size_t graph_ops = 0;
+};

@@ -1,0 +1,373 @@
+// tq_elementwise.cu -- the small fp32 pieces around the denoiser: embedding MLPs, Fourier features,
+// EDM preconditioning + Heun/Euler state update (fp64 state like the reference), layout changes and the
+// moving-average-envelope inverse.  All HBM / latency bound, vectorised where the shapes allow.
+#include <cuda_bf16.h>
+
+#include <memory>
+
+#include "tq_common.h"
+
+namespace tq {
+namespace {
+
+__device__ __forceinline__ float silu_acc(float v) { return v / (1.f + expf(-v)); }
+
+// ---------------------------------------------------------------------------------------------------
+// y[m][j] = sum_k act_in(x[m][k]) W[j][k] + b[j] (+ add[m or 0][j]);  y_act = SiLU(y) in fp32 / bf16
+// Reference: nn.Linear + nn.SiLU of time_mlp / cond_mlp (tqdne/unet.py:210-227), applied as
+// emb = time_mlp(time_embed(t)); emb += cond_mlp(cond) (unet.py:383-388); SiLU of emb_layers (unet.py:92).
+struct LinParams {
+    int M, K, Nout, x_rows;
+    const float* x;
+    const float* W;
+    const float* b;
+    int act_in;
+    const float* add;
+    int add_rows;
+    float* y;
+    void* y_act;
+    int y_act_dtype;
+};
+
+__global__ void __launch_bounds__(256) linear_kernel(const LinParams p) {
+    const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)p.M * p.Nout;
+    if (warp_global >= total) return;
+    const int m = warp_global / p.Nout, j = warp_global % p.Nout;
+    const float* xr = p.x + (long long)(p.x_rows == 1 ? 0 : m) * p.K;
+    const float* wr = p.W + (long long)j * p.K;
+    float a = 0.f;
+    for (int k = lane; k < p.K; k += 32) {
+        float xv = xr[k];
+        if (p.act_in) xv = silu_acc(xv);
+        a = fmaf(xv, __ldg(wr + k), a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+        if (p.b) a += p.b[j];
+        if (p.add) a += p.add[(long long)(p.add_rows == 1 ? 0 : m) * p.Nout + j];
+        const long long o = (long long)m * p.Nout + j;
+        if (p.y) p.y[o] = a;
+        if (p.y_act) {
+            const float s = silu_acc(a);
+            if (p.y_act_dtype == TQ_F32) static_cast<float*>(p.y_act)[o] = s;
+            else static_cast<__nv_bfloat16*>(p.y_act)[o] = __float2bfloat16_rn(s);
+        }
+    }
+}
+
+// Reference: GaussianFourierProjection.forward (tqdne/blocks.py:22-26): h = x[:,None]*W[None,:]*2*pi;
+// cat([sin h, cos h]).
+__global__ void fourier_kernel(const float* t, const float* W, int M, int half, float* feat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * half) return;
+    const int m = i / half, k = i % half;
+    const float h = t[m] * W[k] * 2.f * 3.14159265358979323846f;
+    feat[(long long)m * 2 * half + k] = sinf(h);
+    feat[(long long)m * 2 * half + half + k] = cosf(h);
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void st_as(T* p, float v);
+template <>
+__device__ __forceinline__ void st_as<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_as<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// Reference: LightningEDM.forward (tqdne/edm.py:105-113): sample_in = sample.to(fp32) * c_in(sigma)
+template <typename T>
+__global__ void precondition_kernel(const double* x, T* xin, long long NP, int C, int Cpad, float c_in) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP * Cpad) return;
+    const long long r = i / Cpad;
+    const int c = (int)(i % Cpad);
+    const float v = c < C ? (float)x[r * C + c] * c_in : 0.f;
+    st_as<T>(xin + i, v);
+}
+
+// Reference: Heun step 1 (tqdne/edm.py:176-183) with the denoiser post-scaling folded in
+// (edm.py:111-113): D = F*c_out + c_skip*x32;  d = (x - D)/sigma;  x1 = x + d*dt  (fp64 like the reference)
+template <typename T>
+__global__ void euler_kernel(const double* x, const float* F, int Cf, double* d, double* x1, T* xin, long long NP, int C,
+                             int Cpad, float c_out, float c_skip, float sigma, float dt, float c_in_next, int write_xin) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP * Cpad) return;
+    const long long r = i / Cpad;
+    const int c = (int)(i % Cpad);
+    if (c >= C) {
+        if (write_xin) st_as<T>(xin + i, 0.f);
+        return;
+    }
+    const double xv = x[r * C + c];
+    const float x32 = (float)xv;
+    const float D = F[r * Cf + c] * c_out + c_skip * x32;
+    const double dv = (xv - (double)D) / (double)sigma;
+    const double xn = xv + dv * (double)dt;
+    if (d) d[r * C + c] = dv;
+    x1[r * C + c] = xn;
+    if (write_xin) st_as<T>(xin + i, (float)xn * c_in_next);
+}
+
+// Reference: Heun 2nd-order correction (tqdne/edm.py:186-194):
+// d' = (x1 - D')/sigma';  x = x + dt*(0.5 d + 0.5 d')
+template <typename T>
+__global__ void heun_kernel(double* x, const double* x1, const double* d, const float* F, int Cf, T* xin, long long NP,
+                            int C, int Cpad, float c_out, float c_skip, float sigma_next, float dt, float c_in_next,
+                            int write_xin) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP * Cpad) return;
+    const long long r = i / Cpad;
+    const int c = (int)(i % Cpad);
+    if (c >= C) {
+        if (write_xin) st_as<T>(xin + i, 0.f);
+        return;
+    }
+    const double x1v = x1[r * C + c];
+    const float x32 = (float)x1v;
+    const float D = F[r * Cf + c] * c_out + c_skip * x32;
+    const double dp = (x1v - (double)D) / (double)sigma_next;
+    const double xn = x[r * C + c] + (double)dt * (0.5 * d[r * C + c] + 0.5 * dp);
+    x[r * C + c] = xn;
+    if (write_xin) st_as<T>(xin + i, (float)xn * c_in_next);
+}
+
+__global__ void add_noise_kernel(double* x, const double* noise, double scale, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += noise[i] * scale;
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename TI>
+__device__ __forceinline__ double ld_d(const TI* p);
+template <> __device__ __forceinline__ double ld_d<double>(const double* p) { return *p; }
+template <> __device__ __forceinline__ double ld_d<float>(const float* p) { return (double)*p; }
+template <> __device__ __forceinline__ double ld_d<__nv_bfloat16>(const __nv_bfloat16* p) { return (double)__bfloat162float(*p); }
+template <typename TO>
+__device__ __forceinline__ void st_d(TO* p, double v);
+template <> __device__ __forceinline__ void st_d<double>(double* p, double v) { *p = v; }
+template <> __device__ __forceinline__ void st_d<float>(float* p, double v) { *p = (float)v; }
+template <> __device__ __forceinline__ void st_d<__nv_bfloat16>(__nv_bfloat16* p, double v) { *p = __float2bfloat16_rn((float)v); }
+
+// [N,C,P] -> [N,P,Cpad]: 32x32 smem transpose tiles over (c, p)
+template <typename TI, typename TO>
+__global__ void nchw_to_nhwc_kernel(const TI* src, TO* dst, int C, long long P, int Cpad) {
+    __shared__ double tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j;
+        const long long pp = p0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < C && pp < P) ? ld_d<TI>(src + ((long long)n * C + c) * P + pp) : 0.0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const long long pp = p0 + j;
+        const int c = c0 + threadIdx.x;
+        if (pp < P && c < Cpad) st_d<TO>(dst + ((long long)n * P + pp) * Cpad + c, tile[threadIdx.x][j]);
+    }
+}
+// [N,P,Cld] (first C channels) -> [N,C,P]
+template <typename TI, typename TO>
+__global__ void nhwc_to_nchw_kernel(const TI* src, int Cld, TO* dst, int C, long long P) {
+    __shared__ double tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const long long pp = p0 + j;
+        const int c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < C && pp < P) ? ld_d<TI>(src + ((long long)n * P + pp) * Cld + c) : 0.0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j;
+        const long long pp = p0 + threadIdx.x;
+        if (c < C && pp < P) st_d<TO>(dst + ((long long)n * C + c) * P + pp, tile[threadIdx.x][j]);
+    }
+}
+
+// Reference: MovingAverageEnvelope.invert_representation (tqdne/representation.py:57-60)
+__global__ void mavg_inverse_kernel(const float* rep, float* wave, int Cw, long long L, long long total, double half_log_eps,
+                                    double eps) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long l = i % L;
+    const long long r = i / L;
+    const int c = (int)(r % Cw);
+    const long long n = r / Cw;
+    const double sw = rep[(n * 2 * Cw + c) * L + l];
+    const double le = rep[(n * 2 * Cw + Cw + c) * L + l];
+    wave[i] = (float)(sw * (exp(le + half_log_eps) + eps));
+}
+
+inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+int build_linear(std::vector<Op>& ops, const tq_linear_desc& d) {
+    TQ_CHECK(d.M > 0 && d.K > 0 && d.Nout > 0 && d.x && d.W, "linear: bad arguments");
+    TQ_CHECK(d.x_rows == 1 || d.x_rows == d.M, "linear: x_rows must be 1 or M");
+    TQ_CHECK(!d.add || d.add_rows == 1 || d.add_rows == d.M, "linear: add_rows must be 1 or M");
+    auto p = std::make_shared<LinParams>();
+    p->M = d.M; p->K = d.K; p->Nout = d.Nout; p->x_rows = d.x_rows; p->x = d.x; p->W = d.W; p->b = d.b;
+    p->act_in = d.act_in; p->add = d.add; p->add_rows = d.add_rows; p->y = d.y;
+    p->y_act = d.y_act; p->y_act_dtype = d.y_act_dtype;
+    TQ_CHECK(!d.y_act || d.y_act_dtype == TQ_F32 || d.y_act_dtype == TQ_BF16, "linear: bad y_act_dtype");
+    Op op;
+    op.name = "linear_f32";
+    op.launch = [p](cudaStream_t st) -> int {
+        const long long warps = (long long)p->M * p->Nout;
+        linear_kernel<<<blocks_for(warps * 32, 256), 256, 0, st>>>(*p);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    };
+    ops.push_back(std::move(op));
+    return 0;
+}
+
+int build_fourier(std::vector<Op>& ops, const float* t, const float* W, int M, int half, float* feat) {
+    TQ_CHECK(t && W && feat && M > 0 && half > 0, "fourier: bad arguments");
+    Op op;
+    op.name = "fourier_features";
+    op.launch = [=](cudaStream_t st) -> int {
+        fourier_kernel<<<blocks_for((long long)M * half, 128), 128, 0, st>>>(t, W, M, half, feat);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    };
+    ops.push_back(std::move(op));
+    return 0;
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_edm_precondition(const double* x, void* xin, int32_t dtype, int64_t NP, int32_t C, int32_t Cpad,
+                                   float c_in, void* stream) {
+    TQ_CHECK(x && xin && NP > 0 && C > 0 && Cpad >= C, "edm_precondition: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned g = blocks_for(NP * Cpad, 256);
+    if (dtype == TQ_F32) precondition_kernel<float><<<g, 256, 0, st>>>(x, static_cast<float*>(xin), NP, C, Cpad, c_in);
+    else if (dtype == TQ_BF16)
+        precondition_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(xin), NP, C, Cpad, c_in);
+    else TQ_CHECK(false, "edm_precondition: bad dtype");
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int tq_edm_euler(const double* x, const float* F, int32_t Cf, double* d, double* x1, void* xin, int32_t dtype,
+                            int64_t NP, int32_t C, int32_t Cpad, float c_out, float c_skip, float sigma, float dt,
+                            float c_in_next, int32_t write_xin, void* stream) {
+    TQ_CHECK(x && F && x1 && NP > 0 && C > 0 && Cpad >= C && Cf >= C, "edm_euler: bad arguments");
+    TQ_CHECK(!write_xin || xin, "edm_euler: xin missing");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned g = blocks_for(NP * Cpad, 256);
+    if (dtype == TQ_F32)
+        euler_kernel<float><<<g, 256, 0, st>>>(x, F, Cf, d, x1, static_cast<float*>(xin), NP, C, Cpad, c_out, c_skip, sigma,
+                                               dt, c_in_next, write_xin);
+    else if (dtype == TQ_BF16)
+        euler_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, F, Cf, d, x1, static_cast<__nv_bfloat16*>(xin), NP, C, Cpad, c_out,
+                                                       c_skip, sigma, dt, c_in_next, write_xin);
+    else TQ_CHECK(false, "edm_euler: bad dtype");
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int tq_edm_heun(double* x, const double* x1, const double* d, const float* F, int32_t Cf, void* xin,
+                           int32_t dtype, int64_t NP, int32_t C, int32_t Cpad, float c_out, float c_skip, float sigma_next,
+                           float dt, float c_in_next, int32_t write_xin, void* stream) {
+    TQ_CHECK(x && x1 && d && F && NP > 0 && C > 0 && Cpad >= C && Cf >= C, "edm_heun: bad arguments");
+    TQ_CHECK(!write_xin || xin, "edm_heun: xin missing");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned g = blocks_for(NP * Cpad, 256);
+    if (dtype == TQ_F32)
+        heun_kernel<float><<<g, 256, 0, st>>>(x, x1, d, F, Cf, static_cast<float*>(xin), NP, C, Cpad, c_out, c_skip,
+                                              sigma_next, dt, c_in_next, write_xin);
+    else if (dtype == TQ_BF16)
+        heun_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, x1, d, F, Cf, static_cast<__nv_bfloat16*>(xin), NP, C, Cpad, c_out,
+                                                      c_skip, sigma_next, dt, c_in_next, write_xin);
+    else TQ_CHECK(false, "edm_heun: bad dtype");
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int tq_edm_add_noise(double* x, const double* noise, double scale, int64_t n, void* stream) {
+    TQ_CHECK(x && noise && n > 0, "edm_add_noise: bad arguments");
+    add_noise_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, noise, scale, n);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+namespace {
+template <typename TI>
+int launch_to_nhwc(const void* src, void* dst, int dtype_out, int N, int C, long long P, int Cpad, cudaStream_t st) {
+    dim3 grid(blocks_for(P, 32), (Cpad + 31) / 32, N), block(32, 8);
+    if (dtype_out == TQ_BF16)
+        nchw_to_nhwc_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const TI*>(src), static_cast<__nv_bfloat16*>(dst), C, P, Cpad);
+    else if (dtype_out == TQ_F32)
+        nchw_to_nhwc_kernel<TI, float><<<grid, block, 0, st>>>(static_cast<const TI*>(src), static_cast<float*>(dst), C, P, Cpad);
+    else if (dtype_out == TQ_F64)
+        nchw_to_nhwc_kernel<TI, double><<<grid, block, 0, st>>>(static_cast<const TI*>(src), static_cast<double*>(dst), C, P, Cpad);
+    else TQ_CHECK(false, "nchw_to_nhwc: bad dtype_out");
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+template <typename TI>
+int launch_to_nchw(const void* src, int Cld, void* dst, int dtype_out, int N, int C, long long P, cudaStream_t st) {
+    dim3 grid(blocks_for(P, 32), (C + 31) / 32, N), block(32, 8);
+    if (dtype_out == TQ_BF16)
+        nhwc_to_nchw_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const TI*>(src), Cld, static_cast<__nv_bfloat16*>(dst), C, P);
+    else if (dtype_out == TQ_F32)
+        nhwc_to_nchw_kernel<TI, float><<<grid, block, 0, st>>>(static_cast<const TI*>(src), Cld, static_cast<float*>(dst), C, P);
+    else if (dtype_out == TQ_F64)
+        nhwc_to_nchw_kernel<TI, double><<<grid, block, 0, st>>>(static_cast<const TI*>(src), Cld, static_cast<double*>(dst), C, P);
+    else TQ_CHECK(false, "nhwc_to_nchw: bad dtype_out");
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+}  // namespace
+
+extern "C" int tq_nchw_to_nhwc(const void* src, int32_t dtype_in, void* dst, int32_t dtype_out, int32_t N, int32_t C,
+                               int64_t P, int32_t Cpad, void* stream) {
+    TQ_CHECK(src && dst && N > 0 && C > 0 && P > 0 && Cpad >= C, "nchw_to_nhwc: bad arguments");
+    TQ_CHECK(N <= 65535, "nchw_to_nhwc: batch too large for one launch");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype_in == TQ_F64) return launch_to_nhwc<double>(src, dst, dtype_out, N, C, P, Cpad, st);
+    if (dtype_in == TQ_F32) return launch_to_nhwc<float>(src, dst, dtype_out, N, C, P, Cpad, st);
+    if (dtype_in == TQ_BF16) return launch_to_nhwc<__nv_bfloat16>(src, dst, dtype_out, N, C, P, Cpad, st);
+    TQ_CHECK(false, "nchw_to_nhwc: bad dtype_in");
+}
+
+extern "C" int tq_nhwc_to_nchw(const void* src, int32_t dtype_in, int32_t Cld, void* dst, int32_t dtype_out, int32_t N,
+                               int32_t C, int64_t P, void* stream) {
+    TQ_CHECK(src && dst && N > 0 && C > 0 && P > 0 && Cld >= C, "nhwc_to_nchw: bad arguments");
+    TQ_CHECK(N <= 65535, "nhwc_to_nchw: batch too large for one launch");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype_in == TQ_F64) return launch_to_nchw<double>(src, Cld, dst, dtype_out, N, C, P, st);
+    if (dtype_in == TQ_F32) return launch_to_nchw<float>(src, Cld, dst, dtype_out, N, C, P, st);
+    if (dtype_in == TQ_BF16) return launch_to_nchw<__nv_bfloat16>(src, Cld, dst, dtype_out, N, C, P, st);
+    TQ_CHECK(false, "nhwc_to_nchw: bad dtype_in");
+}
+
+extern "C" int tq_mavg_envelope_inverse(const float* rep, float* wave, int32_t N, int32_t Cw, int64_t L, double log_eps,
+                                        double eps, void* stream) {
+    TQ_CHECK(rep && wave && N > 0 && Cw > 0 && L > 0, "mavg_envelope_inverse: bad arguments");
+    const long long total = (long long)N * Cw * L;
+    mavg_inverse_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rep, wave, Cw, L, total,
+                                                                                              log(log_eps) / 2.0, eps);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}

@@ -1,0 +1,267 @@
+// tq_griffinlim.cu -- batched log-spectrogram inverse: un-normalise, exp, append the zero Nyquist row,
+// then fast Griffin-Lim (momentum 0.99) phase reconstruction, all iterations in ONE launch.
+//
+// Reference: LogSpectrogram.invert_representation / invert_spectrogram (tqdne/representation.py:152-175)
+// calling librosa 0.11 griffinlim(S, n_iter=128, hop_length=32, n_fft=256, random_state=0)
+// (representation.py:103-108).  librosa is a third-party dependency absent from /root/reference; the
+// algorithm restated here (and in oracle/griffinlim_ref.py) is its published one:
+//     angles = S * exp(i*phase0)
+//     repeat n_iter: y = istft(angles); R = stft(y); a = R - m/(1+m) * R_prev;
+//                    angles = S * a / (|a| + tiny);  R_prev = R
+//     return istft(angles)
+// stft/istft: n_fft = win = 256, hop 32, periodic Hann, center=True with zero padding, irfft * window
+// overlap-add divided by the window sum-of-squares where it exceeds tiny, 128 samples trimmed per side.
+//
+// One CTA (16 warps) owns one (sample, component) item for the whole reconstruction.  The padded signal
+// (4320 samples) and the per-warp FFT buffers live in shared memory; a frame's real 256-point transform is
+// a 128-point complex radix-2 FFT held by one warp plus the usual even/odd split.  The overlap-add runs in
+// 8 barrier-separated groups of non-overlapping frames (t mod 8), so the summation order is fixed and no
+// atomics are needed.  The complex spectra (angles, R_prev) and S stream through L2.
+#include <math_constants.h>
+
+#include "tq_common.h"
+
+namespace tq {
+namespace {
+
+constexpr int NFFT = 256;
+constexpr int HOP = 32;
+constexpr int NBIN = NFFT / 2 + 1;  // 129
+constexpr int GL_THREADS = 512;
+constexpr int GL_WARPS = GL_THREADS / 32;
+
+template <typename R>
+struct alignas(2 * sizeof(R)) Cx {
+    R x, y;
+};
+
+struct GlParams {
+    const float* rep;      // [items][128][frames]
+    const double* phase0;  // [129][frames]
+    void* wave;            // [items][hop*(frames-1)]  (float or double = R)
+    void* ws;
+    int items, frames, n_iter;
+    double log_clip, log_max, mom;  // mom = momentum / (1 + momentum)
+};
+
+template <typename R> __device__ __forceinline__ R r_tiny();
+template <> __device__ __forceinline__ float r_tiny<float>() { return 1.17549435e-38f; }
+template <> __device__ __forceinline__ double r_tiny<double>() { return 2.2250738585072014e-308; }
+__device__ __forceinline__ float r_hypot(float a, float b) { return hypotf(a, b); }
+__device__ __forceinline__ double r_hypot(double a, double b) { return hypot(a, b); }
+
+__device__ __forceinline__ int bitrev7(int v) { return (int)(__brev((unsigned)v) >> 25); }
+
+// in-place 128-point complex FFT, decimation in time: input bit-reversed, output natural order
+template <typename R, bool INV>
+__device__ __forceinline__ void fft128(Cx<R>* b, const Cx<R>* tw, int lane) {
+#pragma unroll
+    for (int s = 1; s <= 7; ++s) {
+        const int half = 1 << (s - 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int j = lane + 32 * i;
+            const int pos = j & (half - 1);
+            const int i0 = ((j >> (s - 1)) << s) + pos;
+            const int i1 = i0 + half;
+            Cx<R> w = tw[pos << (7 - s)];
+            if (INV) w.y = -w.y;
+            const Cx<R> v = b[i1];
+            const Cx<R> u = b[i0];
+            const R tr = w.x * v.x - w.y * v.y;
+            const R ti = w.x * v.y + w.y * v.x;
+            b[i0] = Cx<R>{u.x + tr, u.y + ti};
+            b[i1] = Cx<R>{u.x - tr, u.y - ti};
+        }
+        __syncwarp();
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(GL_THREADS) griffinlim_kernel(const GlParams p) {
+    extern __shared__ __align__(16) unsigned char gl_smem[];
+    const int frames = p.frames;
+    const int len = NFFT + HOP * (frames - 1);  // padded signal length
+    R* ypad = reinterpret_cast<R*>(gl_smem);
+    R* win = ypad + ((len + 3) & ~3);
+    Cx<R>* tw128 = reinterpret_cast<Cx<R>*>(win + NFFT);
+    Cx<R>* tw256 = tw128 + 64;
+    Cx<R>* bufs = tw256 + 132;
+
+    const int item = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Cx<R>* buf = bufs + warp * 128;
+
+    const size_t per_item = (size_t)frames * NBIN;
+    R* S = static_cast<R*>(p.ws) + (size_t)item * per_item * 5;
+    Cx<R>* A = reinterpret_cast<Cx<R>*>(S + per_item);
+    Cx<R>* Tp = A + per_item;
+
+    for (int i = tid; i < NFFT; i += GL_THREADS) win[i] = (R)(0.5 - 0.5 * cospi(2.0 * i / NFFT));
+    for (int i = tid; i < 64; i += GL_THREADS) {
+        double s, c;
+        sincospi(-2.0 * i / 128.0, &s, &c);
+        tw128[i] = Cx<R>{(R)c, (R)s};
+    }
+    for (int i = tid; i <= 128; i += GL_THREADS) {
+        double s, c;
+        sincospi(-2.0 * i / 256.0, &s, &c);
+        tw256[i] = Cx<R>{(R)c, (R)s};
+    }
+    // S = exp(((rep + 1) / 2) * (log_max - log_clip) + log_clip), Nyquist row = 0; angles = S * exp(i phase0)
+    const float* rep = p.rep + (size_t)item * 128 * frames;
+    for (int idx = tid; idx < frames * NBIN; idx += GL_THREADS) {
+        const int f = idx / frames, t = idx % frames;  // coalesced read of rep[f][t]
+        R sv = 0;
+        if (f < 128) {
+            const float nls = (rep[(size_t)f * frames + t] + 1.f) / 2.f;  // float32 like the reference input
+            sv = (R)exp((double)nls * (p.log_max - p.log_clip) + p.log_clip);
+        }
+        double sn, cs;
+        sincos(p.phase0[(size_t)f * frames + t], &sn, &cs);
+        S[(size_t)t * NBIN + f] = sv;
+        A[(size_t)t * NBIN + f] = Cx<R>{(R)((double)sv * cs), (R)((double)sv * sn)};
+    }
+    __syncthreads();
+
+    const R mom = (R)p.mom;
+    const R inv_n = (R)(1.0 / 128.0);
+    for (int it = 0; it <= p.n_iter; ++it) {
+        for (int i = tid; i < len; i += GL_THREADS) ypad[i] = 0;
+        __syncthreads();
+        // ---------------- istft: irfft each frame, window, overlap-add (8 groups of disjoint frames)
+        for (int g = 0; g < 8; ++g) {
+            for (int t = g + 8 * warp; t < frames; t += 8 * GL_WARPS) {
+                const Cx<R>* At = A + (size_t)t * NBIN;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = lane + 32 * i;
+                    Cx<R> xk = At[k];
+                    Cx<R> xn = At[128 - k];
+                    if (k == 0) {  // c2r transforms ignore the imaginary parts of DC and Nyquist
+                        xk.y = 0;
+                        xn.y = 0;
+                    }
+                    const R er = (R)0.5 * (xk.x + xn.x), ei = (R)0.5 * (xk.y - xn.y);
+                    const R dr = (R)0.5 * (xk.x - xn.x), di = (R)0.5 * (xk.y + xn.y);
+                    const R c = tw256[k].x, s = -tw256[k].y;  // e^{+2 pi i k / 256}
+                    const R orr = dr * c - di * s, oi = dr * s + di * c;
+                    buf[bitrev7(k)] = Cx<R>{er - oi, ei + orr};
+                }
+                __syncwarp();
+                fft128<R, true>(buf, tw128, lane);
+                R* yt = ypad + HOP * t;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int n = lane + 32 * i;
+                    const Cx<R> z = buf[n];
+                    yt[2 * n] += win[2 * n] * (z.x * inv_n);
+                    yt[2 * n + 1] += win[2 * n + 1] * (z.y * inv_n);
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+        }
+        // ---------------- divide by the window sum of squares; samples outside [128, len-128) are the
+        // centre padding: discarded by istft's trim and zero for the next stft
+        for (int n = tid; n < len; n += GL_THREADS) {
+            R v = 0;
+            if (n >= NFFT / 2 && n < len - NFFT / 2) {
+                R wss = 0;
+                const int r = n & (HOP - 1);
+#pragma unroll
+                for (int j = 0; j < NFFT / HOP; ++j) {
+                    const int o = r + HOP * j;       // offset inside a frame
+                    const int t = (n - o) / HOP;     // exact: n - o is a multiple of HOP
+                    if (n - o >= 0 && t < frames) wss += win[o] * win[o];
+                }
+                v = ypad[n];
+                if (wss > r_tiny<R>()) v /= wss;
+            }
+            ypad[n] = v;
+        }
+        __syncthreads();
+        if (it == p.n_iter) break;
+        // ---------------- stft + fast Griffin-Lim phase update
+        for (int t = warp; t < frames; t += GL_WARPS) {
+            const R* yt = ypad + HOP * t;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int n = lane + 32 * i;
+                buf[bitrev7(n)] = Cx<R>{yt[2 * n] * win[2 * n], yt[2 * n + 1] * win[2 * n + 1]};
+            }
+            __syncwarp();
+            fft128<R, false>(buf, tw128, lane);
+            const size_t row = (size_t)t * NBIN;
+            for (int k = lane; k <= 128; k += 32) {
+                const Cx<R> zk = buf[k & 127];
+                const Cx<R> zn = buf[(128 - k) & 127];
+                const R er = (R)0.5 * (zk.x + zn.x), ei = (R)0.5 * (zk.y - zn.y);
+                const R dr = (R)0.5 * (zk.x - zn.x), di = (R)0.5 * (zk.y + zn.y);
+                const R c = tw256[k].x, s = tw256[k].y;  // e^{-2 pi i k / 256}
+                // X = Xe + tw * Xo,  Xo = -i * (dr + i di) = di - i dr
+                const R xr = er + (di * c + dr * s);
+                const R xi = ei + (di * s - dr * c);
+                R ar = xr, ai = xi;
+                if (it > 0) {
+                    const Cx<R> tp = Tp[row + k];
+                    ar -= mom * tp.x;
+                    ai -= mom * tp.y;
+                }
+                const R den = r_hypot(ar, ai) + r_tiny<R>();
+                const R sv = S[row + k];
+                A[row + k] = Cx<R>{ar / den * sv, ai / den * sv};
+                Tp[row + k] = Cx<R>{xr, xi};
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    const int out_len = HOP * (frames - 1);
+    R* w = static_cast<R*>(p.wave) + (size_t)item * out_len;
+    for (int n = tid; n < out_len; n += GL_THREADS) w[n] = ypad[n + NFFT / 2];
+}
+
+template <typename R>
+size_t gl_smem_bytes(int frames) {
+    const int len = NFFT + HOP * (frames - 1);
+    return sizeof(R) * (((len + 3) & ~3) + NFFT) + sizeof(Cx<R>) * (64 + 132 + GL_WARPS * 128);
+}
+
+}  // namespace
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int64_t tq_griffinlim_ws_bytes(int32_t items, int32_t n_fft, int32_t frames, int32_t precision) {
+    if (items <= 0 || frames <= 0 || n_fft != NFFT) return -1;
+    const int64_t el = precision == TQ_F64 ? 8 : 4;
+    return (int64_t)items * frames * NBIN * 5 * el;
+}
+
+extern "C" int tq_logspec_griffinlim(const float* rep, const double* phase0, void* wave, int32_t items, int32_t n_fft,
+                                     int32_t hop, int32_t frames, int32_t n_iter, double log_clip, double log_max,
+                                     double momentum, int32_t precision, void* ws, void* stream) {
+    TQ_CHECK(n_fft == NFFT && hop == HOP, "griffinlim: only n_fft=256, hop=32 is built (reference SpectrogramConfig)");
+    TQ_CHECK(rep && phase0 && wave && ws && items > 0 && frames > 0 && n_iter >= 0, "griffinlim: bad arguments");
+    TQ_CHECK(frames % 2 == 0, "griffinlim: the frame count must be even");
+    TQ_CHECK(precision == TQ_F32 || precision == TQ_F64, "griffinlim: precision must be TQ_F32 or TQ_F64");
+    GlParams p;
+    p.rep = rep; p.phase0 = phase0; p.wave = wave; p.ws = ws; p.items = items; p.frames = frames; p.n_iter = n_iter;
+    p.log_clip = log_clip; p.log_max = log_max; p.mom = momentum / (1.0 + momentum);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (precision == TQ_F32) {
+        const size_t smem = gl_smem_bytes<float>(frames);
+        TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");
+        TQ_CUDA(cudaFuncSetAttribute(griffinlim_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        griffinlim_kernel<float><<<items, GL_THREADS, smem, st>>>(p);
+    } else {
+        const size_t smem = gl_smem_bytes<double>(frames);
+        TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");
+        TQ_CUDA(cudaFuncSetAttribute(griffinlim_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        griffinlim_kernel<double><<<items, GL_THREADS, smem, st>>>(p);
+    }
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}

@@ -1,0 +1,230 @@
+// tq_norm.cu -- GroupNorm(32 groups) [+ SiLU] over a virtual channel concat, channels-last.
+// Reference: GroupNorm32 / normalization (tqdne/nn.py:11-13,90-105: nn.GroupNorm(32, C), eps 1e-5,
+// computed in fp32) followed by nn.SiLU (tqdne/unet.py:85-88,100-103), input optionally
+// th.cat([h, skip], dim=1) (tqdne/unet.py:396) -- the concat is never materialised before the norm.
+//
+// HBM-bound, two launches: (1) per-(sample, channel) sum / sum-of-squares with 16 B vector loads,
+// block-level reduction and one fp32 atomic per channel per block; (2) affine + SiLU streaming pass.
+// Per-channel partials make groups that straddle the concat boundary (C = 768, 384, 192) free.
+#include <cuda_bf16.h>
+
+#include <memory>
+
+#include "tq_common.h"
+
+namespace tq {
+namespace {
+
+struct GnParams {
+    const void* x0;
+    const void* x1;
+    int N, P, C0, C1;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    int silu;
+    void* y;
+    float* ws;  // [N][C0+C1][2]
+    int chunks;
+};
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        v[2 * k] = __low2float(b2);
+        v[2 * k + 1] = __high2float(b2);
+    }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        w[k] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <typename T>
+__device__ void stats_one_source(const T* x, int C, int P, int n, int chunk, int chunks, float* ws_nc, float* red) {
+    const int cv = C >> 3;            // 8-channel vectors per position
+    const int lanes = 256 / cv;       // position lanes
+    const int tid = threadIdx.x;
+    const int vi = tid % cv, pl = tid / cv;
+    const int per = (P + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(P, p0 + per);
+    float s[8] = {}, ss[8] = {};
+    if (pl < lanes) {
+        const T* base = x + ((long long)n * P) * C + vi * 8;
+        for (int pix = p0 + pl; pix < p1; pix += lanes) {
+            float v[8];
+            load8<T>(base + (long long)pix * C, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] += v[j];
+                ss[j] = fmaf(v[j], v[j], ss[j]);
+            }
+        }
+    }
+    // red[tid][16]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[tid * 17 + j] = s[j];
+        red[tid * 17 + 8 + j] = ss[j];
+    }
+    __syncthreads();
+    // thread (vi2, j) sums over the position lanes
+    for (int o = tid; o < cv * 16; o += 256) {
+        const int vi2 = o >> 4, j = o & 15;
+        float a = 0.f;
+        for (int l = 0; l < lanes; ++l) a += red[(l * cv + vi2) * 17 + j];
+        const int c = vi2 * 8 + (j & 7);
+        atomicAdd(ws_nc + 2 * c + (j >> 3), a);
+    }
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const GnParams p) {
+    __shared__ float red[256 * 17];
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    float* ws_n = p.ws + (long long)n * (p.C0 + p.C1) * 2;
+    stats_one_source<T>(static_cast<const T*>(p.x0), p.C0, p.P, n, chunk, p.chunks, ws_n, red);
+    if (p.C1 > 0) stats_one_source<T>(static_cast<const T*>(p.x1), p.C1, p.P, n, chunk, p.chunks, ws_n + 2 * p.C0, red);
+}
+
+template <typename T>
+__device__ __forceinline__ float silu_f(float v) {
+    if constexpr (sizeof(T) == 4) return v / (1.f + expf(-v));
+    else return v / (1.f + __expf(-v));
+}
+
+template <typename T>
+__device__ void apply_one_source(const T* x, int C, int cbase, int Ct, int P, int n, int chunk, int chunks, T* y,
+                                 const float* ab, int silu) {
+    const int cv = C >> 3;
+    const int lanes = 256 / cv;
+    const int tid = threadIdx.x;
+    const int vi = tid % cv, pl = tid / cv;
+    if (pl >= lanes) return;
+    const int per = (P + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(P, p0 + per);
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = ab[2 * (cbase + vi * 8 + j)];
+        b[j] = ab[2 * (cbase + vi * 8 + j) + 1];
+    }
+    const T* xb = x + ((long long)n * P) * C + vi * 8;
+    T* yb = y + ((long long)n * P) * Ct + cbase + vi * 8;
+    for (int pix = p0 + pl; pix < p1; pix += lanes) {
+        float v[8];
+        load8<T>(xb + (long long)pix * C, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = fmaf(v[j], a[j], b[j]);
+            if (silu) v[j] = silu_f<T>(v[j]);
+        }
+        store8(yb + (long long)pix * Ct, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
+    extern __shared__ float ab[];  // [Ct][2] scale, shift  + [32][2] group mean, rstd
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int Ct = p.C0 + p.C1;
+    const int cpg = Ct / 32;
+    float* gstat = ab + 2 * Ct;
+    const float* ws_n = p.ws + (long long)n * Ct * 2;
+    if (threadIdx.x < 32) {
+        const int g = threadIdx.x;
+        float s = 0.f, ss = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            s += ws_n[2 * c];
+            ss += ws_n[2 * c + 1];
+        }
+        const float inv = 1.f / ((float)cpg * (float)p.P);
+        const float mean = s * inv;
+        float var = ss * inv - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        gstat[2 * g] = mean;
+        gstat[2 * g + 1] = 1.f / sqrtf(var + p.eps);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Ct; c += 256) {
+        const int g = c / cpg;
+        const float sc = gstat[2 * g + 1] * p.gamma[c];
+        ab[2 * c] = sc;
+        ab[2 * c + 1] = p.beta[c] - gstat[2 * g] * sc;
+    }
+    __syncthreads();
+    apply_one_source<T>(static_cast<const T*>(p.x0), p.C0, 0, Ct, p.P, n, chunk, p.chunks, static_cast<T*>(p.y), ab, p.silu);
+    if (p.C1 > 0)
+        apply_one_source<T>(static_cast<const T*>(p.x1), p.C1, p.C0, Ct, p.P, n, chunk, p.chunks, static_cast<T*>(p.y), ab, p.silu);
+}
+
+}  // namespace
+
+int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
+    TQ_CHECK(d.dtype == TQ_BF16 || d.dtype == TQ_F32, "groupnorm: bad dtype");
+    const int Ct = d.C0 + d.C1;
+    TQ_CHECK(d.C0 > 0 && d.C0 % 8 == 0 && d.C1 % 8 == 0 && d.C1 >= 0, "groupnorm: channel counts must be multiples of 8");
+    TQ_CHECK(Ct % 32 == 0, "groupnorm: 32 groups need C %% 32 == 0 (C=%d)", Ct);
+    TQ_CHECK(d.C0 <= 2048 && d.C1 <= 2048, "groupnorm: at most 2048 channels per source");
+    TQ_CHECK(d.x0 && d.y && d.ws && d.gamma && d.beta, "groupnorm: null pointer");
+    TQ_CHECK(d.C1 == 0 || d.x1, "groupnorm: second source missing");
+    auto p = std::make_shared<GnParams>();
+    p->x0 = d.x0; p->x1 = d.x1; p->N = d.N; p->P = d.P; p->C0 = d.C0; p->C1 = d.C1;
+    p->gamma = d.gamma; p->beta = d.beta; p->eps = d.eps; p->silu = d.silu; p->y = d.y; p->ws = d.ws;
+    int chunks = (4 * device_sm_count() + d.N - 1) / d.N;
+    const int max_chunks = (d.P + 31) / 32;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    p->chunks = chunks;
+    const bool f32 = d.dtype == TQ_F32;
+    const size_t ws_bytes = (size_t)d.N * Ct * 2 * sizeof(float);
+    const size_t smem = (size_t)(2 * Ct + 64) * sizeof(float);
+    dim3 grid(chunks, d.N);
+
+    Op st;
+    st.name = f32 ? "gn_stats<f32>" : "gn_stats<bf16>";
+    st.launch = [p, grid, f32, ws_bytes](cudaStream_t s) -> int {
+        TQ_CUDA(cudaMemsetAsync(p->ws, 0, ws_bytes, s));
+        if (f32) gn_stats_kernel<float><<<grid, 256, 0, s>>>(*p);
+        else gn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(*p);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    };
+    ops.push_back(std::move(st));
+    Op ap;
+    ap.name = f32 ? "gn_apply<f32>" : "gn_apply<bf16>";
+    ap.launch = [p, grid, f32, smem](cudaStream_t s) -> int {
+        if (f32) gn_apply_kernel<float><<<grid, 256, smem, s>>>(*p);
+        else gn_apply_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*p);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    };
+    ops.push_back(std::move(ap));
+    return 0;
+}
+
+}  // namespace tq

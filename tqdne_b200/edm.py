@@ -1,0 +1,301 @@
+"""EDM preconditioning + Heun sampler on the B200 engine.
+
+Drop-in for tqdne/edm.py: `EDM` constants/scalars (edm.py:9-52), `LightningEDM(unet_config, optimizer_params,
+num_sampling_steps, deterministic_sampling, edm, autoencoder)` with `.forward`, `.sample`, `.evaluate`
+(edm.py:55-238).  The sampler keeps the reference numerics: fp64 state, fp32 sigma schedule, fp32 model I/O,
+(sigma_next - sigma) rounded in fp32, final step Euler-only.  Each NFE is: one replay of the UNet kernel
+plan + ONE fused element-wise kernel (denoiser post-scaling, Euler/Heun update, next input scaling).
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+from .autoencoder import LightningAutoencoder
+from .engine import current_stream_ptr, nchw_to_nhwc, nhwc_to_nchw, require_cuda, tq_dtype
+from .lightning_shim import LightningModule
+from .lowering import get_coder_plan, get_unet_plan
+from .nn import append_dims
+from .unet import UNetModel
+
+
+class EDM:
+    """Hyper-parameters and scalar maps of Karras et al. (reference: tqdne/edm.py:9-52)."""
+
+    sigma_min: float = 0.002
+    sigma_max: float = 80.0
+    rho: float = 7.0
+    sigma_data: float = 0.5
+    P_mean: float = -1.2
+    P_std: float = 1.2
+    S_churn: float = 40
+    S_min: float = 0.05
+    S_max: float = 50
+    S_noise: float = 1.003
+
+    def sigma(self, eps):
+        return (eps * self.P_std + self.P_mean).exp()
+
+    def loss_weight(self, sigma):
+        return (sigma**2 + self.sigma_data**2) / (sigma * self.sigma_data) ** 2
+
+    def skip_scaling(self, sigma):
+        return self.sigma_data**2 / (sigma**2 + self.sigma_data**2)
+
+    def out_scaling(self, sigma):
+        return sigma * self.sigma_data / (sigma**2 + self.sigma_data**2) ** 0.5
+
+    def in_scaling(self, sigma):
+        return 1 / (sigma**2 + self.sigma_data**2) ** 0.5
+
+    def noise_conditioning(self, sigma):
+        return 0.25 * sigma.log()
+
+    def sampling_sigmas(self, num_steps, device=None):
+        inv_rho = 1 / self.rho
+        idx = torch.arange(num_steps, dtype=torch.float32, device=device)
+        lo, hi = self.sigma_min**inv_rho, self.sigma_max**inv_rho
+        sigmas = (hi + idx / (num_steps - 1) * (lo - hi)) ** self.rho
+        return torch.cat([sigmas, torch.zeros_like(sigmas[:1])])
+
+    def sigma_hat(self, sigma, num_steps):
+        gamma = min(self.S_churn / num_steps, 2**0.5 - 1) if self.S_min <= sigma <= self.S_max else 0
+        return sigma + gamma * sigma
+
+
+def _f(x) -> float:
+    return float(x)
+
+
+class _Coeffs:
+    """fp32 scalars of one noise level, rounded exactly like the reference's fp32 tensor arithmetic (CPU)."""
+
+    def __init__(self, edm: EDM, sigma: torch.Tensor):
+        s = sigma.detach().to("cpu", torch.float32).reshape(())
+        self.sigma = _f(s)
+        self.c_in = _f(edm.in_scaling(s))
+        self.c_out = _f(edm.out_scaling(s))
+        self.c_skip = _f(edm.skip_scaling(s))
+        self.c_noise = _f(edm.noise_conditioning(s)) if self.sigma > 0 else 0.0
+
+
+class LightningEDM(LightningModule):
+    """reference: tqdne/edm.py:55-251 (training step / optimizers are out of this engine's scope)."""
+
+    def __init__(self, unet_config: dict, optimizer_params: dict, num_sampling_steps: int = 25,
+                 deterministic_sampling: bool = True, edm: EDM = EDM(), autoencoder: None | LightningAutoencoder = None):
+        super().__init__()
+        self.unet = UNetModel(**unet_config)
+        self.optimizer_params = optimizer_params
+        self.num_sampling_steps = num_sampling_steps
+        self.deterministic_sampling = deterministic_sampling
+        self.edm = edm
+        self.autoencoder = autoencoder.eval() if autoencoder else None
+        self.config = unet_config
+        if self.autoencoder:
+            for p in self.autoencoder.parameters():
+                p.requires_grad = False
+        self.save_hyperparameters(ignore=("autoencoder"))
+        # engine knobs (not part of the reference API)
+        self.max_positions_per_pass = 256 * 1024   # micro-batch = this / (H*W) samples per Heun pass
+        self.decode_micro_batch = 64
+        self.use_cuda_graph = True
+        self.compat_rng = True    # reproduce the reference's RNG draw order inside sample()
+
+    # ---- precision ---------------------------------------------------------------------------------
+    def set_engine_precision(self, precision: str | None) -> "LightningEDM":
+        """'bf16' -> tcgen05 tensor path, 'fp32' -> FFMA parity path, None -> follow the parameter dtype."""
+        dt = {None: None, "bf16": torch.bfloat16, "fp32": torch.float32}[precision]
+        self.unet.engine_dtype = dt
+        if self.autoencoder:
+            self.autoencoder.encoder.engine_dtype = dt
+            self.autoencoder.decoder.engine_dtype = dt
+        return self
+
+    # ---- denoiser ----------------------------------------------------------------------------------
+    def forward(self, sample, sigma, cond_sample=None, cond=None):
+        """D(x, sigma) = c_out * F(c_in * x, c_noise, cond) + c_skip * x  (reference: edm.py:105-113)."""
+        dim = sample.dim()
+        sample_in = sample * append_dims(self.edm.in_scaling(sigma), dim)
+        inp = sample_in if cond_sample is None else torch.cat((sample_in, cond_sample), dim=1)
+        out = self.unet(inp, self.edm.noise_conditioning(sigma), cond=cond)
+        skip = append_dims(self.edm.skip_scaling(sigma), dim) * sample
+        return out * append_dims(self.edm.out_scaling(sigma), dim) + skip
+
+    # ---- sampling ------------------------------------------------------------------------------------
+    def latent_shape(self, shape) -> tuple:
+        """Shape of autoencoder.encode(zeros(shape)) by arithmetic (the reference runs a full dummy encode,
+        edm.py:155-157)."""
+        enc = self.autoencoder.encoder
+        n_down = sum(1 for m in enc.down_blocks if type(m).__name__ == "Downsample")
+        ch = enc.output_layer.weight.shape[0] // 2
+        return (shape[0], ch, *[s // (2**n_down) for s in shape[2:]])
+
+    @torch.no_grad()
+    def sample(self, shape, cond_sample=None, cond=None, noise=None, generator=None):
+        """Heun 2nd-order sampler (reference: edm.py:146-169).
+
+        `noise` (optional, engine extension): explicit unit-variance fp64 noise of the (latent) shape; when
+        omitted, noise is drawn with the reference's draw order so that equal seeds give equal noise.
+        """
+        if cond_sample is not None:
+            raise NotImplementedError("tqdne_b200: cond_sample (signal-conditioned sampling) is not used by any shipped "
+                                      "tqdne config and is not lowered yet")
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("tqdne_b200: LightningEDM.sample needs the module on a CUDA device (no CPU path)")
+        shape = tuple(shape)
+        if self.autoencoder:
+            full_shape = shape
+            shape = self.latent_shape(shape)
+            if noise is None and self.compat_rng:
+                # reference: encode(zeros) draws randn_like(mean) before the sampler noise (autoencoder.py:39)
+                torch.randn(shape, device=dev, dtype=torch.float32, generator=generator)
+        sigmas = self.edm.sampling_sigmas(self.num_sampling_steps, device="cpu")
+        if noise is None:
+            noise = torch.randn(shape, device=dev, dtype=torch.float64, generator=generator)
+        else:
+            assert tuple(noise.shape) == shape, f"noise must have shape {shape}"
+            noise = noise.to(dev, torch.float64)
+        eps = noise * sigmas[0].to(dev)  # fp64 * 0-dim fp32 -> fp64, like the reference
+
+        N = shape[0]
+        spatial = shape[2:]
+        P = math.prod(spatial)
+        micro = max(1, min(N, self.max_positions_per_pass // P))
+        outs = []
+        for i0 in range(0, N, micro):
+            i1 = min(N, i0 + micro)
+            c = cond[i0:i1] if cond is not None else None
+            outs.append(self._sample_chunk(eps[i0:i1].contiguous(), sigmas, c))
+        x = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)   # fp64 channels-last [N, P, C]
+        C_ = shape[1]
+        if not self.autoencoder:
+            return nhwc_to_nchw(x, N, C_, spatial, C_, torch.float32)
+        return self._decode_latents(x, N, C_, spatial)
+
+    def _sample_chunk(self, eps: torch.Tensor, sigmas: torch.Tensor, cond) -> torch.Tensor:
+        """Deterministic / stochastic Heun loop on one micro-batch; returns the fp64 channels-last state."""
+        lib = _lib.lib()
+        n, C_ = eps.shape[0], eps.shape[1]
+        spatial = tuple(eps.shape[2:])
+        NP = n * math.prod(spatial)
+        plan = get_unet_plan(self.unet, n, spatial, uniform_t=True)
+        if self.use_cuda_graph:
+            plan.plan.enable_graph(True)
+        if cond is not None:
+            require_cuda(cond, "cond")
+        assert (cond is not None) == (self.unet.cond_features is not None), \
+            "must specify cond if and only if the model is conditioned"
+        plan.set_cond(cond)
+        dev = eps.device
+        x = nchw_to_nhwc(eps, torch.float64)              # [n, P, C] fp64
+        x1 = torch.empty_like(x)
+        d = torch.empty_like(x)
+        xin, dt_ = plan.xin.t, tq_dtype(plan.act_dtype)
+        F, Cf, Cpad = plan.out.t, plan.out.C, plan.cin_pad
+        nsteps = self.num_sampling_steps
+        co = [_Coeffs(self.edm, s) for s in sigmas]
+        stochastic = not self.deterministic_sampling
+        if stochastic:
+            hats = [self.edm.sigma_hat(s, nsteps) for s in sigmas[:-1]]
+            co_hat = [_Coeffs(self.edm, s) for s in hats]
+        # all c_noise values of the run, resident on the device: the plan reads plan.t
+        tvals = []
+        for i in range(nsteps):
+            tvals.append(co_hat[i].c_noise if stochastic else co[i].c_noise)
+            tvals.append(co[i + 1].c_noise)
+        tdev = torch.tensor(tvals, dtype=torch.float32, device=dev)
+        st = current_stream_ptr()
+
+        def denoise(k):
+            plan.t.copy_(tdev[k:k + 1])
+            plan.run()
+
+        if not stochastic:
+            _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), dt_, NP, C_, Cpad, co[0].c_in, st), "precondition")
+        for i in range(nsteps):
+            cur, nxt = (co_hat[i] if stochastic else co[i]), co[i + 1]
+            if stochastic:
+                # x_hat = x + S_noise * randn * sqrt(sigma_hat^2 - sigma^2)   (reference: edm.py:203-207)
+                s_hat, s_cur = hats[i], sigmas[i]
+                scale = float((s_hat**2 - s_cur**2) ** 0.5) * self.edm.S_noise
+                nz = torch.randn(x.shape, device=dev, dtype=torch.float64)
+                _lib.check(lib.tq_edm_add_noise(x.data_ptr(), nz.data_ptr(), scale, x.numel(), st), "add_noise")
+                _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), dt_, NP, C_, Cpad, cur.c_in, st), "precondition")
+                dt = float((sigmas[i + 1] - hats[i]).to(torch.float32))
+            else:
+                dt = float(sigmas[i + 1] - sigmas[i])  # fp32 subtraction, like the reference's 0-dim tensors
+            last = i == nsteps - 1
+            denoise(2 * i)
+            _lib.check(lib.tq_edm_euler(x.data_ptr(), F.data_ptr(), Cf, d.data_ptr(), x1.data_ptr(), xin.data_ptr(), dt_,
+                                        NP, C_, Cpad, cur.c_out, cur.c_skip, cur.sigma, dt, nxt.c_in, 0 if last else 1, st),
+                       "euler")
+            if last:
+                x, x1 = x1, x
+                break
+            denoise(2 * i + 1)
+            nn_cin = co[i + 1].c_in  # the next step starts at sigma_{i+1}
+            _lib.check(lib.tq_edm_heun(x.data_ptr(), x1.data_ptr(), d.data_ptr(), F.data_ptr(), Cf, xin.data_ptr(), dt_, NP,
+                                       C_, Cpad, nxt.c_out, nxt.c_skip, nxt.sigma, dt, nn_cin, 0 if stochastic else 1, st),
+                       "heun")
+        return x
+
+    def _decode_latents(self, x: torch.Tensor, N: int, C_: int, spatial: tuple) -> torch.Tensor:
+        """sample.to(fp32) -> autoencoder.decode (reference: edm.py:166-168), micro-batched."""
+        lib = _lib.lib()
+        dec = self.autoencoder.decoder
+        P = math.prod(spatial)
+        outs = []
+        mb = min(N, self.decode_micro_batch)
+        st = current_stream_ptr()
+        for i0 in range(0, N, mb):
+            n = min(mb, N - i0)
+            p = get_coder_plan(dec, "decoder", n, spatial)
+            xs = x[i0:i0 + n]
+            _lib.check(lib.tq_edm_precondition(xs.data_ptr(), p.xin.t.data_ptr(), tq_dtype(p.act_dtype), n * P, C_,
+                                               p.cin_pad, 1.0, st), "decode input")
+            p.run()
+            so = (p.out.H, p.out.W) if len(spatial) == 2 else (p.out.W,)
+            outs.append(nhwc_to_nchw(p.out.t, n, p.cout, so, p.cout, torch.float32))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    # reference API: the two samplers are also callable on their own with explicit eps (edm.py:171-230)
+    @torch.no_grad()
+    def sample_deterministically(self, eps, sigmas, cond_sample=None, cond=None):
+        assert cond_sample is None, "cond_sample is not lowered"
+        keep = self.deterministic_sampling
+        self.deterministic_sampling = True
+        try:
+            x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond)
+        finally:
+            self.deterministic_sampling = keep
+        return nhwc_to_nchw(x, eps.shape[0], eps.shape[1], tuple(eps.shape[2:]), eps.shape[1], torch.float64)
+
+    @torch.no_grad()
+    def sample_stochastically(self, eps, sigmas, cond_sample=None, cond=None):
+        assert cond_sample is None, "cond_sample is not lowered"
+        keep = self.deterministic_sampling
+        self.deterministic_sampling = False
+        try:
+            x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond)
+        finally:
+            self.deterministic_sampling = keep
+        return nhwc_to_nchw(x, eps.shape[0], eps.shape[1], tuple(eps.shape[2:]), eps.shape[1], torch.float64)
+
+    @torch.no_grad()
+    def evaluate(self, batch):
+        """reference: edm.py:232-238."""
+        cond_sample = batch["cond_signal"] if "cond_signal" in batch else None
+        cond = batch["cond"] if "cond" in batch else None
+        return self.sample(batch["signal"].shape, cond_sample, cond)
+
+    # training is outside this engine; fail loudly instead of silently doing nothing
+    def step(self, batch, batch_idx):  # pragma: no cover
+        raise NotImplementedError("tqdne_b200 accelerates sampling; train with the reference tqdne package")
+
+    training_step = validation_step = step

@@ -1,0 +1,191 @@
+"""Signal <-> representation maps; the inverses run on the GPU.
+
+Drop-in for tqdne/representation.py: `LogSpectrogram(stft_channels, hop_size, clip, log_max, library,
+multiprocessing)`, `MovingAverageEnvelope(window_size, log_eps, eps)`, `Identity`, `Normalization` with
+`get_representation` / `invert_representation` accepting torch tensors or NumPy arrays and returning NumPy.
+
+`LogSpectrogram.invert_representation` (reference: representation.py:152-175 -> librosa.griffinlim in a pathos
+process pool) is ONE CUDA launch for the whole batch (csrc/tq_griffinlim.cu); a CUDA tensor input is consumed in
+place, so only the waveforms cross PCIe.  The forward maps (`get_representation`) are not on the sampling path
+and use torch.stft / NumPy.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TQ_F32, TQ_F64
+from .engine import current_stream_ptr
+
+
+def _as_cuda_f32(x, device=None) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    if not x.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError("tqdne_b200: representation inverses run on a CUDA device; none is available "
+                               "(there is no CPU fallback)")
+        x = x.to(device or "cuda")
+    return x.to(torch.float32).contiguous()
+
+
+class Representation:
+    """Abstract representation (reference: representation.py:9-19)."""
+
+    def get_representation(self, waveform):
+        raise NotImplementedError
+
+    def invert_representation(self, representation):
+        raise NotImplementedError
+
+
+class Identity(Representation):
+    def get_representation(self, waveform):
+        return _np(waveform)
+
+    def invert_representation(self, representation):
+        return _np(representation)
+
+
+def _np(x):
+    return x.numpy(force=True) if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+class Normalization(Representation):
+    def __init__(self, mean, std):
+        self.mean, self.std = mean, std
+
+    def get_representation(self, waveform):
+        return (_np(waveform) - self.mean) / self.std
+
+    def invert_representation(self, representation):
+        return _np(representation) * self.std + self.mean
+
+
+class MovingAverageEnvelope(Representation):
+    """Scaled signal + log moving-average envelope (reference: representation.py:41-60)."""
+
+    def __init__(self, window_size=128, log_eps=1e-6, eps=1e-6):
+        self.window_size, self.log_eps, self.eps = window_size, log_eps, eps
+
+    def get_representation(self, waveform):
+        w = _np(waveform)
+        kernel = np.full(self.window_size, 1.0 / self.window_size)
+        flat = np.abs(w).reshape(-1, w.shape[-1])
+        env = np.stack([np.convolve(row, kernel, mode="same") for row in flat]).reshape(w.shape)
+        return np.concatenate([w / (env + self.eps), np.log(env + self.log_eps) - np.log(self.log_eps) / 2], axis=-2)
+
+    def invert_representation_device(self, representation) -> torch.Tensor:
+        rep = _as_cuda_f32(representation)
+        lead, (c2, L) = rep.shape[:-2], rep.shape[-2:]
+        assert c2 % 2 == 0, "expected [.., 2*channels, L]"
+        n = int(math.prod(lead)) if lead else 1
+        out = torch.empty(*lead, c2 // 2, L, device=rep.device, dtype=torch.float32)
+        _lib.check(_lib.lib().tq_mavg_envelope_inverse(rep.data_ptr(), out.data_ptr(), n, c2 // 2, L, self.log_eps,
+                                                       self.eps, current_stream_ptr()), "mavg_envelope_inverse")
+        return out
+
+    def invert_representation(self, representation):
+        return self.invert_representation_device(representation).cpu().numpy()
+
+
+class LogSpectrogram(Representation):
+    """Log-magnitude STFT in [-1, 1]; inverse = exp + fast Griffin-Lim (reference: representation.py:63-175).
+
+    Extra keyword (engine extension): `precision` = "fp32" (default) or "fp64" arithmetic for Griffin-Lim
+    (the reference runs complex128 under NumPy >= 2 and complex64 under NumPy 1.x).
+    `library` and `multiprocessing` are accepted for signature compatibility and ignored: there is no
+    librosa / process pool here.
+    """
+
+    n_iter = 128          # librosa.griffinlim(n_iter=128, ...) representation.py:106-108
+    momentum = 0.99       # librosa default
+    random_state = 0
+
+    def __init__(self, stft_channels=256, hop_size=None, clip=1e-8, log_max=3, library="librosa", multiprocessing=True,
+                 precision="fp32"):
+        self.clip = clip
+        self.log_clip = np.log(clip)
+        self.log_max = log_max
+        self.library = library
+        self.stft_channels = stft_channels
+        self.hop_size = stft_channels // 4 if hop_size is None else hop_size
+        if precision not in ("fp32", "fp64"):
+            raise ValueError("precision must be 'fp32' or 'fp64'")
+        self.precision = precision
+        self._phase = {}
+        self._ws = None
+        self.max_items_per_launch = 3072
+
+    def disable_multiprocessing(self):
+        """Kept for API compatibility (reference: representation.py:135-138); nothing to close."""
+
+    # ---- forward (not on the sampling path) ---------------------------------------------------------
+    def get_spectrogram(self, waveform):
+        w = torch.as_tensor(_np(waveform))
+        shape = w.shape
+        flat = w.reshape(-1, shape[-1]).to(torch.float64)
+        win = torch.hann_window(self.stft_channels, periodic=True, dtype=torch.float64)
+        spec = torch.stft(flat, n_fft=self.stft_channels, hop_length=self.hop_size, window=win, center=True,
+                          pad_mode="constant", return_complex=True)
+        spec = spec[:, :-1]  # drop the Nyquist row (representation.py:147)
+        return spec.reshape(*shape[:-1], *spec.shape[1:]).numpy()
+
+    def get_representation(self, waveform):
+        mag = np.abs(self.get_spectrogram(waveform))
+        log_spec = np.log(np.clip(mag, self.clip, None))
+        return (log_spec - self.log_clip) / (self.log_max - self.log_clip) * 2 - 1
+
+    # ---- inverse (hot path) ----------------------------------------------------------------------------
+    def _phase0(self, frames: int, device) -> torch.Tensor:
+        key = (frames, str(device))
+        if key not in self._phase:
+            rng = np.random.RandomState(seed=self.random_state)
+            u = rng.random(size=(self.stft_channels // 2 + 1, frames))
+            self._phase[key] = torch.from_numpy(2 * np.pi * u).to(device)
+        return self._phase[key]
+
+    def invert_representation_device(self, representation) -> torch.Tensor:
+        """[.., n_fft/2, frames] in [-1, 1] -> waveforms [.., hop*(frames-1)] as a CUDA tensor."""
+        rep = _as_cuda_f32(representation)
+        lead, (nb, frames) = rep.shape[:-2], rep.shape[-2:]
+        if nb != self.stft_channels // 2:
+            raise ValueError(f"expected {self.stft_channels // 2} frequency rows, got {nb}")
+        items = int(math.prod(lead)) if lead else 1
+        lib = _lib.lib()
+        prec = TQ_F64 if self.precision == "fp64" else TQ_F32
+        odt = torch.float64 if prec == TQ_F64 else torch.float32
+        out_len = self.hop_size * (frames - 1)
+        out = torch.empty(items, out_len, device=rep.device, dtype=odt)
+        rep2 = rep.reshape(items, nb, frames)
+        phase = self._phase0(frames, rep.device)
+        step = min(items, self.max_items_per_launch)
+        need = lib.tq_griffinlim_ws_bytes(step, self.stft_channels, frames, prec)
+        if need < 0:
+            raise RuntimeError("tqdne_b200: unsupported STFT size for the Griffin-Lim kernel")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != rep.device:
+            self._ws = torch.empty(need, device=rep.device, dtype=torch.uint8)
+        st = current_stream_ptr()
+        for i0 in range(0, items, step):
+            n = min(step, items - i0)
+            _lib.check(lib.tq_logspec_griffinlim(rep2[i0:i0 + n].data_ptr(), phase.data_ptr(), out[i0:i0 + n].data_ptr(), n,
+                                                 self.stft_channels, self.hop_size, frames, self.n_iter,
+                                                 float(self.log_clip), float(self.log_max), self.momentum, prec,
+                                                 self._ws.data_ptr(), st), "logspec_griffinlim")
+        return out.reshape(*lead, out_len)
+
+    def invert_representation(self, representation):
+        return self.invert_representation_device(representation).cpu().numpy()
+
+    def invert_spectrogram(self, spec):
+        """Magnitudes [.., n_fft/2, frames] -> waveforms (reference: representation.py:152-161)."""
+        s = torch.as_tensor(_np(spec)) if not isinstance(spec, torch.Tensor) else spec
+        log_spec = torch.log(torch.clamp(s.to(torch.float64), min=1e-300))
+        rep = (log_spec - self.log_clip) / (self.log_max - self.log_clip) * 2 - 1
+        return self.invert_representation(rep.to(torch.float32))
