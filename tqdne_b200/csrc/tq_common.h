@@ -28,6 +28,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     do {                                                                                      \
         cudaError_t e__ = (expr);                                                             \
         if (e__ != cudaSuccess) {                                                             \
+            (void)cudaGetLastError(); /* do not leave a stale error for the next launch check */ \
             tq::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
             return 1;                                                                         \
         }                                                                                     \

@@ -103,7 +103,7 @@ __global__ void euler_kernel(const double* x, const float* F, int Cf, double* d,
     }
     const double xv = x[r * C + c];
     const float x32 = (float)xv;
-    const float D = F[r * Cf + c] * c_out + c_skip * x32;
+    const float D = __fadd_rn(__fmul_rn(F[r * Cf + c], c_out), __fmul_rn(c_skip, x32));  // no FMA: torch rounds each op
     const double dv = (xv - (double)D) / (double)sigma;
     const double xn = xv + dv * (double)dt;
     if (d) d[r * C + c] = dv;
@@ -127,7 +127,7 @@ __global__ void heun_kernel(double* x, const double* x1, const double* d, const 
     }
     const double x1v = x1[r * C + c];
     const float x32 = (float)x1v;
-    const float D = F[r * Cf + c] * c_out + c_skip * x32;
+    const float D = __fadd_rn(__fmul_rn(F[r * Cf + c], c_out), __fmul_rn(c_skip, x32));  // no FMA: torch rounds each op
     const double dp = (x1v - (double)D) / (double)sigma_next;
     const double xn = x[r * C + c] + (double)dt * (0.5 * d[r * C + c] + 0.5 * dp);
     x[r * C + c] = xn;

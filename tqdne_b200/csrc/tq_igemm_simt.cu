@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) igemm_simt_kernel(const SimtParams p) {
 int build_conv_simt(std::vector<Op>& ops, const tq_conv_desc& d) {
     TQ_CHECK(d.dtype == TQ_BF16 || d.dtype == TQ_F32, "simt igemm: bad dtype");
     TQ_CHECK(d.num_srcs >= 1 && d.num_srcs <= 4, "num_srcs out of range");
-    TQ_CHECK(d.num_classes == 1 || d.num_classes == 4, "num_classes must be 1 or 4");
+    TQ_CHECK(d.num_classes == 1 || d.num_classes == 2 || d.num_classes == 4, "num_classes must be 1, 2 or 4");
     TQ_CHECK(d.ktot % 64 == 0 && d.cout_pad % 64 == 0, "weight matrix must be padded to 64x64 blocks");
     TQ_CHECK(d.out_dtype == TQ_F32 || d.out_dtype == TQ_BF16, "bad out_dtype");
     auto p = std::make_shared<SimtParams>();

@@ -372,7 +372,7 @@ void tile_shape_for(int H, int W, int* bw, int* bh, int* bn) {
 int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     TQ_CHECK(d.dtype == TQ_BF16, "sm100 igemm needs bf16 operands");
     TQ_CHECK(d.num_srcs >= 1 && d.num_srcs <= 4, "num_srcs out of range");
-    TQ_CHECK(d.num_classes == 1 || d.num_classes == 4, "num_classes must be 1 or 4");
+    TQ_CHECK(d.num_classes == 1 || d.num_classes == 2 || d.num_classes == 4, "num_classes must be 1, 2 or 4");
     TQ_CHECK(d.num_slices >= 1, "conv needs at least one K slice");
     TQ_CHECK(d.ktot % 64 == 0 && d.cout_pad % 64 == 0, "weight matrix must be padded to 64x64 blocks");
     TQ_CHECK(d.cout >= 1 && d.cout <= d.cout_pad, "cout out of range");

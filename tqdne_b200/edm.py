@@ -83,6 +83,33 @@ class _Coeffs:
         self.c_noise = _f(edm.noise_conditioning(s)) if self.sigma > 0 else 0.0
 
 
+class _SideStream:
+    """Run on a non-legacy stream ordered after the caller's stream; order the caller after it on exit."""
+
+    def __init__(self, owner):
+        self.owner, self.ctx = owner, None
+
+    def __enter__(self):
+        self.cur = torch.cuda.current_stream()
+        if self.cur.cuda_stream != 0:
+            return self
+        s = self.owner.__dict__.get("_tq_stream")
+        if s is None:
+            s = torch.cuda.Stream()
+            self.owner.__dict__["_tq_stream"] = s
+        s.wait_stream(self.cur)
+        self.s = s
+        self.ctx = torch.cuda.stream(s)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.cur.wait_stream(self.s)
+        return False
+
+
 class LightningEDM(LightningModule):
     """reference: tqdne/edm.py:55-251 (training step / optimizers are out of this engine's scope)."""
 
@@ -167,16 +194,25 @@ class LightningEDM(LightningModule):
         spatial = shape[2:]
         P = math.prod(spatial)
         micro = max(1, min(N, self.max_positions_per_pass // P))
-        outs = []
-        for i0 in range(0, N, micro):
-            i1 = min(N, i0 + micro)
-            c = cond[i0:i1] if cond is not None else None
-            outs.append(self._sample_chunk(eps[i0:i1].contiguous(), sigmas, c))
-        x = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)   # fp64 channels-last [N, P, C]
-        C_ = shape[1]
-        if not self.autoencoder:
-            return nhwc_to_nchw(x, N, C_, spatial, C_, torch.float32)
-        return self._decode_latents(x, N, C_, spatial)
+        with self._engine_stream():
+            outs = []
+            for i0 in range(0, N, micro):
+                i1 = min(N, i0 + micro)
+                c = cond[i0:i1] if cond is not None else None
+                outs.append(self._sample_chunk(eps[i0:i1].contiguous(), sigmas, c))
+            x = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)   # fp64 channels-last [N, P, C]
+            C_ = shape[1]
+            if not self.autoencoder:
+                result = nhwc_to_nchw(x, N, C_, spatial, C_, torch.float32)
+            else:
+                result = self._decode_latents(x, N, C_, spatial)
+        result.record_stream(torch.cuda.current_stream())
+        return result
+
+    def _engine_stream(self):
+        """CUDA graphs cannot be captured on the legacy default stream: run the sampler on a side stream that
+        is ordered after / before the caller's current stream."""
+        return _SideStream(self)
 
     def _sample_chunk(self, eps: torch.Tensor, sigmas: torch.Tensor, cond) -> torch.Tensor:
         """Deterministic / stochastic Heun loop on one micro-batch; returns the fp64 channels-last state."""
@@ -271,10 +307,13 @@ class LightningEDM(LightningModule):
         keep = self.deterministic_sampling
         self.deterministic_sampling = True
         try:
-            x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond)
+            with self._engine_stream():
+                x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond)
+                out = nhwc_to_nchw(x, eps.shape[0], eps.shape[1], tuple(eps.shape[2:]), eps.shape[1], torch.float64)
         finally:
             self.deterministic_sampling = keep
-        return nhwc_to_nchw(x, eps.shape[0], eps.shape[1], tuple(eps.shape[2:]), eps.shape[1], torch.float64)
+        out.record_stream(torch.cuda.current_stream())
+        return out
 
     @torch.no_grad()
     def sample_stochastically(self, eps, sigmas, cond_sample=None, cond=None):
@@ -282,10 +321,13 @@ class LightningEDM(LightningModule):
         keep = self.deterministic_sampling
         self.deterministic_sampling = False
         try:
-            x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond)
+            with self._engine_stream():
+                x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond)
+                out = nhwc_to_nchw(x, eps.shape[0], eps.shape[1], tuple(eps.shape[2:]), eps.shape[1], torch.float64)
         finally:
             self.deterministic_sampling = keep
-        return nhwc_to_nchw(x, eps.shape[0], eps.shape[1], tuple(eps.shape[2:]), eps.shape[1], torch.float64)
+        out.record_stream(torch.cuda.current_stream())
+        return out
 
     @torch.no_grad()
     def evaluate(self, batch):

@@ -68,6 +68,7 @@ class PackedConv:
     kernel: tuple
     extra_kb: dict = field(default_factory=dict)  # fused 1x1 shortcut: (seg_index, chunk) -> K block
     sc_seg_pad: list = field(default_factory=list)  # padded channel count per shortcut segment
+    macs_per_out: int = 0  # real (unpadded) multiply-adds per output element: taps*Cin (+ shortcut Cin)
 
 
 def pack_conv(weight: torch.Tensor, bias: torch.Tensor | None, segments: list[int], dtype: torch.dtype,
@@ -127,8 +128,9 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor | None, segments: list[in
         if bs is not None:
             b[:O] += bs.detach().to(torch.float32)
     assert col == ktot
+    macs = len(taps) * I + (sum(shortcut[2]) if shortcut is not None else 0)
     return PackedConv(B.to(dtype).contiguous(), b.contiguous(), O, cout_pad, ktot, taps, seg_pad, kb_of, kernel, extra_kb,
-                      sc_seg_pad)
+                      sc_seg_pad, macs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -188,7 +190,8 @@ class Plan:
         self.pool = Pool(device, act_dtype)
         self.keep: list = []
         self.gn_ws = None
-        self.flops = 0  # algorithmic FLOPs (2*MAC of the reference op, no padding) of the dense ops
+        # one entry per kernel launch of the plan: (kind, algorithmic FLOPs, algorithmic HBM bytes)
+        self.op_meta: list[tuple] = []
 
     def __del__(self):
         try:
@@ -328,6 +331,7 @@ class Plan:
             d.out_class_off[i] = class_off[i]
         d.block_n = block_n
         _lib.check(self.lib.tq_plan_add_conv(self.h, C.byref(d)), "plan_add_conv")
+        self.op_meta.append(("conv", 2 * N * Ho * Wo * pc.cout * pc.macs_per_out, 0))
         self.keep += [pc.weights, pc.bias, emb, out.t] + [v[0] for v in src_views]
         if residual is not None:
             self.keep.append(residual.t)
@@ -351,6 +355,10 @@ class Plan:
         d.y = out.t.data_ptr()
         d.ws = self._gn_scratch(2 * a0.N * 2048).data_ptr() if Ct <= 2048 else self._gn_scratch(2 * a0.N * Ct).data_ptr()
         _lib.check(self.lib.tq_plan_add_groupnorm(self.h, C.byref(d)), "plan_add_groupnorm")
+        esz = a0.t.element_size()
+        nel = a0.N * a0.P * Ct
+        self.op_meta.append(("gn_stats", 0, nel * esz))          # one read
+        self.op_meta.append(("gn_apply", 0, 2 * nel * esz))      # one read + one write
         self.keep += [g, b, a0.t, out.t] + ([a1.t] if a1 else [])
         return out
 
@@ -362,6 +370,7 @@ class Plan:
         d.N, d.T, d.heads, d.d = qkv.N, qkv.P, heads, Cc // heads
         d.qkv, d.out = qkv.t.data_ptr(), out.t.data_ptr()
         _lib.check(self.lib.tq_plan_add_attention(self.h, C.byref(d)), "plan_add_attention")
+        self.op_meta.append(("attention", 4 * qkv.N * qkv.P * qkv.P * Cc, 0))
         self.keep += [qkv.t, out.t]
         return out
 
@@ -378,11 +387,13 @@ class Plan:
         d.y_act = y_act.data_ptr() if y_act is not None else None
         d.y_act_dtype = tq_dtype(y_act.dtype) if y_act is not None else TQ_F32
         _lib.check(self.lib.tq_plan_add_linear(self.h, C.byref(d)), "plan_add_linear")
+        self.op_meta.append(("linear", 2 * M * W.shape[0] * W.shape[1], 0))
         self.keep += [x, W, b, add, y, y_act]
 
     def fourier(self, t, Wf, M, feat):
         _lib.check(self.lib.tq_plan_add_fourier(self.h, t.data_ptr(), Wf.data_ptr(), M, Wf.numel(), feat.data_ptr()),
                    "plan_add_fourier")
+        self.op_meta.append(("fourier", 0, 0))
         self.keep += [t, Wf, feat]
 
     # -- execution ------------------------------------------------------------------------------
