@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- waveforms/sec of the HighFEM latent EDM sampling hot path on N B200s (one process per GPU).
+
+A "step" is one pass of the hot path over one batch: 25 Heun steps (49 denoiser calls) of the latent
+UNet -> autoencoder decode -> log-spectrogram inverse (128 Griffin-Lim iterations) -> [B, 3, 4064] waveforms,
+B = 256 per GPU (BASELINE.json configs[1]); the batch shards over GPUs as independent samples (weak scaling)
+with a final gather of the waveforms.  Random-init weights of the named architecture, synthetic conditioning.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 ... bench.py --gpus 8 ...
+    python bench.py --impl reference --steps 2 --warmup 1     # the reference algorithm on the host CPUs
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event time, max over ranks.
+`e2e`: the same pass through the public API from pinned HOST buffers (cond + noise H2D, waveforms D2H).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+NFE_STEPS = 25
+FLOP_PER_WAVEFORM = 49 * 16.979e9 + 27.206e9  # SURVEY 8.1 / BASELINE.md section 3 (conv+attn+linear, 2*MAC)
+METRIC = "waveforms/sec (3-comp, 25 Heun steps, latent EDM + decode + Griffin-Lim)"
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# model construction (shared by both arms): named architecture, seeded synthetic weights
+# ------------------------------------------------------------------------------------------------------
+def build_state_dict(edm, seed=0):
+    from oracle.weights import seeded_state_dict, shapes_of
+
+    sd = seeded_state_dict(shapes_of(edm), seed)
+    # keep the random-init decoder's output inside the normalised log-spectrogram range [-1, 1]
+    for k in ("autoencoder.decoder.output_layer.weight", "autoencoder.decoder.output_layer.bias"):
+        sd[k] = sd[k] * 0.05
+    return sd
+
+
+def cond_grid(n: int):
+    """magnitude x hypocentral distance x vs30 grid, depth 10 km, gap 130 deg, z-scored with the reference's
+    dataset statistics (tqdne/generate_waveforms.py:128-159); feature order (dist, mag, vs30, depth, gap)."""
+    import numpy as np
+
+    mags = np.linspace(4.5, 7.5, 16)
+    dists = np.linspace(10.0, 200.0, 16)
+    vs30s = np.linspace(150.0, 900.0, 8)
+    g = np.stack(np.meshgrid(dists, mags, vs30s, indexing="ij"), -1).reshape(-1, 3)
+    g = np.tile(g, (max(1, -(-n // len(g))), 1))[:n]
+    raw = np.concatenate([g, np.full((n, 1), 10.0), np.full((n, 1), 130.0)], axis=1)
+    stats = np.array([[101.29891904350877, 40.78415968551517], [4.801697862929673, 0.7146698731358634],
+                      [384.7045105848187, 220.11269086015872], [38.359214998072, 22.472499592355014],
+                      [129.92139043457396, 89.69479051949207]])
+    return ((raw - stats[:, 0]) / stats[:, 1]).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------------
+def _gl_item(args):
+    from oracle import griffinlim_ref
+
+    return griffinlim_ref.logspec_inverse(args, n_iter=128, precision="fp64")
+
+
+class CpuPipeline:
+    """Latent pipeline on the CPU: the unmodified reference modules when /root/reference is present (build
+    container), else the oracle port (GPU box).  Griffin-Lim fans out over a process pool like the reference's
+    pathos pool (tqdne/representation.py:128-129,156-157); librosa is absent everywhere, so the restated
+    griffinlim is used in both cases."""
+
+    def __init__(self, batch: int):
+        import torch
+
+        import tqdne_b200 as tq
+        from oracle import reference_loader
+        self.torch = torch
+        self.batch = batch
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        from types import SimpleNamespace
+
+        cfg = SimpleNamespace(features_keys=("dist", "mag", "vs30", "depth", "gap"), channels=3, latent_channels=8)
+        self.enc_cfg, self.dec_cfg = tq.get_2d_autoencoder_configs(cfg)
+        self.unet_cfg = tq.get_2d_unet_config(cfg, 8, 8)
+        shell = tq.LightningEDM(self.unet_cfg, {}, autoencoder=tq.LightningAutoencoder(self.enc_cfg, self.dec_cfg, {}))
+        self.sd = build_state_dict(shell)
+        self.kind = "port"
+        self.ref_edm = None
+        if reference_loader.available():
+            ref = reference_loader.load()
+            ae = ref.autoencoder.LightningAutoencoder(self.enc_cfg, self.dec_cfg, {})
+            self.ref_edm = ref.edm.LightningEDM(self.unet_cfg, {}, num_sampling_steps=NFE_STEPS, autoencoder=ae)
+            self.ref_edm.load_state_dict(self.sd)
+            self.ref_edm.eval()
+            self.kind = "reference"
+        import numpy as np
+
+        self.cond = torch.from_numpy(cond_grid(batch))
+        self.np = np
+        import multiprocessing as mp
+
+        self.pool = mp.get_context("fork").Pool(min(self.cores, 3 * batch))
+
+    def step(self, seed: int):
+        torch = self.torch
+        from oracle import torch_ref
+
+        gen = torch.Generator().manual_seed(seed)
+        noise = torch.randn((self.batch, 8, 32, 32), generator=gen, dtype=torch.float64)
+        with torch.no_grad():
+            if self.ref_edm is not None:
+                sig = self.ref_edm.edm.sampling_sigmas(NFE_STEPS)
+                lat = self.ref_edm.sample_deterministically(noise * sig[0], sig, None, self.cond)
+                rep = self.ref_edm.autoencoder.decode(lat.to(torch.float32))
+            else:
+                sig = torch_ref.sampling_sigmas(NFE_STEPS)
+                lat = torch_ref.heun_sample(self.sd, self.unet_cfg, noise * sig[0], sig, self.cond)
+                rep = torch_ref.decoder_forward(self.sd, self.dec_cfg, lat.float(), prefix="autoencoder.decoder.")
+        items = rep.numpy().reshape(-1, 1, 128, 128)
+        waves = self.pool.map(_gl_item, list(items))
+        return self.np.concatenate(waves).reshape(self.batch, 3, -1)
+
+    def close(self):
+        self.pool.close()
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    batch = args.cpu_batch
+    pipe = CpuPipeline(batch)
+    for i in range(args.warmup):
+        pipe.step(100 + i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        w = pipe.step(i)
+    dt = time.perf_counter() - t0
+    pipe.close()
+    assert w.shape == (batch, 3, 4064)
+    val = batch * args.steps / dt
+    sample = f"{batch} waveforms per step: full 25-step Heun (49 NFE) + decode + 128-iteration Griffin-Lim"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "waveforms/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "HighFEM latent EDM: latent UNet Heun sampling + autoencoder decode + log-spectrogram "
+                               "inverse (bounded CPU sample of the batch-256 workload)", "batch_per_step": batch,
+                   "heun_steps": NFE_STEPS, "nfe": 2 * NFE_STEPS - 1, "weights": "random-init (seeded)"},
+        "cpu_baseline": {"value": val, "unit": "waveforms/s", "cores": pipe.cores, "kind": pipe.kind, "sample": sample},
+        "e2e": {"value": val, "unit": "waveforms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def kernel_breakdown(edm, batch, iters=3):
+    """Per-launch CUDA-event timing of one denoiser call (eager replay of the UNet plan, op by op)."""
+    import torch
+
+    from tqdne_b200.lowering import get_unet_plan
+
+    plan = get_unet_plan(edm.unet, batch, (32, 32), uniform_t=True)
+    p = plan.plan
+    n = p.num_ops
+    names = p.op_names()
+    meta = p.op_meta
+    assert len(meta) == n, (len(meta), n)
+    s = torch.cuda.Stream()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n + 1)] for _ in range(iters)]
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            p.run_range(0, n)
+        for it in range(iters):
+            ev[it][0].record(s)
+            for i in range(n):
+                p.run_range(i, i + 1)
+                ev[it][i + 1].record(s)
+    s.synchronize()
+    agg = {}
+    for i in range(n):
+        ms = sum(ev[it][i].elapsed_time(ev[it][i + 1]) for it in range(iters)) / iters
+        kind = names[i].split("<")[0].split(" ")[0]
+        a = agg.setdefault(kind, {"ms": 0.0, "launches": 0, "flops": 0, "bytes": 0})
+        a["ms"] += ms
+        a["launches"] += 1
+        a["flops"] += meta[i][1]
+        a["bytes"] += meta[i][2]
+    return agg
+
+
+def run_engine(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import tqdne_b200 as tq
+    from tqdne_b200 import _lib, sharding
+    from tqdne_b200.config import LatentSpectrogramConfig
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    total = B * world
+    lo, hi = sharding.shard_bounds(total, rank, world)
+
+    cfg = LatentSpectrogramConfig()
+    enc_cfg, dec_cfg = tq.get_2d_autoencoder_configs(cfg)
+    unet_cfg = tq.get_2d_unet_config(cfg, cfg.latent_channels, cfg.latent_channels)
+    edm = tq.LightningEDM(unet_cfg, {}, num_sampling_steps=NFE_STEPS,
+                          autoencoder=tq.LightningAutoencoder(enc_cfg, dec_cfg, {}))
+    edm.load_state_dict(build_state_dict(edm))
+    edm.eval().to(dev).set_engine_precision(args.precision)
+    rep_inv = cfg.representation
+
+    cond_all = torch.from_numpy(cond_grid(total))
+    cond_host = cond_all[lo:hi].contiguous().pin_memory()
+    noise_host = sharding.global_noise((8, 32, 32), lo, hi, seed=1, device="cpu").pin_memory()
+    cond_dev = cond_host.to(dev)
+    noise_dev = noise_host.to(dev)
+    h2d = cond_host.numel() * 4 + noise_host.numel() * 8
+    d2h = (hi - lo) * 3 * cfg.t * 4
+
+    def step_resident():
+        rep = edm.sample((hi - lo, 3, 128, 128), cond=cond_dev, noise=noise_dev)
+        return rep_inv.invert_representation_device(rep)
+
+    def step_e2e():
+        c = cond_host.to(dev, non_blocking=True)
+        z = noise_host.to(dev, non_blocking=True)
+        rep = edm.sample((hi - lo, 3, 128, 128), cond=c, noise=z)
+        wav = rep_inv.invert_representation_device(rep)
+        if world > 1:
+            full = sharding.gather_waveforms(wav, total)   # the one collective: final gather to rank 0
+            return full.cpu() if full is not None else None
+        return wav.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1]), out
+
+    for _ in range(max(3, args.warmup)):
+        w = step_resident()
+    assert tuple(w.shape) == (hi - lo, 3, cfg.t) and bool(torch.isfinite(w).all()), "non-finite waveforms"
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _lib.launch_count_reset()
+    ev_ms, wall_ms, _ = timed(step_resident, args.steps)
+    launches = _lib.launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    step_e2e()  # warm the pinned-copy path
+    e2e_ev_ms, e2e_wall_ms, _ = timed(step_e2e, args.steps)
+    e2e_ms = max(e2e_ev_ms, e2e_wall_ms)  # the D2H at the end is host-synchronous: wall clock bounds it
+
+    value = total * args.steps / (ev_ms / 1e3)
+    e2e_value = total * args.steps / (e2e_ms / 1e3)
+    pk = peaks()
+    line = {
+        "metric": METRIC, "value": value, "unit": "waveforms/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "HighFEM latent EDM: latent UNet Heun sampling + autoencoder decode + log-spectrogram "
+                               "inverse, batch 256 per B200 (BASELINE.json configs[1])",
+                   "batch_per_gpu": B, "global_batch": total, "heun_steps": NFE_STEPS, "nfe": 2 * NFE_STEPS - 1,
+                   "griffinlim_iters": 128, "weights": "random-init (seeded)", "parallelism": f"batch-sharded x{world}",
+                   "cache": "activations of one denoiser call (~1.5 GB) exceed the 126 MB L2; no L2 flush needed",
+                   "cuda_graph": bool(edm.use_cuda_graph)},
+        "e2e": {"value": e2e_value, "unit": "waveforms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "achieved_tflops_per_gpu": value / world * FLOP_PER_WAVEFORM / 1e12,
+        "frac_of_bf16_sustained_peak": value / world * FLOP_PER_WAVEFORM / 1e12 / pk["bf16_tflops_sustained"],
+        "wall_ms_per_step": wall_ms / args.steps,
+    }
+    if rank == 0 and world == 1:
+        agg = kernel_breakdown(edm, hi - lo)
+        tot_ms = sum(a["ms"] for a in agg.values())
+        conv = agg.get("igemm_sm100") or agg.get("igemm_simt")
+        ach = conv["flops"] / (conv["ms"] / 1e3) / 1e12
+        line["roofline"] = {
+            "kernel": "igemm_sm100 (tcgen05 implicit-GEMM conv), all launches of one denoiser call",
+            "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+            "peak_source": f"{pk['source']} bf16 burst (MEASURED_PEAKS.json)", "traffic": None,
+            "launches_per_call": conv["launches"], "share_of_denoiser_call": conv["ms"] / tot_ms,
+        }
+        gn = {k: agg[k] for k in agg if k.startswith("gn_")}
+        if gn:
+            gb = sum(a["bytes"] for a in gn.values())
+            gms = sum(a["ms"] for a in gn.values())
+            line["roofline_groupnorm"] = {"bound": "hbm", "achieved": gb / (gms / 1e3) / 1e9, "peak": pk["hbm_gbs"],
+                                          "unit": "GB/s", "frac": gb / (gms / 1e3) / 1e9 / pk["hbm_gbs"],
+                                          "share_of_denoiser_call": gms / tot_ms}
+        line["kernel_ms_per_denoiser_call"] = {k: round(a["ms"], 4) for k, a in sorted(agg.items())}
+        if not args.no_cpu_baseline:
+            pipe = CpuPipeline(args.cpu_batch)
+            t0 = time.perf_counter()
+            pipe.step(0)
+            dt = time.perf_counter() - t0
+            pipe.close()
+            line["cpu_baseline"] = {"value": args.cpu_batch / dt, "unit": "waveforms/s", "cores": pipe.cores,
+                                    "kind": pipe.kind,
+                                    "sample": f"{args.cpu_batch} waveforms, full 25-step Heun + decode + 128-iter "
+                                              f"Griffin-Lim, {dt:.1f} s on the host"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="waveforms per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=4, help="waveforms per step of the CPU arm / CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()
