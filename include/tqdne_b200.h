@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 1
+#define TQ_ABI_VERSION 2
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -45,6 +45,9 @@ int      tq_plan_run(tq_plan* p, void* stream);
 int      tq_plan_run_range(tq_plan* p, int first, int last, void* stream);
 /* capture the whole plan into a CUDA graph once; later tq_plan_run() replays the graph */
 int      tq_plan_enable_graph(tq_plan* p, int enable);
+/* cudaMemsetAsync(ptr, 0, bytes) as a plan op; at_front != 0 inserts it before every op added so
+ * far (the statistics arena of a plan is cleared once, ahead of the first producer)              */
+int      tq_plan_add_memset(tq_plan* p, void* ptr, int64_t bytes, int32_t at_front);
 /* name of the kernel behind op i (for profiles and tests) */
 const char* tq_plan_op_name(const tq_plan* p, int i);
 
@@ -92,6 +95,12 @@ typedef struct {
     int64_t out_sn, out_sy, out_sx;   /* element strides of the output                           */
     int64_t out_class_off[4];         /* element offset of each parity class                     */
     int32_t block_n;          /* 0 = auto, else 64 / 128 / 256                                   */
+    float*  stats;            /* device [N][cout][2] fp32 or NULL: per-(sample, channel) sum and  *
+                               * sum of squares of the STORED output, accumulated with atomics in  *
+                               * the epilogue (feeds tq_gn_desc.stats0/1 of the consuming          *
+                               * GroupNorm: the normalisation never re-reads the tensor for its    *
+                               * statistics).  The caller zeroes it before the conv runs           *
+                               * (tq_plan_add_memset).  Needs cout % 32 == 0.                      */
 } tq_conv_desc;
 int tq_plan_add_conv(tq_plan* p, const tq_conv_desc* d);
 
@@ -100,7 +109,10 @@ int tq_plan_add_conv(tq_plan* p, const tq_conv_desc* d);
  * out_layers (unet.py:85-103, blocks.py:238-250), attention norm (blocks.py:126), `out`
  * (unet.py:354-356), fed by th.cat([h, hs.pop()], dim=1) (unet.py:396) without materialising it.
  * x0:[N,P,C0] (+ x1:[N,P,C1]) -> y:[N,P,C0+C1]; stats in fp32; eps as given; 32 groups.
- * `ws` is a caller-provided fp32 scratch of 2*N*(C0+C1) floats.                                 */
+ * `ws` is a caller-provided fp32 scratch of 2*N*(C0+C1) floats, used when the per-channel sums  *
+ * are not supplied: stats0 / stats1 ([N][C0][2], [N][C1][2], written by the producing conv's    *
+ * epilogue, tq_conv_desc.stats) skip the statistics pass, leaving ONE streaming pass (2 B read  *
+ * + 2 B written per element in bf16).  Both or neither must be given for a two-source norm.     */
 typedef struct {
     int32_t dtype;         /* TQ_BF16 | TQ_F32 for x0, x1, y                                      */
     int32_t N, P, C0, C1;  /* P = H*W positions                                                   */
@@ -110,6 +122,7 @@ typedef struct {
     int32_t silu;          /* apply x*sigmoid(x) after the affine                                  */
     void*   y;
     float*  ws;
+    const float* stats0; const float* stats1;
 } tq_gn_desc;
 int tq_plan_add_groupnorm(tq_plan* p, const tq_gn_desc* d);
 

@@ -7,6 +7,7 @@ class FakeLib:
     def __init__(self):
         self.calls = []
         self.convs = []
+        self.gns = []
 
     def __getattr__(self, name):
         def fn(*args):
@@ -25,7 +26,10 @@ class FakeLib:
                     srcs=[(d.srcs[i].N, d.srcs[i].H, d.srcs[i].W, d.srcs[i].C, d.srcs[i].sn, d.srcs[i].sy, d.srcs[i].sx)
                           for i in range(d.num_srcs)],
                     out_strides=(d.out_sn, d.out_sy, d.out_sx), class_off=list(d.out_class_off), out_dtype=d.out_dtype,
-                    has_emb=bool(d.emb), has_res=bool(d.residual)))
+                    has_emb=bool(d.emb), has_res=bool(d.residual), stats=d.stats))
+            if name == "tq_plan_add_groupnorm":
+                d = args[1]._obj if hasattr(args[1], "_obj") else args[1].contents
+                self.gns.append(dict(N=d.N, P=d.P, C0=d.C0, C1=d.C1, stats0=d.stats0, stats1=d.stats1, ws=d.ws))
             if name == "tq_last_error":
                 return b""
             return 0

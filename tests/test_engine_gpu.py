@@ -105,7 +105,7 @@ def test_sample_reproduces_reference_rng_draw_order():
     n2 = torch.randn((2, 8, 32, 32), device="cuda", dtype=torch.float64, generator=gen2)
     b = edm.sample((2, 3, 128, 128), cond=g["cond"].cuda(), noise=n2)
     # GroupNorm statistics use fp32 atomics: runs agree to rounding, not bit-for-bit
-    assert rel_l2(a, b) < 1e-6
+    assert rel_l2(a, b) < 2e-5
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
@@ -193,4 +193,6 @@ def test_launch_accounting_counts_native_kernels():
     net(g["x"].cuda(), g["t"].cuda(), g["cond"].cuda())
     torch.cuda.synchronize()
     n = _lib.launch_count()
-    assert n > 150, n  # ~78 convs + 2*51 GroupNorm launches + 6 attention + embeddings + layout
+    # 65 convs (14 shortcuts fused) + 51 GroupNorm (statistics come from the conv epilogues) + 6 attention
+    # + embeddings + layout
+    assert 120 <= n <= 140, n

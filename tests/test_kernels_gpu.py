@@ -246,6 +246,60 @@ def test_groupnorm_silu_matches_torch(case, dtype):
     assert rel_l2(got, ref) < (4e-3 if dtype == torch.bfloat16 else 3e-6)
 
 
+FUSED_GN_CASES = [
+    # name, N, spatial, cin, cout, k, upsample  -- rows of one sample per epilogue warp: 32, 32, 16, 4, 32 (1D ragged)
+    ("32x32", 3, (32, 32), 64, 128, 3, False),
+    ("8x8", 5, (8, 8), 128, 256, 3, False),
+    ("4x4", 9, (4, 4), 128, 512, 3, False),
+    ("2x2", 7, (2, 2), 64, 64, 1, False),
+    ("1d_ragged", 2, (500,), 64, 64, 5, False),
+    ("up_2d", 3, (8, 8), 64, 128, 3, True),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("case", FUSED_GN_CASES, ids=[c[0] for c in FUSED_GN_CASES])
+def test_conv_epilogue_statistics_feed_groupnorm(case, dtype):
+    """The conv epilogue's per-(sample, channel) sums replace the GroupNorm statistics pass: statistics checked
+    directly, then GN(+SiLU) of the conv output -- alone and as the first half of a concat -- against torch."""
+    from tqdne_b200.engine import pack_conv
+
+    name, N, sp, cin, cout, k, up = case
+    g = torch.Generator(device="cuda").manual_seed(len(name) + cout)
+    dims = len(sp)
+    x = torch.randn(N, cin, *sp, device="cuda", generator=g)
+    w = torch.randn(cout, cin, *([k] * dims), device="cuda", generator=g) / math.sqrt(cin * k**dims)
+    b = torch.randn(cout, device="cuda", generator=g) * 0.5
+    plan = _plan(dtype)
+    y = plan.conv(pack_conv(w, b, [cin], dtype), [_act(x, dtype)], upsample=up, dims=dims, stats=True)
+    assert y.stats is not None
+    gamma = 1 + 0.1 * torch.randn(cout, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(cout, device="cuda", generator=g)
+    o1 = plan.groupnorm([y], gamma, beta, silu=True)
+    # second source of a concat: another conv output with its own statistics buffer
+    w2 = torch.randn(64, cin, *([1] * dims), device="cuda", generator=g) / math.sqrt(cin)
+    y2 = plan.conv(pack_conv(w2, None, [cin], dtype), [_act(x, dtype)], upsample=up, dims=dims, stats=True)
+    gamma2 = 1 + 0.1 * torch.randn(cout + 64, device="cuda", generator=g)
+    beta2 = 0.1 * torch.randn(cout + 64, device="cuda", generator=g)
+    o2 = plan.groupnorm([y, y2], gamma2, beta2, silu=False)
+    names = plan.op_names()
+    assert names[0] == "memset" and not any("gn_stats" in n for n in names)
+    for rep in range(2):  # a second run must start from a cleared arena again
+        plan.run()
+    torch.cuda.synchronize()
+    yn = _to_nchw(y, dims)           # the stored (rounded) conv output
+    flat = yn.reshape(N, cout, -1).double()
+    st = y.stats.reshape(N, cout, 2).double()
+    tol_s = 1e-5 if dtype == torch.float32 else 1e-4
+    assert rel_l2(st[..., 0], flat.sum(-1)) < 10 * tol_s   # sums of zero-mean data: looser relative bound
+    assert rel_l2(st[..., 1], (flat * flat).sum(-1)) < tol_s
+    tol = 4e-3 if dtype == torch.bfloat16 else 3e-6
+    ref1 = F.silu(F.group_norm(yn, 32, gamma, beta, eps=1e-5))
+    assert rel_l2(_to_nchw(o1, dims), ref1) < tol
+    ref2 = F.group_norm(torch.cat([yn, _to_nchw(y2, dims)], dim=1), 32, gamma2, beta2, eps=1e-5)
+    assert rel_l2(_to_nchw(o2, dims), ref2) < tol
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 @pytest.mark.parametrize("N,T,heads,d", [(3, 16, 4, 128), (2, 100, 4, 64), (1, 508, 4, 64), (2, 256, 2, 32)])
 def test_attention_matches_reference_formula(N, T, heads, d, dtype):

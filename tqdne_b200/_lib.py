@@ -11,6 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
+ABI_VERSION = 2  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -49,6 +50,7 @@ class TqConvDesc(C.Structure):
         ("out_sn", C.c_int64), ("out_sy", C.c_int64), ("out_sx", C.c_int64),
         ("out_class_off", C.c_int64 * 4),
         ("block_n", C.c_int32),
+        ("stats", C.c_void_p),
     ]
 
 
@@ -62,6 +64,7 @@ class TqGnDesc(C.Structure):
         ("silu", C.c_int32),
         ("y", C.c_void_p),
         ("ws", C.c_void_p),
+        ("stats0", C.c_void_p), ("stats1", C.c_void_p),
     ]
 
 
@@ -98,6 +101,7 @@ SIGNATURES = {
     "tq_plan_run_range": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "tq_plan_enable_graph": (C.c_int, [_VP, C.c_int]),
     "tq_plan_op_name": (C.c_char_p, [_VP, C.c_int]),
+    "tq_plan_add_memset": (C.c_int, [_VP, _VP, _I64, _I32]),
     "tq_plan_add_conv": (C.c_int, [_VP, C.POINTER(TqConvDesc)]),
     "tq_plan_add_groupnorm": (C.c_int, [_VP, C.POINTER(TqGnDesc)]),
     "tq_plan_add_attention": (C.c_int, [_VP, C.POINTER(TqAttnDesc)]),
@@ -135,7 +139,7 @@ def lib() -> C.CDLL:
             raise RuntimeError(f"tqdne_b200: {LIB_PATH} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
-    if handle.tq_abi_version() != 1:
+    if handle.tq_abi_version() != ABI_VERSION:
         raise RuntimeError("tqdne_b200: ABI version mismatch between _lib.py and libtqdne_b200.so")
     _lib = handle
     return handle

@@ -107,6 +107,20 @@ int tq_plan_enable_graph(tq_plan* p, int enable) {
     return 0;
 }
 
+int tq_plan_add_memset(tq_plan* p, void* ptr, int64_t bytes, int32_t at_front) {
+    TQ_CHECK(p && ptr && bytes > 0, "memset: bad arguments");
+    drop_graph(p);
+    Op op;
+    op.name = "memset";
+    op.launch = [ptr, bytes](cudaStream_t st) -> int {
+        TQ_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, st));
+        return 0;
+    };
+    if (at_front) p->ops.insert(p->ops.begin(), std::move(op));
+    else p->ops.push_back(std::move(op));
+    return 0;
+}
+
 int tq_plan_add_conv(tq_plan* p, const tq_conv_desc* d) {
     TQ_CHECK(p && d, "null argument");
     TQ_CHECK(d->slices != nullptr && d->weights != nullptr && d->out != nullptr, "conv: null pointer");

@@ -130,8 +130,105 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// T <= 32 (latent config: 4x4 = 16 tokens): one CTA per (sample, head) holds q, k, v and the T x T
+// probabilities in shared memory; no key blocking, no online softmax.
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        v[2 * k] = __low2float(b2);
+        v[2 * k + 1] = __high2float(b2);
+    }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(128) attention_small_kernel(const AttnParams p) {
+    extern __shared__ float sm[];
+    constexpr int PITCH = D + 1;
+    const int Tn = p.T;
+    float* Qs = sm;                  // [T][PITCH]
+    float* Ks = Qs + Tn * PITCH;     // [T][PITCH]
+    float* Vs = Ks + Tn * PITCH;     // [T][D]
+    float* Ps = Vs + Tn * D;         // [T][T+1]
+    const int C = p.heads * D;
+    const int ld = 3 * C;
+    const int h = blockIdx.x % p.heads;
+    const int n = blockIdx.x / p.heads;
+    const int tid = threadIdx.x;
+    const float scale = 1.f / sqrtf(sqrtf((float)D));
+    const T* base = static_cast<const T*>(p.qkv) + (long long)n * Tn * ld + h * D;
+    constexpr int VPR = D / 8;  // 16 B vectors per row
+    for (int i = tid; i < 3 * Tn * VPR; i += 128) {
+        const int which = i / (Tn * VPR);
+        const int r = (i / VPR) % Tn, vc = i % VPR;
+        float v[8];
+        ld8<T>(base + (long long)r * ld + which * C + vc * 8, v);
+        float* dst = which == 0 ? Qs + r * PITCH : (which == 1 ? Ks + r * PITCH : Vs + r * D);
+        const float sc = which == 2 ? 1.f : scale;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[vc * 8 + j] = v[j] * sc;
+    }
+    __syncthreads();
+    for (int i = tid; i < Tn * Tn; i += 128) {
+        const int qi = i / Tn, ki = i % Tn;
+        const float* q = Qs + qi * PITCH;
+        const float* k = Ks + ki * PITCH;
+        float a = 0.f;
+#pragma unroll 16
+        for (int c = 0; c < D; ++c) a = fmaf(q[c], k[c], a);
+        Ps[qi * (Tn + 1) + ki] = a;
+    }
+    __syncthreads();
+    if (tid < Tn) {
+        float* pr = Ps + tid * (Tn + 1);
+        float m = -INFINITY;
+        for (int k = 0; k < Tn; ++k) m = fmaxf(m, pr[k]);
+        float l = 0.f;
+        for (int k = 0; k < Tn; ++k) {
+            const float e = expf(pr[k] - m);
+            pr[k] = e;
+            l += e;
+        }
+        const float inv = 1.f / l;
+        for (int k = 0; k < Tn; ++k) pr[k] *= inv;
+    }
+    __syncthreads();
+    T* ob = static_cast<T*>(p.out) + (long long)n * Tn * C + h * D;
+    for (int i = tid; i < Tn * D; i += 128) {
+        const int qi = i / D, c = i % D;
+        const float* pr = Ps + qi * (Tn + 1);
+        float a = 0.f;
+        for (int k = 0; k < Tn; ++k) a = fmaf(pr[k], Vs[k * D + c], a);
+        st_f(ob + (long long)qi * C + c, a);
+    }
+}
+
 template <typename T, int D>
 int launch_attn(const AttnParams& p, cudaStream_t st) {
+    if (p.T <= 32) {
+        const size_t smem = (size_t)(2 * p.T * (D + 1) + p.T * D + p.T * (p.T + 1)) * sizeof(float);
+        static bool attr_small = false;
+        if (!attr_small) {
+            TQ_CUDA(cudaFuncSetAttribute(attention_small_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr_small = true;
+        }
+        attention_small_kernel<T, D><<<p.N * p.heads, 128, smem, st>>>(p);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    }
     const size_t smem = (size_t)(2 * KBLK * (D + 1) + QB * D + 4 * KBLK) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {

@@ -29,6 +29,7 @@ struct SimtParams {
     void* out;
     long long out_sn, out_sy, out_sx;
     long long out_class_off[4];
+    float* stats;  // [N][cout][2] or nullptr (same meaning as in the tensor-core kernel)
 };
 
 __device__ __forceinline__ float to_f(float v) { return v; }
@@ -107,7 +108,12 @@ __global__ void __launch_bounds__(256) igemm_simt_kernel(const SimtParams p) {
             if (p.emb) o += p.emb[(long long)n * p.emb_ld + c];
             if (p.residual) o += to_f(static_cast<const T*>(p.residual)[off + c]);
             if constexpr (OUT_F32) static_cast<float*>(p.out)[off + c] = o;
-            else static_cast<__nv_bfloat16*>(p.out)[off + c] = __float2bfloat16_rn(o);
+            else {
+                const __nv_bfloat16 ob = __float2bfloat16_rn(o);
+                static_cast<__nv_bfloat16*>(p.out)[off + c] = ob;
+                o = __bfloat162float(ob);
+            }
+            if (p.stats) atomicAdd(reinterpret_cast<float2*>(p.stats) + (long long)n * p.cout + c, make_float2(o, o * o));
         }
     }
 }
@@ -149,6 +155,8 @@ int build_conv_simt(std::vector<Op>& ops, const tq_conv_desc& d) {
     p->residual = d.residual; p->out = d.out;
     p->out_sn = d.out_sn; p->out_sy = d.out_sy; p->out_sx = d.out_sx;
     for (int i = 0; i < 4; ++i) p->out_class_off[i] = d.out_class_off[i];
+    p->stats = d.stats;
+    TQ_CHECK(d.stats == nullptr || (reinterpret_cast<uintptr_t>(d.stats) & 7) == 0, "conv statistics buffer must be 8 B aligned");
 
     dim3 grid((unsigned)((p->M + 63) / 64), (unsigned)(d.cout_pad / 64), (unsigned)d.num_classes);
     TQ_CHECK(grid.y <= 65535, "too many output channels for the simt grid");

@@ -51,6 +51,8 @@ struct alignas(64) IgemmParams {
     void* out;
     long long out_sn, out_sy, out_sx;
     long long out_class_off[4];
+    float* stats;  // [N][cout][2] per-(sample, channel) sum / sum of squares, or nullptr
+    int seg;       // rows of one sample inside an epilogue warp: min(32, bw*bh)
 };
 
 template <int BN>
@@ -223,19 +225,19 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                     mbar_arrive(tempty_bar(acc));
                 }
                 const int cg = t.n_tile * BN + c;
-                if (!valid || cg >= p.cout) continue;
+                if (cg >= p.cout) continue;  // warp-uniform: zero-padded weight rows
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c + j];
                 if (p.vec_ok) {
-                    if (emb_row) {
+                    if (valid && emb_row) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 e = __ldg(reinterpret_cast<const float4*>(emb_row + cg + j));
                             v[j] += e.x; v[j + 1] += e.y; v[j + 2] += e.z; v[j + 3] += e.w;
                         }
                     }
-                    if (p.residual) {
+                    if (valid && p.residual) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + cg);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -250,23 +252,68 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                         }
                     }
                     if constexpr (OUT_F32) {
-                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + cg);
+                        if (valid) {
+                            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + cg);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int j = 0; j < 8; ++j)
+                                op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
                     } else {
-                        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + cg);
+                        uint32_t w[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t w[4];
+                        for (int k = 0; k < 16; ++k) {
+                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                            w[k] = *reinterpret_cast<const uint32_t*>(&b2);
+                            // the statistics describe the tensor as stored (bf16-rounded)
+                            v[2 * k] = __low2float(b2);
+                            v[2 * k + 1] = __high2float(b2);
+                        }
+                        if (valid) {
+                            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + cg);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j * 8 + 2 * k], v[j * 8 + 2 * k + 1]);
-                                w[k] = *reinterpret_cast<const uint32_t*>(&b2);
-                            }
-                            op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                            for (int j = 0; j < 4; ++j) op[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
                         }
                     }
-                } else {
+                    if (p.stats != nullptr) {
+                        // GroupNorm statistics of the consumer, fused here: per-(sample, channel) sum and
+                        // sum of squares over this warp's rows.  Recursive halving across lanes: every step
+                        // trades half of the channels with the partner lane, so after log2(seg) steps a lane
+                        // owns 32/seg channels summed over the seg rows of its sample.
+                        float q[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            v[j] = valid ? v[j] : 0.f;
+                            q[j] = v[j] * v[j];
+                        }
+                        int cb = 0;
+#pragma unroll
+                        for (int s = 0; s < 5; ++s) {
+                            const int nh = 16 >> s;
+                            const int o = p.seg >> (s + 1);
+                            if (o == 0) break;
+                            const bool upper = (lane & o) != 0;
+                            cb += upper ? nh : 0;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (j < nh) {
+                                    const float sv = upper ? v[j] : v[j + nh];
+                                    const float kv = upper ? v[j + nh] : v[j];
+                                    const float sq = upper ? q[j] : q[j + nh];
+                                    const float kq = upper ? q[j + nh] : q[j];
+                                    v[j] = kv + __shfl_xor_sync(0xffffffffu, sv, o);
+                                    q[j] = kq + __shfl_xor_sync(0xffffffffu, sq, o);
+                                }
+                            }
+                        }
+                        const int cnt = 32 / p.seg;
+                        if (n < p.N) {
+                            float2* sp = reinterpret_cast<float2*>(p.stats) + (long long)n * p.cout + cg + cb;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < cnt) atomicAdd(sp + j, make_float2(v[j], q[j]));
+                        }
+                    }
+                } else if (valid) {
                     // ragged / unaligned edge (Cout in {3, 6, 8}): scalar path
 #pragma unroll 1
                     for (int j = 0; j < 32; ++j) {
@@ -438,6 +485,13 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     if (d.residual) vec = vec && (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0 && d.out_sn % 8 == 0 &&
                           d.out_sy % 8 == 0 && d.out_sx % 8 == 0;
     p->vec_ok = vec ? 1 : 0;
+    p->stats = d.stats;
+    {
+        const int rows = p->bw * p->bh;
+        p->seg = rows < 32 ? rows : 32;
+    }
+    TQ_CHECK(d.stats == nullptr || (vec && (reinterpret_cast<uintptr_t>(d.stats) & 7) == 0),
+             "conv statistics need a vectorisable epilogue (cout %% 32 == 0, aligned strides) and an 8 B aligned buffer");
 
     const int grid = p->total_tiles < device_sm_count() ? p->total_tiles : device_sm_count();
     const bool f32 = d.out_dtype == TQ_F32;

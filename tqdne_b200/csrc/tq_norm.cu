@@ -3,9 +3,12 @@
 // computed in fp32) followed by nn.SiLU (tqdne/unet.py:85-88,100-103), input optionally
 // th.cat([h, skip], dim=1) (tqdne/unet.py:396) -- the concat is never materialised before the norm.
 //
-// HBM-bound, two launches: (1) per-(sample, channel) sum / sum-of-squares with 16 B vector loads,
-// block-level reduction and one fp32 atomic per channel per block; (2) affine + SiLU streaming pass.
-// Per-channel partials make groups that straddle the concat boundary (C = 768, 384, 192) free.
+// HBM-bound.  The per-(sample, channel) sum / sum-of-squares normally arrive from the epilogue of the
+// convolution that produced the tensor (tq_conv_desc.stats), so the norm is ONE streaming pass:
+// affine + SiLU, 16 B vector loads, four independent loads in flight per thread.  A stand-alone
+// statistics pass (block reduction + one fp32 atomic per channel per block) remains for inputs that
+// did not come out of a conv.  Per-channel partials make groups that straddle the concat boundary
+// (C = 768, 384, 192) free.
 #include <cuda_bf16.h>
 
 #include <memory>
@@ -25,6 +28,8 @@ struct GnParams {
     int silu;
     void* y;
     float* ws;  // [N][C0+C1][2]
+    const float* st0;  // [N][C0][2]  (== ws when the statistics pass ran)
+    const float* st1;  // [N][C1][2]
     int chunks;
 };
 
@@ -104,20 +109,29 @@ template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const GnParams p) {
     __shared__ float red[256 * 17];
     const int n = blockIdx.y, chunk = blockIdx.x;
-    float* ws_n = p.ws + (long long)n * (p.C0 + p.C1) * 2;
-    stats_one_source<T>(static_cast<const T*>(p.x0), p.C0, p.P, n, chunk, p.chunks, ws_n, red);
-    if (p.C1 > 0) stats_one_source<T>(static_cast<const T*>(p.x1), p.C1, p.P, n, chunk, p.chunks, ws_n + 2 * p.C0, red);
+    // scratch layout: [N][C0][2] followed by [N][C1][2] (the layout a producing conv writes per tensor)
+    float* ws0 = p.ws + (long long)n * p.C0 * 2;
+    float* ws1 = p.ws + (long long)p.N * p.C0 * 2 + (long long)n * p.C1 * 2;
+    stats_one_source<T>(static_cast<const T*>(p.x0), p.C0, p.P, n, chunk, p.chunks, ws0, red);
+    if (p.C1 > 0) stats_one_source<T>(static_cast<const T*>(p.x1), p.C1, p.P, n, chunk, p.chunks, ws1, red);
 }
 
 template <typename T>
 __device__ __forceinline__ float silu_f(float v) {
     if constexpr (sizeof(T) == 4) return v / (1.f + expf(-v));
-    else return v / (1.f + __expf(-v));
+    else {
+        // x * sigmoid(x) = 0.5 x (1 + tanh(x / 2)): one MUFU op; its 2^-11 error is below bf16 rounding
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+        return v * fmaf(0.5f, t, 0.5f);
+    }
 }
 
+constexpr int GN_UNROLL = 4;
+
 template <typename T>
-__device__ void apply_one_source(const T* x, int C, int cbase, int Ct, int P, int n, int chunk, int chunks, T* y,
-                                 const float* ab, int silu) {
+__device__ __forceinline__ void apply_one_source(const T* __restrict__ x, int C, int cbase, int Ct, int P, int n, int chunk,
+                                                 int chunks, T* __restrict__ y, const float* ab, int silu) {
     const int cv = C >> 3;
     const int lanes = 256 / cv;
     const int tid = threadIdx.x;
@@ -133,7 +147,22 @@ __device__ void apply_one_source(const T* x, int C, int cbase, int Ct, int P, in
     }
     const T* xb = x + ((long long)n * P) * C + vi * 8;
     T* yb = y + ((long long)n * P) * Ct + cbase + vi * 8;
-    for (int pix = p0 + pl; pix < p1; pix += lanes) {
+    int pix = p0 + pl;
+    for (; pix + (GN_UNROLL - 1) * lanes < p1; pix += GN_UNROLL * lanes) {
+        float v[GN_UNROLL][8];
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) load8<T>(xb + (long long)(pix + u * lanes) * C, v[u]);
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[u][j] = fmaf(v[u][j], a[j], b[j]);
+                if (silu) v[u][j] = silu_f<T>(v[u][j]);
+            }
+            store8(yb + (long long)(pix + u * lanes) * Ct, v[u]);
+        }
+    }
+    for (; pix < p1; pix += lanes) {
         float v[8];
         load8<T>(xb + (long long)pix * C, v);
 #pragma unroll
@@ -152,20 +181,30 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
     const int Ct = p.C0 + p.C1;
     const int cpg = Ct / 32;
     float* gstat = ab + 2 * Ct;
-    const float* ws_n = p.ws + (long long)n * Ct * 2;
-    if (threadIdx.x < 32) {
-        const int g = threadIdx.x;
+    const float* s0 = p.st0 + (long long)n * p.C0 * 2;
+    const float* s1 = p.st1 ? p.st1 + (long long)n * p.C1 * 2 : nullptr;
+    {
+        // 8 threads per group: strided partial sums over the group's channels, then a 3-step shuffle
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
         float s = 0.f, ss = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            s += ws_n[2 * c];
-            ss += ws_n[2 * c + 1];
+        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
+            const float* q = c < p.C0 ? s0 + 2 * c : s1 + 2 * (c - p.C0);
+            s += q[0];
+            ss += q[1];
         }
-        const float inv = 1.f / ((float)cpg * (float)p.P);
-        const float mean = s * inv;
-        float var = ss * inv - mean * mean;
-        var = var < 0.f ? 0.f : var;
-        gstat[2 * g] = mean;
-        gstat[2 * g + 1] = 1.f / sqrtf(var + p.eps);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (sub == 0) {
+            const float inv = 1.f / ((float)cpg * (float)p.P);
+            const float mean = s * inv;
+            float var = ss * inv - mean * mean;
+            var = var < 0.f ? 0.f : var;
+            gstat[2 * g] = mean;
+            gstat[2 * g + 1] = 1.f / sqrtf(var + p.eps);
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < Ct; c += 256) {
@@ -188,12 +227,18 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
     TQ_CHECK(d.C0 > 0 && d.C0 % 8 == 0 && d.C1 % 8 == 0 && d.C1 >= 0, "groupnorm: channel counts must be multiples of 8");
     TQ_CHECK(Ct % 32 == 0, "groupnorm: 32 groups need C %% 32 == 0 (C=%d)", Ct);
     TQ_CHECK(d.C0 <= 2048 && d.C1 <= 2048, "groupnorm: at most 2048 channels per source");
-    TQ_CHECK(d.x0 && d.y && d.ws && d.gamma && d.beta, "groupnorm: null pointer");
+    TQ_CHECK(d.x0 && d.y && d.gamma && d.beta, "groupnorm: null pointer");
     TQ_CHECK(d.C1 == 0 || d.x1, "groupnorm: second source missing");
+    const bool have_stats = d.stats0 != nullptr;
+    TQ_CHECK(have_stats || d.ws, "groupnorm: neither producer statistics nor a scratch buffer given");
+    TQ_CHECK(!have_stats || d.C1 == 0 || d.stats1, "groupnorm: statistics of the second source missing");
+    TQ_CHECK(have_stats || !d.stats1, "groupnorm: statistics of the first source missing");
     auto p = std::make_shared<GnParams>();
     p->x0 = d.x0; p->x1 = d.x1; p->N = d.N; p->P = d.P; p->C0 = d.C0; p->C1 = d.C1;
     p->gamma = d.gamma; p->beta = d.beta; p->eps = d.eps; p->silu = d.silu; p->y = d.y; p->ws = d.ws;
-    int chunks = (4 * device_sm_count() + d.N - 1) / d.N;
+    p->st0 = have_stats ? d.stats0 : d.ws;
+    p->st1 = have_stats ? d.stats1 : (d.C1 > 0 ? d.ws + (size_t)d.N * d.C0 * 2 : nullptr);
+    int chunks = (8 * device_sm_count() + d.N - 1) / d.N;
     const int max_chunks = (d.P + 31) / 32;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
@@ -203,17 +248,19 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
     const size_t smem = (size_t)(2 * Ct + 64) * sizeof(float);
     dim3 grid(chunks, d.N);
 
-    Op st;
-    st.name = f32 ? "gn_stats<f32>" : "gn_stats<bf16>";
-    st.launch = [p, grid, f32, ws_bytes](cudaStream_t s) -> int {
-        TQ_CUDA(cudaMemsetAsync(p->ws, 0, ws_bytes, s));
-        if (f32) gn_stats_kernel<float><<<grid, 256, 0, s>>>(*p);
-        else gn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(*p);
-        TQ_CUDA(cudaGetLastError());
-        count_launch();
-        return 0;
-    };
-    ops.push_back(std::move(st));
+    if (!have_stats) {
+        Op st;
+        st.name = f32 ? "gn_stats<f32>" : "gn_stats<bf16>";
+        st.launch = [p, grid, f32, ws_bytes](cudaStream_t s) -> int {
+            TQ_CUDA(cudaMemsetAsync(p->ws, 0, ws_bytes, s));
+            if (f32) gn_stats_kernel<float><<<grid, 256, 0, s>>>(*p);
+            else gn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(*p);
+            TQ_CUDA(cudaGetLastError());
+            count_launch();
+            return 0;
+        };
+        ops.push_back(std::move(st));
+    }
     Op ap;
     ap.name = f32 ? "gn_apply<f32>" : "gn_apply<bf16>";
     ap.launch = [p, grid, f32, smem](cudaStream_t s) -> int {

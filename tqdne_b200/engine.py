@@ -145,6 +145,7 @@ class Act:
     H: int
     W: int
     C: int
+    stats: torch.Tensor | None = None   # [N, C, 2] fp32 per-(sample, channel) sum / sum of squares (conv epilogue)
 
     @property
     def P(self) -> int:
@@ -190,6 +191,8 @@ class Plan:
         self.pool = Pool(device, act_dtype)
         self.keep: list = []
         self.gn_ws = None
+        self._stats_block = None   # bump-allocated arena of conv-epilogue GroupNorm statistics
+        self._stats_used = 0
         # one entry per kernel launch of the plan: (kind, algorithmic FLOPs, algorithmic HBM bytes)
         self.op_meta: list[tuple] = []
 
@@ -209,6 +212,23 @@ class Plan:
     def release(self, a: Act) -> None:
         self.pool.put(a.t)
 
+    STATS_BLOCK_FLOATS = 4 << 20  # 16 MiB per arena block
+
+    def _stats_alloc(self, nfloats: int) -> torch.Tensor:
+        """Statistics buffers are unique per producing conv (never pooled) and live in a few arena blocks, each
+        cleared by ONE memset op placed at the front of the plan."""
+        nfloats = (nfloats + 3) // 4 * 4
+        if self._stats_block is None or self._stats_used + nfloats > self._stats_block.numel():
+            size = max(self.STATS_BLOCK_FLOATS, nfloats)
+            self._stats_block = torch.zeros(size, device=self.device, dtype=torch.float32)
+            self._stats_used = 0
+            self.keep.append(self._stats_block)
+            _lib.check(self.lib.tq_plan_add_memset(self.h, self._stats_block.data_ptr(), size * 4, 1), "plan_add_memset")
+            self.op_meta.insert(0, ("memset", 0, 0))
+        v = self._stats_block[self._stats_used:self._stats_used + nfloats]
+        self._stats_used += nfloats
+        return v
+
     def _gn_scratch(self, nfloats: int) -> torch.Tensor:
         if self.gn_ws is None or self.gn_ws.numel() < nfloats:
             self.gn_ws = torch.empty(nfloats, device=self.device, dtype=torch.float32)
@@ -218,8 +238,9 @@ class Plan:
     # -- ops ------------------------------------------------------------------------------------
     def conv(self, pc: PackedConv, srcs: list[Act], *, out: Act | None = None, out_dtype=None, stride: int = 1,
              upsample: bool = False, emb: torch.Tensor | None = None, emb_ld: int = 0, residual: Act | None = None,
-             shortcut_srcs: list[Act] | None = None, block_n: int = 0, dims: int = 2) -> Act:
-        """Append one implicit-GEMM conv.  `srcs` are the concat segments of the conv input."""
+             shortcut_srcs: list[Act] | None = None, block_n: int = 0, dims: int = 2, stats: bool = False) -> Act:
+        """Append one implicit-GEMM conv.  `srcs` are the concat segments of the conv input.  `stats`: also
+        accumulate the per-(sample, channel) GroupNorm sums of the output in the epilogue."""
         N, H, W = srcs[0].N, srcs[0].H, srcs[0].W
         assert len(srcs) == len(pc.seg_pad)
         kh, kw = pc.kernel
@@ -330,6 +351,9 @@ class Plan:
         for i in range(4):
             d.out_class_off[i] = class_off[i]
         d.block_n = block_n
+        if stats and pc.cout % 32 == 0:
+            out.stats = self._stats_alloc(N * pc.cout * 2)
+            d.stats = out.stats.data_ptr()
         _lib.check(self.lib.tq_plan_add_conv(self.h, C.byref(d)), "plan_add_conv")
         self.op_meta.append(("conv", 2 * N * Ho * Wo * pc.cout * pc.macs_per_out, 0))
         self.keep += [pc.weights, pc.bias, emb, out.t] + [v[0] for v in src_views]
@@ -353,11 +377,17 @@ class Plan:
         d.eps = GN_EPS
         d.silu = 1 if silu else 0
         d.y = out.t.data_ptr()
-        d.ws = self._gn_scratch(2 * a0.N * 2048).data_ptr() if Ct <= 2048 else self._gn_scratch(2 * a0.N * Ct).data_ptr()
+        fused = a0.stats is not None and (a1 is None or a1.stats is not None)
+        if fused:
+            d.stats0 = a0.stats.data_ptr()
+            d.stats1 = a1.stats.data_ptr() if a1 else None
+        else:
+            d.ws = self._gn_scratch(2 * a0.N * max(Ct, 2048)).data_ptr()
         _lib.check(self.lib.tq_plan_add_groupnorm(self.h, C.byref(d)), "plan_add_groupnorm")
         esz = a0.t.element_size()
         nel = a0.N * a0.P * Ct
-        self.op_meta.append(("gn_stats", 0, nel * esz))          # one read
+        if not fused:
+            self.op_meta.append(("gn_stats", 0, nel * esz))      # one read
         self.op_meta.append(("gn_apply", 0, 2 * nel * esz))      # one read + one write
         self.keep += [g, b, a0.t, out.t] + ([a1.t] if a1 else [])
         return out

@@ -75,19 +75,19 @@ class Lowerer:
         gn2, conv2 = blk.out_layers[0], blk.out_layers[3]
         h0 = plan.groupnorm(srcs, gn1.weight, gn1.bias, silu=True)
         e = emb[:, emb_off:] if emb is not None else None
-        h1 = self.conv(conv1, [h0], emb=e, emb_ld=emb_ld)
+        h1 = self.conv(conv1, [h0], emb=e, emb_ld=emb_ld, stats=True)
         plan.release(h0)
         h2 = plan.groupnorm([h1], gn2.weight, gn2.bias, silu=True)
         plan.release(h1)
         skip = blk.skip_connection
         if isinstance(skip, nn.Identity):
             assert len(srcs) == 1
-            out = self.conv(conv2, [h2], residual=srcs[0])
+            out = self.conv(conv2, [h2], residual=srcs[0], stats=True)
         else:
             if skip.weight[0, 0].numel() != 1:
                 raise NotImplementedError("tqdne_b200: ResBlock(use_conv=True) spatial shortcut is not lowered")
             # out = conv2(h2) + skip_1x1(cat(srcs)): one GEMM, K = taps*Cout + sum(Cin segments)
-            out = self.conv(conv2, [h2], shortcut=skip, shortcut_srcs=srcs)
+            out = self.conv(conv2, [h2], shortcut=skip, shortcut_srcs=srcs, stats=True)
         plan.release(h2)
         if free_inputs:
             for a in srcs:
@@ -103,19 +103,19 @@ class Lowerer:
         a = plan.attention(qkv, heads)
         self.flops += 4 * x.N * x.P * x.P * x.C  # QK^T and PV, 2*MAC each
         plan.release(qkv)
-        out = self.conv(blk.proj_out, [a], residual=x)
+        out = self.conv(blk.proj_out, [a], residual=x, stats=True)
         plan.release(a)
         if free_input:
             plan.release(x)
         return out
 
     def downsample(self, blk: B.Downsample, x: Act) -> Act:
-        return self.conv(blk.op, [x])
+        return self.conv(blk.op, [x], stats=True)
 
     def upsample(self, blk: B.Upsample, x: Act, free_input: bool) -> Act:
         if not blk.use_conv:
             raise NotImplementedError("tqdne_b200: Upsample(use_conv=False) is not lowered")
-        out = self.conv(blk.conv, [x], upsample=True)
+        out = self.conv(blk.conv, [x], upsample=True, stats=True)
         if free_input:
             self.plan.release(x)
         return out
@@ -204,7 +204,7 @@ class UNetPlan:
                 elif isinstance(layer, B.Upsample):
                     o = low.upsample(layer, cur[0], fi)
                 elif isinstance(layer, (nn.Conv1d, nn.Conv2d)):
-                    o = low.conv(layer, cur, segments=[layer.weight.shape[1]])
+                    o = low.conv(layer, cur, segments=[layer.weight.shape[1]], stats=True)
                 else:
                     raise NotImplementedError(f"tqdne_b200: cannot lower {type(layer).__name__}")
                 cur = [o]
@@ -301,7 +301,7 @@ class CoderPlan:
         cin = net.input_layer.weight.shape[1]
         self.cin, self.cin_pad = cin, (cin + 63) // 64 * 64
         self.xin = Act(torch.zeros(N * H * W * self.cin_pad, device=dev, dtype=act_dtype), N, H, W, self.cin_pad)
-        h = low.conv(net.input_layer, [self.xin], segments=[cin])
+        h = low.conv(net.input_layer, [self.xin], segments=[cin], stats=True)
         seq = net.down_blocks if kind == "encoder" else net.up_blocks
         for layer in seq:
             if isinstance(layer, B.ResBlock):
