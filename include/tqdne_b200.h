@@ -100,7 +100,9 @@ typedef struct {
                                * the epilogue (feeds tq_gn_desc.stats0/1 of the consuming          *
                                * GroupNorm: the normalisation never re-reads the tensor for its    *
                                * statistics).  The caller zeroes it before the conv runs           *
-                               * (tq_plan_add_memset).  Needs cout % 32 == 0.                      */
+                               * (tq_plan_add_memset).  bf16 outputs only.                         */
+    int32_t cta_group;        /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row   *
+                               * tile (tcgen05.mma.cta_group::2)                                    */
 } tq_conv_desc;
 int tq_plan_add_conv(tq_plan* p, const tq_conv_desc* d);
 

@@ -102,8 +102,9 @@ def test_conv_matches_torch(case, dtype):
     assert rel_l2(_to_nchw(out, dims), ref) < tol
 
 
+@pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("block_n", [64, 128, 256])
-def test_conv_block_n_variants_fp32_out(block_n):
+def test_conv_block_n_variants_fp32_out(block_n, cta_group):
     from tqdne_b200.engine import pack_conv
 
     g = torch.Generator(device="cuda").manual_seed(block_n)
@@ -112,7 +113,7 @@ def test_conv_block_n_variants_fp32_out(block_n):
     b = torch.randn(256, device="cuda", generator=g) * 0.1
     plan = _plan(torch.bfloat16)
     out = plan.conv(pack_conv(w, b, [128], torch.bfloat16), [_act(x, torch.bfloat16)], out_dtype=torch.float32,
-                    block_n=block_n)
+                    block_n=block_n, cta_group=cta_group)
     plan.run()
     torch.cuda.synchronize()
     ref = _ref_conv(_rt(x, torch.bfloat16), _rt(w, torch.bfloat16), b)
@@ -176,6 +177,41 @@ def test_conv_residual_and_ragged_fp32_output(dtype):
     assert rel_l2(_to_nchw(y, 2), _ref_conv(xr, _rt(w, dtype), b) + xr) < tol
     assert rel_l2(_to_nchw(y8, 2), _ref_conv(xr, _rt(w8, dtype), b8)) < (2e-5 if dtype == torch.bfloat16 else 1e-5)
     assert rel_l2(_to_nchw(ys, 2), _ref_conv(_rt(x8, dtype), _rt(ws, dtype), None)) < tol
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+@pytest.mark.parametrize("shape", [(5, (8, 8)), (2, (32, 32)), (9, (4, 4)), (3, (300,))], ids=["8x8_oddtiles", "32x32", "4x4", "1d_ragged"])
+def test_conv_tile_configs_bf16_epilogue(block_n, cta_group, shape):
+    """Every (BN, CTA-group) instantiation of the tensor-core kernel with the full bf16 epilogue: bias + per-sample
+    embedding + residual (TMA in), TMA store out, fused GroupNorm statistics; odd tile counts leave the second CTA
+    of the last pair without rows."""
+    from tqdne_b200.engine import pack_conv
+
+    N, sp = shape
+    dims = len(sp)
+    g = torch.Generator(device="cuda").manual_seed(block_n + cta_group + N)
+    cin = cout = 256
+    x = torch.randn(N, cin, *sp, device="cuda", generator=g)
+    w = torch.randn(cout, cin, *([3] * dims), device="cuda", generator=g) / math.sqrt(cin * 3**dims)
+    b = torch.randn(cout, device="cuda", generator=g) * 0.2
+    emb = torch.randn(N, 512, device="cuda", generator=g)
+    plan = _plan(torch.bfloat16)
+    xa = _act(x, torch.bfloat16)
+    y = plan.conv(pack_conv(w, b, [cin], torch.bfloat16), [xa], residual=xa, emb=emb[:, 128:], emb_ld=512, dims=dims,
+                  block_n=block_n, cta_group=cta_group, stats=True)
+    plan.run()
+    torch.cuda.synchronize()
+    assert f"BN={block_n},CG={cta_group}" in plan.op_names()[-1]
+    xr = _rt(x, torch.bfloat16)
+    e = emb[:, 128:128 + cout]
+    ref = _ref_conv(xr, _rt(w, torch.bfloat16), b) + e[(...,) + (None,) * dims] + xr
+    yn = _to_nchw(y, dims)
+    assert rel_l2(yn, ref) < 5e-3
+    flat = yn.reshape(N, cout, -1).double()
+    st = y.stats.reshape(N, cout, 2).double()
+    assert rel_l2(st[..., 0], flat.sum(-1)) < 1e-4
+    assert rel_l2(st[..., 1], (flat * flat).sum(-1)) < 1e-4
 
 
 def test_linear_as_1x1_conv_on_tensor_path():

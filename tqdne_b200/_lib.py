@@ -51,6 +51,7 @@ class TqConvDesc(C.Structure):
         ("out_class_off", C.c_int64 * 4),
         ("block_n", C.c_int32),
         ("stats", C.c_void_p),
+        ("cta_group", C.c_int32),
     ]
 
 

@@ -3,17 +3,31 @@
 // One persistent, warp-specialised kernel covers every dense contraction of the denoiser and decoder
 // (reference: nn.Conv1d/Conv2d from tqdne/nn.py:16-24 at the call sites listed in include/tqdne_b200.h):
 //
-//   D[128 positions, BN channels] += A_slice[128, 64] * W_slice[BN, 64]^T   for every K-slice
+//   D[128*CG positions, BN channels] += A_slice[128*CG, 64] * W_slice[BN, 64]^T   for every K-slice
 //
-//   warp 0   TMA producer : per slice one 4-D box load of the shifted input window (zero fill outside
-//                           the image = "same" padding) + one 2-D box load of the weight block, both
-//                           landing in 128B-swizzled shared memory, completion on an mbarrier
-//   warp 1   MMA issuer   : one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per slice into a TMEM
-//                           accumulator; tcgen05.commit releases the smem stage / publishes the tile
-//   warp 2   TMEM allocator (2*BN columns: the accumulator is double buffered so the epilogue of tile
-//                           i overlaps the MMAs of tile i+1)
-//   warps 4-7 epilogue     : tcgen05.ld the accumulator (lane = output position), add bias, per-sample
-//                           embedding and residual, convert and store channels-last
+// CG = 2 runs a CTA PAIR (cluster of two SMs) on one 256 x BN tile with tcgen05.mma.cta_group::2: each CTA
+// stages its own 128 activation rows and only HALF of the weight rows, so the shared-memory fill and the
+// operand reads per SM drop by a quarter to a third compared with two independent 128 x BN tiles -- the
+// resource that bounds this kernel (the operand tiles are streamed from L2 for every tap).
+//
+//   warp 0   TMA producer : per slice one 4-D box load of the shifted input window (zero fill outside the
+//                           image = "same" padding) + one 2-D box load of the weight block, both landing in
+//                           128B-swizzled shared memory; transaction bytes of both CTAs complete on the
+//                           leader's mbarrier
+//   warp 1   MMA issuer   : (leader CTA) one thread issues tcgen05.mma (M=128*CG, N=BN, K=16) x4 per slice
+//                           into a TMEM accumulator; tcgen05.commit (multicast to the pair) releases the
+//                           smem stage / publishes the tile
+//   warp 2   TMEM allocator (2*BN columns: the accumulator is double buffered so the epilogue of tile i
+//                           overlaps the MMAs of tile i+1)
+//   warps 4-11 epilogue   : 8 warps = 4 TMEM lane quarters x 2 column halves.  bf16 outputs go through a
+//                           per-warp 32-row x 64-channel staging buffer in shared memory: the residual
+//                           arrives there by TMA (issued before the accumulator is ready), the warp adds
+//                           bias / per-sample embedding / residual to its tcgen05.ld rows in place, and the
+//                           result leaves by TMA store (coalesced, clipped at the tensor edge, asynchronous).
+//                           The GroupNorm statistics of the consumer (per-(sample, channel) sum and sum of
+//                           squares) are column sums over the same staging buffer + one float4 atomic per
+//                           lane.  fp32 outputs (embedding GEMM, the two ragged Cout in {3, 8} convs) use
+//                           direct stores.
 //
 // Activations are channels-last, so the 128x64 A tile of a slice is the TMA box
 // {64 ch, bw, bh, bn} of the [N,H,W,C] tensor with bw*bh*bn = 128: rows of 128 B, K-major,
@@ -33,17 +47,23 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int EPI_BUF_BYTES = 32 * 64 * 2;  // one epilogue unit: 32 rows x 64 bf16 channels
+constexpr int MAX_SMEM = 232448;            // 227 KiB opt-in limit per CTA
 
 struct alignas(64) IgemmParams {
     CUtensorMap amap[4];
     CUtensorMap bmap;
+    CUtensorMap omap[4];  // bf16 output per parity class, box = one epilogue unit
+    CUtensorMap rmap;     // residual, same geometry as omap[0]
     const int4* slices;
     int num_slices, num_classes;
     int N, H, W, bw, bh, bn;
-    int tiles_x, tiles_y, m_tiles, n_tiles, total_tiles;
+    int tiles_x, tiles_y, m_tiles, m_groups, n_tiles, total_tiles;
     int cout;
-    int vec_ok;
+    int vec_ok;   // fp32 direct-store path only
+    int has_res;  // residual comes in through rmap (bf16 path)
     const float* bias;
     const float* emb;
     int emb_ld;
@@ -55,29 +75,34 @@ struct alignas(64) IgemmParams {
     int seg;       // rows of one sample inside an epilogue warp: min(32, bw*bh)
 };
 
-template <int BN>
+template <int BN, int CG>
 struct Cfg {
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int BNC = BN / CG;  // weight rows staged per CTA
+    static constexpr int B_BYTES = BNC * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int UNITS = BN >= 128 ? BN / 128 : 1;  // 64-channel groups per epilogue warp
+    static constexpr int EPI_BYTES = kEpiWarps * UNITS * EPI_BUF_BYTES;
+    static constexpr int AUX_BYTES = 512;
+    static constexpr int STAGES_FIT = (MAX_SMEM - 1024 - EPI_BYTES - AUX_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
-    static constexpr int AUX_BYTES = (2 * STAGES + 4) * 8 + 16 + BN * 4;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + AUX_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + AUX_BYTES;
+    static_assert(STAGES >= 3, "pipeline too shallow");
+    static_assert((2 * STAGES + 4 + kEpiWarps) * 8 + 16 <= AUX_BYTES, "aux region too small");
 };
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 struct TileCoord {
     int cls, n_tile, x0, y0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+// pair-level tile index -> coordinates of THIS CTA's 128-row tile (rank selects the half of the 256-row tile)
+template <int CG>
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile, int rank) {
     TileCoord t;
     t.n_tile = tile % p.n_tiles;
     int r = tile / p.n_tiles;
-    int m_tile = r % p.m_tiles;
-    t.cls = r / p.m_tiles;
+    const int m_group = r % p.m_groups;
+    t.cls = r / p.m_groups;
+    const int m_tile = m_group * CG + rank;  // may be == m_tiles (odd count): all rows out of range
     int tx = m_tile % p.tiles_x;
     int r2 = m_tile / p.tiles_x;
     int ty = r2 % p.tiles_y;
@@ -88,27 +113,49 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
     return t;
 }
 
-template <int BN, bool OUT_F32>
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+template <int BN, int CG, bool OUT_F32>
 __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_constant__ IgemmParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
-    uint8_t* aux = smem_raw + (base - raw_addr) + C::STAGES * C::STAGE_BYTES;
-    const uint32_t bar0 = base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t epi_base = base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t bar0 = epi_base + C::EPI_BYTES;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + a); };
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + 2 + a); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(aux + (2 * C::STAGES + 4) * 8);
-    float* bias_s = reinterpret_cast<float*>(aux + (2 * C::STAGES + 4) * 8 + 16);
+    auto res_bar = [&](int w) { return bar0 + 8u * (2 * C::STAGES + 4 + w); };
+    const uint32_t slot_off = (bar0 - raw_addr) + 8u * (2 * C::STAGES + 4 + kEpiWarps);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + slot_off);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = blockIdx.x / CG;
+    const int num_clusters = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.amap[i]);
         tma_prefetch_desc(&p.bmap);
+        if constexpr (!OUT_F32) {
+            tma_prefetch_desc(&p.omap[0]);
+            if (p.has_res) tma_prefetch_desc(&p.rmap);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -117,26 +164,29 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 128);
+            mbar_init(tempty_bar(a), CG * kEpiWarps);
         }
+        for (int w = 0; w < kEpiWarps; ++w) mbar_init(res_bar(w), 1);
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
-        tmem_relinquish();
+        tmem_alloc_cg<CG>(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
+        tmem_relinquish_cg<CG>();
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must exist before anything remote targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
         if (lane == 0) {
+            const uint32_t full_leader0 = CG == 2 ? mapa_shared(full_bar(0), 0) : full_bar(0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile);
+            for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+                const TileCoord t = decode_tile<CG>(p, tile, rank);
                 const int4* sl = p.slices + (size_t)t.cls * p.num_slices;
                 for (int s = 0; s < p.num_slices; ++s) {
                     const int4 v = __ldg(sl + s);
@@ -144,10 +194,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                     const int dx = (short)(v.x >> 16);
                     const int dy = (short)(v.y & 0xffff);
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), CG * C::STAGE_BYTES);
                     const uint32_t a_dst = base + stage * C::STAGE_BYTES;
-                    tma_load_4d(a_dst, &p.amap[src], full_bar(stage), v.z, t.x0 + dx, t.y0 + dy, t.n0);
-                    tma_load_2d(a_dst + A_BYTES, &p.bmap, full_bar(stage), v.w * BK, t.n_tile * BN);
+                    if constexpr (CG == 1) {
+                        tma_load_4d(a_dst, &p.amap[src], full_bar(stage), v.z, t.x0 + dx, t.y0 + dy, t.n0);
+                        tma_load_2d(a_dst + A_BYTES, &p.bmap, full_bar(stage), v.w * BK, t.n_tile * BN);
+                    } else {
+                        const uint32_t fb = full_leader0 + 8u * stage;
+                        tma_load_4d_pair(a_dst, &p.amap[src], fb, v.z, t.x0 + dx, t.y0 + dy, t.n0);
+                        tma_load_2d_pair(a_dst + A_BYTES, &p.bmap, fb, v.w * BK, t.n_tile * BN + rank * C::BNC);
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -156,14 +212,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        // ------------------------------------------------------------------ MMA issuer (leader CTA)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -176,166 +232,246 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // +32 B per K=16 step inside the 128 B swizzle row (address field is >> 4)
-                        umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (s | k) != 0);
+                        umma_bf16_cg<CG>(d_tmem, da + 2u * k, db + 2u * k, idesc, (s | k) != 0);
                     }
-                    umma_commit(empty_bar(stage));
+                    umma_commit_cg<CG>(empty_bar(stage));
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit(tfull_bar(acc));
+                umma_commit_cg<CG>(tfull_bar(acc));
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (128 threads)
-        const int q = warp & 3;
+        // ------------------------------------------------------------------ epilogue (8 warps, both CTAs)
+        const int ew = warp - 4;
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int half = ew >> 2;
         const int row = q * 32 + lane;
-        const int et = threadIdx.x - 128;
+        const int rows_per_sample = p.bw * p.bh;
         const int dxr = row % p.bw;
         const int dyr = (row / p.bw) % p.bh;
-        const int dnr = row / (p.bw * p.bh);
+        const int dnr = row / rows_per_sample;
+        // origin of this warp's 32-row sub-box inside the tile box
+        const int sx0 = (q * 32) % p.bw, sy0 = ((q * 32) / p.bw) % p.bh, sn0 = (q * 32) / rows_per_sample;
+        const uint32_t ebuf = epi_base + ew * C::UNITS * EPI_BUF_BYTES;
+        const uint32_t rbar = res_bar(ew);
+        uint32_t rphase = 0;
+        const uint32_t tempty0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const TileCoord t = decode_tile(p, tile);
-            named_bar_sync(1, 128);
-            for (int i = et; i < BN; i += 128) {
-                const int c = t.n_tile * BN + i;
-                bias_s[i] = (p.bias != nullptr && c < p.cout) ? __ldg(p.bias + c) : 0.f;
-            }
-            named_bar_sync(1, 128);
+        for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+            const TileCoord t = decode_tile<CG>(p, tile, rank);
             const int n = t.n0 + dnr, y = t.y0 + dyr, x = t.x0 + dxr;
             const bool valid = (n < p.N) && (y < p.H) && (x < p.W);
-            const long long off = p.out_class_off[t.cls] + (long long)n * p.out_sn + (long long)y * p.out_sy +
-                                  (long long)x * p.out_sx;
-            const float* emb_row = p.emb ? p.emb + (long long)n * p.emb_ld : nullptr;
+            const float* emb_row = p.emb ? p.emb + (long long)(n < p.N ? n : 0) * p.emb_ld : nullptr;
+            const uint32_t acc_addr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
 
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + acc * BN + c + (uint32_t(q * 32) << 16), r);
-                tmem_ld_wait();
-                if (c + 32 >= BN) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-                    tc_fence_before();
-                    mbar_arrive(tempty_bar(acc));
-                }
-                const int cg = t.n_tile * BN + c;
-                if (cg >= p.cout) continue;  // warp-uniform: zero-padded weight rows
-                float v[32];
+            if constexpr (!OUT_F32) {
+                // 64-channel units of this warp: column group half + 2u of the BN tile (BN = 64: half 0 only)
+                bool unit_on[C::UNITS];
+                int unit_col[C::UNITS];
+                int n_on = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c + j];
-                if (p.vec_ok) {
-                    if (valid && emb_row) {
+                for (int u = 0; u < C::UNITS; ++u) {
+                    unit_col[u] = (BN >= 128 ? half + 2 * u : 0) * 64;
+                    unit_on[u] = (BN >= 128 || half == 0) && (t.n_tile * BN + unit_col[u]) < p.cout;
+                    n_on += unit_on[u] ? 1 : 0;
+                }
+                // staging buffers are free once the previous tile's TMA stores have finished reading them
+                if (lane == 0) bulk_wait_read<0>();
+                fence_proxy_async();  // the statistics pass read the buffers through the generic proxy
+                __syncwarp();
+                const bool res = p.has_res && n_on > 0;
+                if (res && lane == 0) {
+                    mbar_arrive_expect_tx(rbar, n_on * EPI_BUF_BYTES);
+#pragma unroll
+                    for (int u = 0; u < C::UNITS; ++u)
+                        if (unit_on[u])
+                            tma_load_4d(ebuf + u * EPI_BUF_BYTES, &p.rmap, rbar, t.n_tile * BN + unit_col[u], t.x0 + sx0,
+                                        t.y0 + sy0, t.n0 + sn0);
+                }
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                if (res) {
+                    mbar_wait(rbar, rphase);
+                    rphase ^= 1u;
+                }
+                int done = 0;
+#pragma unroll
+                for (int u = 0; u < C::UNITS; ++u) {
+                    if (!unit_on[u]) continue;  // warp-uniform
+                    const int cg0 = t.n_tile * BN + unit_col[u];
+                    const uint32_t buf = ebuf + u * EPI_BUF_BYTES;
+                    const uint32_t rowp = buf + lane * 128;
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(acc_addr + unit_col[u] + h2 * 32, r);
+                        float add[32];
+                        const int cg = cg0 + h2 * 32;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 e = __ldg(reinterpret_cast<const float4*>(emb_row + cg + j));
-                            v[j] += e.x; v[j + 1] += e.y; v[j + 2] += e.z; v[j + 3] += e.w;
+                            float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + cg + j))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (emb_row) {
+                                const float4 e = __ldg(reinterpret_cast<const float4*>(emb_row + cg + j));
+                                b.x += e.x; b.y += e.y; b.z += e.z; b.w += e.w;
+                            }
+                            add[j] = b.x; add[j + 1] = b.y; add[j + 2] = b.z; add[j + 3] = b.w;
                         }
-                    }
-                    if (valid && p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + cg);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + add[j];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint4 u = __ldg(rp + j);
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                            // 16 B chunk (h2*4 + j) of this row sits at chunk position (.. ^ (row & 7)): SWIZZLE_128B
+                            const uint32_t a16 = rowp + (((h2 * 4 + j) ^ (lane & 7)) << 4);
+                            if (res) {
+                                const uint4 u4 = lds128(a16);
+                                const uint32_t rw[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[k]);
+                                    v[j * 8 + 2 * k] += __low2float(b2);
+                                    v[j * 8 + 2 * k + 1] += __high2float(b2);
+                                }
+                            }
+                            uint32_t w[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-                                v[j * 8 + 2 * k] += __low2float(b2);
-                                v[j * 8 + 2 * k + 1] += __high2float(b2);
+                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j * 8 + 2 * k], v[j * 8 + 2 * k + 1]);
+                                // rows beyond the tensor edge are clipped by the TMA store; zero them for the statistics
+                                w[k] = valid ? *reinterpret_cast<const uint32_t*>(&b2) : 0u;
+                            }
+                            sts128(a16, make_uint4(w[0], w[1], w[2], w[3]));
+                        }
+                    }
+                    if (++done == n_on) {
+                        // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+                            else mbar_arrive(tempty_bar(acc));
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&p.omap[t.cls], buf, cg0, t.x0 + sx0, t.y0 + sy0, t.n0 + sn0);
+                        bulk_commit();
+                    }
+                    if (p.stats != nullptr) {
+                        // GroupNorm statistics of the consumer: lane l owns channels cg0 + 2l, 2l+1 (one 32-bit word
+                        // per row of the staging buffer); rows of one sample are p.seg consecutive rows
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        const uint32_t wsel = lane >> 2, wlo = (lane & 3) << 2;
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const uint32_t word = lds32(buf + rr * 128 + (((wsel ^ (rr & 7)) << 4) | wlo));
+                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&word);
+                            const float f0 = __low2float(b2), f1 = __high2float(b2);
+                            s0 += f0; q0 = fmaf(f0, f0, q0);
+                            s1 += f1; q1 = fmaf(f1, f1, q1);
+                            if (((rr + 1) & (p.seg - 1)) == 0) {
+                                const int ns = t.n0 + (q * 32 + rr) / rows_per_sample;
+                                if (ns < p.N)
+                                    atomicAdd(reinterpret_cast<float4*>(p.stats + ((long long)ns * p.cout + cg0 + 2 * lane) * 2),
+                                              make_float4(s0, q0, s1, q1));
+                                s0 = s1 = q0 = q1 = 0.f;
                             }
                         }
                     }
-                    if constexpr (OUT_F32) {
-                        if (valid) {
-                            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + cg);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        }
-                    } else {
-                        uint32_t w[16];
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) {
-                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-                            w[k] = *reinterpret_cast<const uint32_t*>(&b2);
-                            // the statistics describe the tensor as stored (bf16-rounded)
-                            v[2 * k] = __low2float(b2);
-                            v[2 * k + 1] = __high2float(b2);
-                        }
-                        if (valid) {
-                            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + cg);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) op[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-                        }
+                }
+                if (n_on == 0) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+                        else mbar_arrive(tempty_bar(acc));
                     }
-                    if (p.stats != nullptr) {
-                        // GroupNorm statistics of the consumer, fused here: per-(sample, channel) sum and
-                        // sum of squares over this warp's rows.  Recursive halving across lanes: every step
-                        // trades half of the channels with the partner lane, so after log2(seg) steps a lane
-                        // owns 32/seg channels summed over the seg rows of its sample.
-                        float q[32];
+                }
+            } else {
+                // ---------------- fp32 output: direct stores (embedding GEMM, ragged Cout convs)
+                const long long off = p.out_class_off[t.cls] + (long long)n * p.out_sn + (long long)y * p.out_sy +
+                                      (long long)x * p.out_sx;
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                constexpr int CH = BN / 2 / 32;  // 32-column chunks per warp
+#pragma unroll 1
+                for (int ci = 0; ci < CH; ++ci) {
+                    const int c = half * (BN / 2) + ci * 32;
+                    uint32_t r[32];
+                    tmem_ld_32x32(acc_addr + c, r);
+                    tmem_ld_wait();
+                    const int cg = t.n_tile * BN + c;
+                    if (!valid || cg >= p.cout) continue;
+                    float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            v[j] = valid ? v[j] : 0.f;
-                            q[j] = v[j] * v[j];
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + cg + j) : 0.f);
+                    if (p.vec_ok) {
+                        if (emb_row) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 e = __ldg(reinterpret_cast<const float4*>(emb_row + cg + j));
+                                v[j] += e.x; v[j + 1] += e.y; v[j + 2] += e.z; v[j + 3] += e.w;
+                            }
                         }
-                        int cb = 0;
+                        if (p.residual) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + cg);
 #pragma unroll
-                        for (int s = 0; s < 5; ++s) {
-                            const int nh = 16 >> s;
-                            const int o = p.seg >> (s + 1);
-                            if (o == 0) break;
-                            const bool upper = (lane & o) != 0;
-                            cb += upper ? nh : 0;
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 u = __ldg(rp + j);
+                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                if (j < nh) {
-                                    const float sv = upper ? v[j] : v[j + nh];
-                                    const float kv = upper ? v[j + nh] : v[j];
-                                    const float sq = upper ? q[j] : q[j + nh];
-                                    const float kq = upper ? q[j + nh] : q[j];
-                                    v[j] = kv + __shfl_xor_sync(0xffffffffu, sv, o);
-                                    q[j] = kq + __shfl_xor_sync(0xffffffffu, sq, o);
+                                for (int k = 0; k < 4; ++k) {
+                                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+                                    v[j * 8 + 2 * k] += __low2float(b2);
+                                    v[j * 8 + 2 * k + 1] += __high2float(b2);
                                 }
                             }
                         }
-                        const int cnt = 32 / p.seg;
-                        if (n < p.N) {
-                            float2* sp = reinterpret_cast<float2*>(p.stats) + (long long)n * p.cout + cg + cb;
+                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + cg);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < cnt) atomicAdd(sp + j, make_float2(v[j], q[j]));
+                        for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+                        // ragged / unaligned edge (Cout in {3, 6, 8}): scalar path
+#pragma unroll 1
+                        for (int j = 0; j < 32; ++j) {
+                            if (cg + j >= p.cout) break;
+                            float o = v[j];
+                            if (emb_row) o += __ldg(emb_row + cg + j);
+                            if (p.residual) o += __bfloat162float(p.residual[off + cg + j]);
+                            static_cast<float*>(p.out)[off + cg + j] = o;
                         }
                     }
-                } else if (valid) {
-                    // ragged / unaligned edge (Cout in {3, 6, 8}): scalar path
-#pragma unroll 1
-                    for (int j = 0; j < 32; ++j) {
-                        if (cg + j >= p.cout) break;
-                        float o = v[j];
-                        if (emb_row) o += __ldg(emb_row + cg + j);
-                        if (p.residual) o += __bfloat162float(p.residual[off + cg + j]);
-                        if constexpr (OUT_F32) static_cast<float*>(p.out)[off + cg + j] = o;
-                        else static_cast<__nv_bfloat16*>(p.out)[off + cg + j] = __float2bfloat16_rn(o);
-                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+                    else mbar_arrive(tempty_bar(acc));
                 }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
+        if constexpr (!OUT_F32) {
+            if (lane == 0) bulk_wait_read<0>();  // smem must stay alive until the last TMA stores have read it
+        }
     }
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // no CTA of the pair may exit while the other can still signal it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, C::TMEM_COLS);
+        tmem_dealloc_cg<CG>(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -352,30 +488,32 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-int encode_src_map(CUtensorMap* m, const tq_src& s, int bw, int bh, int bn) {
+// channels-last [N, H, W, C] view with element strides (sn, sy, sx, 1) -> 4-D map with box {64, bw, bh, bn}
+int encode_nhwc_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int Cc, long long sn, long long sy, long long sx,
+                    int bw, int bh, int bn, const char* what) {
     auto enc = get_encode_fn();
     TQ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
-    TQ_CHECK(s.C % 64 == 0, "conv source channels must be a multiple of 64 (got %d)", s.C);
-    TQ_CHECK(s.sx % 8 == 0 && s.sn % 8 == 0 && (s.H == 1 || s.sy % 8 == 0), "conv source strides must be 16 B multiples");
-    TQ_CHECK((reinterpret_cast<uintptr_t>(s.ptr) & 15) == 0, "conv source pointer must be 16 B aligned");
-    cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.N};
-    long long sy = (s.H == 1 && s.sy == 0) ? (long long)s.W * s.sx : s.sy;
-    cuuint64_t strides[3] = {(cuuint64_t)s.sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)s.sn * 2};
+    TQ_CHECK(Cc % 64 == 0, "%s: channels must be a multiple of 64 (got %d)", what, Cc);
+    TQ_CHECK(sx % 8 == 0 && sn % 8 == 0 && (H == 1 || sy % 8 == 0), "%s: strides must be 16 B multiples", what);
+    TQ_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s: pointer must be 16 B aligned", what);
+    cuuint64_t dims[4] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const long long sy_eff = (H == 1 && (sy == 0 || sy % 8 != 0)) ? (long long)W * sx : sy;
+    cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy_eff * 2, (cuuint64_t)sn * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.ptr), dims, strides, box, estr,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    TQ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed with CUresult %d", (int)r);
+    TQ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
     return 0;
 }
 
-int encode_weight_map(CUtensorMap* m, const void* w, int cout_pad, int ktot, int bn_tile) {
+int encode_weight_map(CUtensorMap* m, const void* w, int cout_pad, int ktot, int rows) {
     auto enc = get_encode_fn();
     TQ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout_pad};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)bn_tile};
+    cuuint32_t box[2] = {64, (cuuint32_t)rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -390,19 +528,43 @@ int pow2_floor(int v) {
     return p;
 }
 
-template <int BN, bool OUT_F32>
+template <int BN, int CG, bool OUT_F32>
 int launch_igemm(const IgemmParams& p, int grid, cudaStream_t st) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        TQ_CUDA(cudaFuncSetAttribute(igemm_sm100_kernel<BN, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        TQ_CUDA(cudaFuncSetAttribute(igemm_sm100_kernel<BN, CG, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
         attr_set = true;
     }
-    igemm_sm100_kernel<BN, OUT_F32><<<grid, kThreads, C::SMEM_BYTES, st>>>(p);
-    TQ_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TQ_CUDA(cudaLaunchKernelEx(&cfg, igemm_sm100_kernel<BN, CG, OUT_F32>, p));
     count_launch();
     return 0;
+}
+
+template <int BN, int CG>
+int launch_igemm_o(const IgemmParams& p, int grid, bool f32, cudaStream_t st) {
+    return f32 ? launch_igemm<BN, CG, true>(p, grid, st) : launch_igemm<BN, CG, false>(p, grid, st);
+}
+
+// cycles per 64-deep K slice per SM: the larger of the tensor-pipe time (2*BN) and the shared-memory traffic
+// (operand fill + operand read at 128 B/clk): the model behind the automatic (BN, CG) choice
+long long slice_cycles(int bn, int cg) {
+    const long long mma = 2LL * bn;
+    const long long smem = (A_BYTES + (long long)(bn / cg) * BK * 2) / 64;
+    return mma > smem ? mma : smem;
 }
 
 }  // namespace
@@ -424,28 +586,75 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     TQ_CHECK(d.ktot % 64 == 0 && d.cout_pad % 64 == 0, "weight matrix must be padded to 64x64 blocks");
     TQ_CHECK(d.cout >= 1 && d.cout <= d.cout_pad, "cout out of range");
     TQ_CHECK((reinterpret_cast<uintptr_t>(d.weights) & 15) == 0, "weights must be 16 B aligned");
+    TQ_CHECK(d.out_dtype == TQ_F32 || d.out_dtype == TQ_BF16, "bad out_dtype");
+    const bool f32 = d.out_dtype == TQ_F32;
+    TQ_CHECK(f32 || d.cout % 64 == 0, "bf16 outputs need cout %% 64 == 0 on the tensor path (got %d)", d.cout);
+    TQ_CHECK(d.stats == nullptr || !f32, "conv statistics are produced for bf16 outputs only");
+    TQ_CHECK(d.residual == nullptr || d.num_classes == 1, "residual add needs a single output class");
 
     auto p = std::make_shared<IgemmParams>();
     memset(p.get(), 0, sizeof(IgemmParams));
     p->N = d.N; p->H = d.H; p->W = d.W;
     tile_shape_for(d.H, d.W, &p->bw, &p->bh, &p->bn);
-    int bn_tile = d.block_n;
-    if (bn_tile == 0) {
-        bn_tile = d.cout_pad % 256 == 0 ? 256 : (d.cout_pad % 128 == 0 ? 128 : 64);
-        // prefer enough tiles to fill the machine
-        long long m_tiles = (long long)((d.W + p->bw - 1) / p->bw) * ((d.H + p->bh - 1) / p->bh) *
-                            ((d.N + p->bn - 1) / p->bn) * d.num_classes;
-        const int sms = device_sm_count();
-        while (bn_tile > 64 && m_tiles * (d.cout_pad / bn_tile) < 2LL * sms && d.cout_pad % (bn_tile / 2) == 0)
-            bn_tile /= 2;
-    }
-    TQ_CHECK(bn_tile == 64 || bn_tile == 128 || bn_tile == 256, "block_n must be 64, 128 or 256");
-    TQ_CHECK(d.cout_pad % bn_tile == 0, "cout_pad must be a multiple of block_n");
+    p->tiles_x = (d.W + p->bw - 1) / p->bw;
+    p->tiles_y = (d.H + p->bh - 1) / p->bh;
+    const int tiles_n = (d.N + p->bn - 1) / p->bn;
+    p->m_tiles = p->tiles_x * p->tiles_y * tiles_n;
+    const int sms = device_sm_count();
 
-    for (int i = 0; i < d.num_srcs; ++i)
-        if (encode_src_map(&p->amap[i], d.srcs[i], p->bw, p->bh, p->bn)) return 1;
+    int cg = d.cta_group;
+    TQ_CHECK(cg == 0 || cg == 1 || cg == 2, "cta_group must be 0 (auto), 1 or 2");
+    if (cg == 0) cg = p->m_tiles >= 2 ? 2 : 1;
+    int bn_tile = d.block_n;
+    TQ_CHECK(bn_tile == 0 || bn_tile == 64 || bn_tile == 128 || bn_tile == 256, "block_n must be 0, 64, 128 or 256");
+    if (bn_tile == 0) {
+        long long best = -1;
+        for (int cand : {256, 128, 64}) {
+            if (cand > 64 && cand / 2 >= d.cout_pad) continue;  // would mostly compute padding
+            const long long m_groups = (p->m_tiles + cg - 1) / cg;
+            const long long tiles = m_groups * ((d.cout_pad + cand - 1) / cand) * d.num_classes;
+            const long long clusters = sms / cg;
+            const long long rounds = (tiles + clusters - 1) / clusters;
+            const long long cost = rounds * ((long long)d.num_slices * slice_cycles(cand, cg) + 700);
+            if (best < 0 || cost < best) {
+                best = cost;
+                bn_tile = cand;
+            }
+        }
+    }
+    p->m_groups = (p->m_tiles + cg - 1) / cg;
+    p->n_tiles = (d.cout_pad + bn_tile - 1) / bn_tile;
+    p->total_tiles = p->m_groups * p->n_tiles * d.num_classes;
+
+    for (int i = 0; i < d.num_srcs; ++i) {
+        const tq_src& s = d.srcs[i];
+        if (encode_nhwc_map(&p->amap[i], s.ptr, s.N, s.H, s.W, s.C, s.sn, s.sy, s.sx, p->bw, p->bh, p->bn, "conv source"))
+            return 1;
+    }
     for (int i = d.num_srcs; i < 4; ++i) p->amap[i] = p->amap[0];
-    if (encode_weight_map(&p->bmap, d.weights, d.cout_pad, d.ktot, bn_tile)) return 1;
+    if (encode_weight_map(&p->bmap, d.weights, d.cout_pad, d.ktot, bn_tile / cg)) return 1;
+
+    // epilogue unit box: the 32 consecutive tile rows one epilogue warp owns
+    const int sbw = p->bw < 32 ? p->bw : 32;
+    const int sbh = p->bh < 32 / sbw ? p->bh : 32 / sbw;
+    const int sbn = 32 / (sbw * sbh);
+    if (!f32) {
+        for (int c = 0; c < d.num_classes; ++c) {
+            const __nv_bfloat16* ob = static_cast<const __nv_bfloat16*>(d.out) + d.out_class_off[c];
+            if (encode_nhwc_map(&p->omap[c], ob, d.N, d.H, d.W, d.cout, d.out_sn, d.out_sy, d.out_sx, sbw, sbh, sbn,
+                                "conv output"))
+                return 1;
+        }
+        for (int c = d.num_classes; c < 4; ++c) p->omap[c] = p->omap[0];
+        if (d.residual) {
+            if (encode_nhwc_map(&p->rmap, d.residual, d.N, d.H, d.W, d.cout, d.out_sn, d.out_sy, d.out_sx, sbw, sbh, sbn,
+                                "conv residual"))
+                return 1;
+            p->has_res = 1;
+        } else {
+            p->rmap = p->omap[0];
+        }
+    }
 
     const size_t nsl = (size_t)d.num_classes * d.num_slices;
     for (size_t i = 0; i < nsl; ++i) {
@@ -463,12 +672,6 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     p->slices = static_cast<const int4*>(dsl);
     p->num_slices = d.num_slices;
     p->num_classes = d.num_classes;
-    p->tiles_x = (d.W + p->bw - 1) / p->bw;
-    p->tiles_y = (d.H + p->bh - 1) / p->bh;
-    const int tiles_n = (d.N + p->bn - 1) / p->bn;
-    p->m_tiles = p->tiles_x * p->tiles_y * tiles_n;
-    p->n_tiles = d.cout_pad / bn_tile;
-    p->total_tiles = p->m_tiles * p->n_tiles * d.num_classes;
     p->cout = d.cout;
     p->bias = d.bias;
     p->emb = d.emb;
@@ -477,35 +680,44 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     p->out = d.out;
     p->out_sn = d.out_sn; p->out_sy = d.out_sy; p->out_sx = d.out_sx;
     for (int i = 0; i < 4; ++i) p->out_class_off[i] = d.out_class_off[i];
-    const int oalign = d.out_dtype == TQ_F32 ? 4 : 8;
-    bool vec = d.cout % 32 == 0 && d.out_sn % oalign == 0 && d.out_sy % oalign == 0 && d.out_sx % oalign == 0;
-    vec = vec && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0;
-    for (int i = 0; i < d.num_classes; ++i) vec = vec && d.out_class_off[i] % oalign == 0;
-    if (d.emb) vec = vec && d.emb_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.emb) & 15) == 0;
-    if (d.residual) vec = vec && (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0 && d.out_sn % 8 == 0 &&
-                          d.out_sy % 8 == 0 && d.out_sx % 8 == 0;
-    p->vec_ok = vec ? 1 : 0;
+    if (f32) {
+        bool vec = d.cout % 32 == 0 && d.out_sn % 4 == 0 && d.out_sy % 4 == 0 && d.out_sx % 4 == 0;
+        vec = vec && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0;
+        for (int i = 0; i < d.num_classes; ++i) vec = vec && d.out_class_off[i] % 4 == 0;
+        if (d.emb) vec = vec && d.emb_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.emb) & 15) == 0;
+        if (d.residual) vec = vec && (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0 && d.out_sn % 8 == 0 &&
+                              d.out_sy % 8 == 0 && d.out_sx % 8 == 0;
+        p->vec_ok = vec ? 1 : 0;
+    } else {
+        TQ_CHECK(!d.bias || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "bias must be 16 B aligned");
+        TQ_CHECK(!d.emb || (d.emb_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.emb) & 15) == 0),
+                 "per-sample embedding must be 16 B aligned with emb_ld %% 4 == 0");
+    }
     p->stats = d.stats;
     {
         const int rows = p->bw * p->bh;
         p->seg = rows < 32 ? rows : 32;
     }
-    TQ_CHECK(d.stats == nullptr || (vec && (reinterpret_cast<uintptr_t>(d.stats) & 7) == 0),
-             "conv statistics need a vectorisable epilogue (cout %% 32 == 0, aligned strides) and an 8 B aligned buffer");
+    TQ_CHECK(d.stats == nullptr || (reinterpret_cast<uintptr_t>(d.stats) & 15) == 0,
+             "conv statistics buffer must be 16 B aligned");
 
-    const int grid = p->total_tiles < device_sm_count() ? p->total_tiles : device_sm_count();
-    const bool f32 = d.out_dtype == TQ_F32;
-    TQ_CHECK(d.out_dtype == TQ_F32 || d.out_dtype == TQ_BF16, "bad out_dtype");
+    const int clusters = p->total_tiles < sms / cg ? p->total_tiles : sms / cg;
+    const int grid = clusters * cg;
 
     Op op;
-    char nm[96];
-    snprintf(nm, sizeof nm, "igemm_sm100<BN=%d,%s> tiles=%d slices=%d", bn_tile, f32 ? "f32" : "bf16", p->total_tiles,
-             d.num_slices);
+    char nm[112];
+    snprintf(nm, sizeof nm, "igemm_sm100<BN=%d,CG=%d,%s> tiles=%d slices=%d", bn_tile, cg, f32 ? "f32" : "bf16",
+             p->total_tiles, d.num_slices);
     op.name = nm;
-    op.launch = [p, dsl_owner, grid, bn_tile, f32](cudaStream_t st) -> int {
-        if (bn_tile == 256) return f32 ? launch_igemm<256, true>(*p, grid, st) : launch_igemm<256, false>(*p, grid, st);
-        if (bn_tile == 128) return f32 ? launch_igemm<128, true>(*p, grid, st) : launch_igemm<128, false>(*p, grid, st);
-        return f32 ? launch_igemm<64, true>(*p, grid, st) : launch_igemm<64, false>(*p, grid, st);
+    op.launch = [p, dsl_owner, grid, bn_tile, cg, f32](cudaStream_t st) -> int {
+        if (cg == 2) {
+            if (bn_tile == 256) return launch_igemm_o<256, 2>(*p, grid, f32, st);
+            if (bn_tile == 128) return launch_igemm_o<128, 2>(*p, grid, f32, st);
+            return launch_igemm_o<64, 2>(*p, grid, f32, st);
+        }
+        if (bn_tile == 256) return launch_igemm_o<256, 1>(*p, grid, f32, st);
+        if (bn_tile == 128) return launch_igemm_o<128, 1>(*p, grid, f32, st);
+        return launch_igemm_o<64, 1>(*p, grid, f32, st);
     };
     ops.push_back(std::move(op));
     return 0;

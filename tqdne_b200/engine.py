@@ -238,7 +238,8 @@ class Plan:
     # -- ops ------------------------------------------------------------------------------------
     def conv(self, pc: PackedConv, srcs: list[Act], *, out: Act | None = None, out_dtype=None, stride: int = 1,
              upsample: bool = False, emb: torch.Tensor | None = None, emb_ld: int = 0, residual: Act | None = None,
-             shortcut_srcs: list[Act] | None = None, block_n: int = 0, dims: int = 2, stats: bool = False) -> Act:
+             shortcut_srcs: list[Act] | None = None, block_n: int = 0, dims: int = 2, stats: bool = False,
+             cta_group: int = 0) -> Act:
         """Append one implicit-GEMM conv.  `srcs` are the concat segments of the conv input.  `stats`: also
         accumulate the per-(sample, channel) GroupNorm sums of the output in the epilogue."""
         N, H, W = srcs[0].N, srcs[0].H, srcs[0].W
@@ -351,7 +352,9 @@ class Plan:
         for i in range(4):
             d.out_class_off[i] = class_off[i]
         d.block_n = block_n
-        if stats and pc.cout % 32 == 0:
+        d.cta_group = cta_group
+        tensor_path = self.act_dtype == torch.bfloat16
+        if stats and ((tensor_path and odt == torch.bfloat16 and pc.cout % 64 == 0) or (not tensor_path and pc.cout % 32 == 0)):
             out.stats = self._stats_alloc(N * pc.cout * 2)
             d.stats = out.stats.data_ptr()
         _lib.check(self.lib.tq_plan_add_conv(self.h, C.byref(d)), "plan_add_conv")
