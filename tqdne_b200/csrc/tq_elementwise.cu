@@ -29,13 +29,28 @@ struct LinParams {
     int y_act_dtype;
 };
 
+__device__ __forceinline__ void linear_epilogue(const LinParams& p, float a, int m, int j) {
+    if (p.b) a += p.b[j];
+    if (p.add) a += p.add[(long long)(p.add_rows == 1 ? 0 : m) * p.Nout + j];
+    const long long o = (long long)m * p.Nout + j;
+    if (p.y) p.y[o] = a;
+    if (p.y_act) {
+        const float s = silu_acc(a);
+        if (p.y_act_dtype == TQ_F32) static_cast<float*>(p.y_act)[o] = s;
+        else static_cast<__nv_bfloat16*>(p.y_act)[o] = __float2bfloat16_rn(s);
+    }
+}
+
+// one warp per dot product; with a single shared input row (x_rows == 1: every sample of a sampler step has the
+// same noise level) the dot product is computed once per output column and the epilogue fans out over the rows
 __global__ void __launch_bounds__(256) linear_kernel(const LinParams p) {
     const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const long long total = (long long)p.M * p.Nout;
+    const bool shared_row = p.x_rows == 1;
+    const long long total = shared_row ? p.Nout : (long long)p.M * p.Nout;
     if (warp_global >= total) return;
-    const int m = warp_global / p.Nout, j = warp_global % p.Nout;
-    const float* xr = p.x + (long long)(p.x_rows == 1 ? 0 : m) * p.K;
+    const int m = shared_row ? 0 : warp_global / p.Nout, j = shared_row ? warp_global : warp_global % p.Nout;
+    const float* xr = p.x + (long long)m * p.K;
     const float* wr = p.W + (long long)j * p.K;
     float a = 0.f;
     for (int k = lane; k < p.K; k += 32) {
@@ -45,16 +60,10 @@ __global__ void __launch_bounds__(256) linear_kernel(const LinParams p) {
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
-        if (p.b) a += p.b[j];
-        if (p.add) a += p.add[(long long)(p.add_rows == 1 ? 0 : m) * p.Nout + j];
-        const long long o = (long long)m * p.Nout + j;
-        if (p.y) p.y[o] = a;
-        if (p.y_act) {
-            const float s = silu_acc(a);
-            if (p.y_act_dtype == TQ_F32) static_cast<float*>(p.y_act)[o] = s;
-            else static_cast<__nv_bfloat16*>(p.y_act)[o] = __float2bfloat16_rn(s);
-        }
+    if (shared_row) {
+        for (int mm = lane; mm < p.M; mm += 32) linear_epilogue(p, a, mm, j);
+    } else if (lane == 0) {
+        linear_epilogue(p, a, m, j);
     }
 }
 
@@ -220,7 +229,7 @@ int build_linear(std::vector<Op>& ops, const tq_linear_desc& d) {
     Op op;
     op.name = "linear_f32";
     op.launch = [p](cudaStream_t st) -> int {
-        const long long warps = (long long)p->M * p->Nout;
+        const long long warps = p->x_rows == 1 ? p->Nout : (long long)p->M * p->Nout;
         linear_kernel<<<blocks_for(warps * 32, 256), 256, 0, st>>>(*p);
         TQ_CUDA(cudaGetLastError());
         count_launch();

@@ -73,7 +73,20 @@ struct alignas(64) IgemmParams {
     long long out_class_off[4];
     float* stats;  // [N][cout][2] per-(sample, channel) sum / sum of squares, or nullptr
     int seg;       // rows of one sample inside an epilogue warp: min(32, bw*bh)
+    unsigned long long* prof;  // debug (TQ_IGEMM_PROF=1): [grid][8] cycle counters, else nullptr
 };
+
+__device__ __forceinline__ long long clk() { return clock64(); }
+// mbarrier wait that adds the cycles spent waiting to `acc` when profiling is on
+__device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bool on, long long& acc) {
+    if (!on) {
+        mbar_wait(bar, parity);
+        return;
+    }
+    const long long t0 = clk();
+    mbar_wait(bar, parity);
+    acc += clk() - t0;
+}
 
 template <int BN, int CG>
 struct Cfg {
@@ -185,6 +198,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
             const uint32_t full_leader0 = CG == 2 ? mapa_shared(full_bar(0), 0) : full_bar(0);
             int stage = 0;
             uint32_t phase = 0;
+            const bool prof = p.prof != nullptr;
+            long long w_empty = 0;
             for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
                 const TileCoord t = decode_tile<CG>(p, tile, rank);
                 const int4* sl = p.slices + (size_t)t.cls * p.num_slices;
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                     const int src = (short)(v.x & 0xffff);
                     const int dx = (short)(v.x >> 16);
                     const int dy = (short)(v.y & 0xffff);
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_wait_prof(empty_bar(stage), phase ^ 1u, prof, w_empty);
                     if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), CG * C::STAGE_BYTES);
                     const uint32_t a_dst = base + stage * C::STAGE_BYTES;
                     if constexpr (CG == 1) {
@@ -210,6 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                     }
                 }
             }
+            if (prof) p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_empty;
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA)
@@ -219,12 +235,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            const bool prof = p.prof != nullptr;
+            long long w_full = 0, w_tempty = 0;
+            const long long t_begin = clk();
             for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                mbar_wait_prof(tempty_bar(acc), acc_phase ^ 1u, prof, w_tempty);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int s = 0; s < p.num_slices; ++s) {
-                    mbar_wait(full_bar(stage), phase);
+                    mbar_wait_prof(full_bar(stage), phase, prof, w_full);
                     tc_fence_after();
                     const uint32_t a_addr = base + stage * C::STAGE_BYTES;
                     const uint64_t da = umma_desc_sw128(a_addr);
@@ -243,6 +262,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                 umma_commit_cg<CG>(tfull_bar(acc));
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
+            }
+            if (prof) {
+                p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clk() - t_begin);
+                p.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
+                p.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tempty;
             }
         }
     } else if (warp >= 4) {
@@ -263,6 +287,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
         const uint32_t tempty0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
         int acc = 0;
         uint32_t acc_phase = 0;
+        const bool prof = p.prof != nullptr && ew == 0;
+        long long w_tfull = 0, w_res = 0, w_store = 0;
+        const long long e_begin = clk();
         for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
             const TileCoord t = decode_tile<CG>(p, tile, rank);
             const int n = t.n0 + dnr, y = t.y0 + dyr, x = t.x0 + dxr;
@@ -282,7 +309,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                     n_on += unit_on[u] ? 1 : 0;
                 }
                 // staging buffers are free once the previous tile's TMA stores have finished reading them
-                if (lane == 0) bulk_wait_read<0>();
+                {
+                    const long long t0 = prof ? clk() : 0;
+                    if (lane == 0) bulk_wait_read<0>();
+                    if (prof) w_store += clk() - t0;
+                }
                 fence_proxy_async();  // the statistics pass read the buffers through the generic proxy
                 __syncwarp();
                 const bool res = p.has_res && n_on > 0;
@@ -294,10 +325,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                             tma_load_4d(ebuf + u * EPI_BUF_BYTES, &p.rmap, rbar, t.n_tile * BN + unit_col[u], t.x0 + sx0,
                                         t.y0 + sy0, t.n0 + sn0);
                 }
-                mbar_wait(tfull_bar(acc), acc_phase);
+                mbar_wait_prof(tfull_bar(acc), acc_phase, prof, w_tfull);
                 tc_fence_after();
                 if (res) {
-                    mbar_wait(rbar, rphase);
+                    mbar_wait_prof(rbar, rphase, prof, w_res);
                     rphase ^= 1u;
                 }
                 int done = 0;
@@ -463,6 +494,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
         }
         if constexpr (!OUT_F32) {
             if (lane == 0) bulk_wait_read<0>();  // smem must stay alive until the last TMA stores have read it
+        }
+        if (prof && lane == 0) {
+            p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clk() - e_begin);
+            p.prof[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull;
+            p.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_res;
+            p.prof[blockIdx.x * 8 + 7] = (unsigned long long)w_store;
         }
     }
 
@@ -703,13 +740,49 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
 
     const int clusters = p->total_tiles < sms / cg ? p->total_tiles : sms / cg;
     const int grid = clusters * cg;
+    std::shared_ptr<void> prof_owner;
+    if (const char* e = getenv("TQ_IGEMM_PROF"); e && e[0] == '1') {
+        void* pb = nullptr;
+        TQ_CUDA(cudaMalloc(&pb, (size_t)grid * 8 * sizeof(unsigned long long)));
+        TQ_CUDA(cudaMemset(pb, 0, (size_t)grid * 8 * sizeof(unsigned long long)));
+        prof_owner.reset(pb, [](void* q) { cudaFree(q); });
+        p->prof = static_cast<unsigned long long*>(pb);
+    }
 
     Op op;
     char nm[112];
     snprintf(nm, sizeof nm, "igemm_sm100<BN=%d,CG=%d,%s> tiles=%d slices=%d", bn_tile, cg, f32 ? "f32" : "bf16",
              p->total_tiles, d.num_slices);
     op.name = nm;
-    op.launch = [p, dsl_owner, grid, bn_tile, cg, f32](cudaStream_t st) -> int {
+    const std::string opname = nm;
+    op.launch = [p, dsl_owner, prof_owner, opname, grid, bn_tile, cg, f32](cudaStream_t st) -> int {
+        struct ProfDump {
+            const IgemmParams* p; int grid; int cg; cudaStream_t st; const std::string* name;
+            ~ProfDump() {
+                if (!p->prof) return;
+                cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+                cudaStreamIsCapturing(st, &cs);
+                if (cs != cudaStreamCaptureStatusNone) return;
+                cudaStreamSynchronize(st);
+                std::vector<unsigned long long> h((size_t)grid * 8);
+                cudaMemcpy(h.data(), p->prof, h.size() * 8, cudaMemcpyDeviceToHost);
+                double a[8] = {};
+                int nl = 0;
+                for (int b = 0; b < grid; ++b) {
+                    for (int k = 3; k < 8; ++k) a[k] += (double)h[b * 8 + k] / grid;
+                    if (b % cg == 0) {
+                        for (int k = 0; k < 3; ++k) a[k] += (double)h[b * 8 + k];
+                        ++nl;
+                    }
+                }
+                for (int k = 0; k < 3; ++k) a[k] /= nl;
+                const double tiles_per = (double)p->total_tiles / (grid / cg);
+                fprintf(stderr, "[igemm prof] %s | per CTA avg cycles: mma total %.0f (wait full %.0f, wait tempty %.0f) | "
+                        "producer wait empty %.0f | epi warp total %.0f (wait tfull %.0f, wait res %.0f, wait store %.0f) | "
+                        "%.2f tiles/cluster -> %.0f cyc/tile, %.0f cyc/slice\n", name->c_str(), a[0], a[1], a[2], a[3], a[4], a[5],
+                        a[6], a[7], tiles_per, a[0] / tiles_per, a[0] / tiles_per / p->num_slices);
+            }
+        } dump{p.get(), grid, cg, st, &opname};
         if (cg == 2) {
             if (bn_tile == 256) return launch_igemm_o<256, 2>(*p, grid, f32, st);
             if (bn_tile == 128) return launch_igemm_o<128, 2>(*p, grid, f32, st);

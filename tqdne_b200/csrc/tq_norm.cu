@@ -129,68 +129,143 @@ __device__ __forceinline__ float silu_f(float v) {
 
 constexpr int GN_UNROLL = 4;
 
+// 8 consecutive channels of one position, as loaded (converted to fp32 only when consumed: half the registers
+// for bf16, which lets four CTAs share an SM with four 16 B loads in flight per thread)
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+    uint4 u;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void get(float (&v)[8]) const {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+            v[2 * k] = __low2float(b2);
+            v[2 * k + 1] = __high2float(b2);
+        }
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = __ldg(reinterpret_cast<const float4*>(p));
+        b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    }
+    __device__ __forceinline__ void get(float (&v)[8]) const {
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
 template <typename T>
-__device__ __forceinline__ void apply_one_source(const T* __restrict__ x, int C, int cbase, int Ct, int P, int n, int chunk,
-                                                 int chunks, T* __restrict__ y, const float* ab, int silu) {
+struct SrcView {
+    const T* xb;   // first element of this thread's channel vector at position 0 of the sample
+    T* yb;
+    int C, lanes, pl, cvec0;  // cvec0: first channel (index in the concatenated tensor) of the vector
+    int pix, p1;
+    bool on;
+};
+
+template <typename T>
+__device__ __forceinline__ SrcView<T> make_view(const T* x, int C, int cbase, int Ct, int P, int n, int chunk, int chunks, T* y) {
+    SrcView<T> v;
     const int cv = C >> 3;
-    const int lanes = 256 / cv;
-    const int tid = threadIdx.x;
-    const int vi = tid % cv, pl = tid / cv;
-    if (pl >= lanes) return;
+    v.C = C;
+    v.lanes = 256 / cv;
+    const int vi = threadIdx.x % cv;
+    v.pl = threadIdx.x / cv;
+    v.on = v.pl < v.lanes;
     const int per = (P + chunks - 1) / chunks;
-    const int p0 = chunk * per, p1 = min(P, p0 + per);
-    float a[8], b[8];
+    const int p0 = chunk * per;
+    v.p1 = min(P, p0 + per);
+    v.pix = p0 + v.pl;
+    v.cvec0 = cbase + vi * 8;
+    v.xb = x + ((long long)n * P) * C + vi * 8;
+    v.yb = y + ((long long)n * P) * Ct + v.cvec0;
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void emit8(const Raw8<T>& r, const float (&a)[8], const float (&b)[8], int silu, T* dst) {
+    float v[8];
+    r.get(v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        a[j] = ab[2 * (cbase + vi * 8 + j)];
-        b[j] = ab[2 * (cbase + vi * 8 + j) + 1];
+        v[j] = fmaf(v[j], a[j], b[j]);
+        if (silu) v[j] = silu_f<T>(v[j]);
     }
-    const T* xb = x + ((long long)n * P) * C + vi * 8;
-    T* yb = y + ((long long)n * P) * Ct + cbase + vi * 8;
-    int pix = p0 + pl;
-    for (; pix + (GN_UNROLL - 1) * lanes < p1; pix += GN_UNROLL * lanes) {
-        float v[GN_UNROLL][8];
+    store8(dst, v);
+}
+
+template <typename T>
+__device__ __forceinline__ void stream_source(SrcView<T>& s, const float (&a)[8], const float (&b)[8], int silu, int Ct,
+                                              Raw8<T> (&pre)[GN_UNROLL], bool have_pre) {
+    if (!s.on) return;
+    const int step = GN_UNROLL * s.lanes;
+    if (have_pre) {
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) load8<T>(xb + (long long)(pix + u * lanes) * C, v[u]);
-#pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                v[u][j] = fmaf(v[u][j], a[j], b[j]);
-                if (silu) v[u][j] = silu_f<T>(v[u][j]);
-            }
-            store8(yb + (long long)(pix + u * lanes) * Ct, v[u]);
-        }
+        for (int u = 0; u < GN_UNROLL; ++u) emit8<T>(pre[u], a, b, silu, s.yb + (long long)(s.pix + u * s.lanes) * Ct);
+        s.pix += step;
     }
-    for (; pix < p1; pix += lanes) {
-        float v[8];
-        load8<T>(xb + (long long)pix * C, v);
+    for (; s.pix + (GN_UNROLL - 1) * s.lanes < s.p1; s.pix += step) {
+        Raw8<T> r[GN_UNROLL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            v[j] = fmaf(v[j], a[j], b[j]);
-            if (silu) v[j] = silu_f<T>(v[j]);
-        }
-        store8(yb + (long long)pix * Ct, v);
+        for (int u = 0; u < GN_UNROLL; ++u) r[u].load(s.xb + (long long)(s.pix + u * s.lanes) * s.C);
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) emit8<T>(r[u], a, b, silu, s.yb + (long long)(s.pix + u * s.lanes) * Ct);
+    }
+    for (; s.pix < s.p1; s.pix += s.lanes) {
+        Raw8<T> r;
+        r.load(s.xb + (long long)s.pix * s.C);
+        emit8<T>(r, a, b, silu, s.yb + (long long)s.pix * Ct);
+    }
+}
+
+// scale / shift of 8 consecutive channels from the group statistics in shared memory
+__device__ __forceinline__ void affine8(const float* gstat, int cpg, int c0, const float4 (&g4)[2], const float4 (&b4)[2],
+                                        float (&a)[8], float (&b)[8]) {
+    const float gm[8] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w};
+    const float bt[8] = {b4[0].x, b4[0].y, b4[0].z, b4[0].w, b4[1].x, b4[1].y, b4[1].z, b4[1].w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int g = (c0 + j) / cpg;
+        a[j] = gstat[2 * g + 1] * gm[j];
+        b[j] = bt[j] - gstat[2 * g] * a[j];
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
-    extern __shared__ float ab[];  // [Ct][2] scale, shift  + [32][2] group mean, rstd
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(const GnParams p) {
+    __shared__ float gstat[64];  // [32][2] group mean, rstd
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int Ct = p.C0 + p.C1;
     const int cpg = Ct / 32;
-    float* gstat = ab + 2 * Ct;
-    const float* s0 = p.st0 + (long long)n * p.C0 * 2;
-    const float* s1 = p.st1 ? p.st1 + (long long)n * p.C1 * 2 : nullptr;
+    T* y = static_cast<T*>(p.y);
+    SrcView<T> v0 = make_view<T>(static_cast<const T*>(p.x0), p.C0, 0, Ct, p.P, n, chunk, p.chunks, y);
+    // (1) everything that does not depend on the statistics goes out first: the first batch of activations
+    // and this thread's gamma / beta
+    Raw8<T> pre[GN_UNROLL];
+    const bool have_pre = v0.on && v0.pix + (GN_UNROLL - 1) * v0.lanes < v0.p1;
+    if (have_pre) {
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) pre[u].load(v0.xb + (long long)(v0.pix + u * v0.lanes) * v0.C);
+    }
+    float4 g4[2], b4[2];
+    if (v0.on) {
+        g4[0] = __ldg(reinterpret_cast<const float4*>(p.gamma + v0.cvec0));
+        g4[1] = __ldg(reinterpret_cast<const float4*>(p.gamma + v0.cvec0) + 1);
+        b4[0] = __ldg(reinterpret_cast<const float4*>(p.beta + v0.cvec0));
+        b4[1] = __ldg(reinterpret_cast<const float4*>(p.beta + v0.cvec0) + 1);
+    }
+    // (2) group statistics from the per-channel sums: 8 threads per group, then a 3-step shuffle
     {
-        // 8 threads per group: strided partial sums over the group's channels, then a 3-step shuffle
+        const float* s0 = p.st0 + (long long)n * p.C0 * 2;
+        const float* s1 = p.st1 ? p.st1 + (long long)n * p.C1 * 2 : nullptr;
         const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
         float s = 0.f, ss = 0.f;
         for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
-            const float* q = c < p.C0 ? s0 + 2 * c : s1 + 2 * (c - p.C0);
-            s += q[0];
-            ss += q[1];
+            const float2 q = __ldcg(reinterpret_cast<const float2*>(c < p.C0 ? s0 + 2 * c : s1 + 2 * (c - p.C0)));
+            s += q.x;
+            ss += q.y;
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
@@ -207,16 +282,20 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < Ct; c += 256) {
-        const int g = c / cpg;
-        const float sc = gstat[2 * g + 1] * p.gamma[c];
-        ab[2 * c] = sc;
-        ab[2 * c + 1] = p.beta[c] - gstat[2 * g] * sc;
+    float a[8], b[8];
+    if (v0.on) affine8(gstat, cpg, v0.cvec0, g4, b4, a, b);
+    stream_source<T>(v0, a, b, p.silu, Ct, pre, have_pre);
+    if (p.C1 > 0) {
+        SrcView<T> v1 = make_view<T>(static_cast<const T*>(p.x1), p.C1, p.C0, Ct, p.P, n, chunk, p.chunks, y);
+        if (v1.on) {
+            g4[0] = __ldg(reinterpret_cast<const float4*>(p.gamma + v1.cvec0));
+            g4[1] = __ldg(reinterpret_cast<const float4*>(p.gamma + v1.cvec0) + 1);
+            b4[0] = __ldg(reinterpret_cast<const float4*>(p.beta + v1.cvec0));
+            b4[1] = __ldg(reinterpret_cast<const float4*>(p.beta + v1.cvec0) + 1);
+            affine8(gstat, cpg, v1.cvec0, g4, b4, a, b);
+        }
+        stream_source<T>(v1, a, b, p.silu, Ct, pre, false);
     }
-    __syncthreads();
-    apply_one_source<T>(static_cast<const T*>(p.x0), p.C0, 0, Ct, p.P, n, chunk, p.chunks, static_cast<T*>(p.y), ab, p.silu);
-    if (p.C1 > 0)
-        apply_one_source<T>(static_cast<const T*>(p.x1), p.C1, p.C0, Ct, p.P, n, chunk, p.chunks, static_cast<T*>(p.y), ab, p.silu);
 }
 
 }  // namespace
@@ -245,7 +324,7 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
     p->chunks = chunks;
     const bool f32 = d.dtype == TQ_F32;
     const size_t ws_bytes = (size_t)d.N * Ct * 2 * sizeof(float);
-    const size_t smem = (size_t)(2 * Ct + 64) * sizeof(float);
+    const size_t smem = 0;
     dim3 grid(chunks, d.N);
 
     if (!have_stats) {
