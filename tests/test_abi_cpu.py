@@ -1,0 +1,75 @@
+"""CPU: the C-ABI shared library builds for sm_100a without a GPU, loads, and exports exactly what
+include/tqdne_b200.h declares (no compute calls here)."""
+import ctypes
+import re
+import subprocess
+
+import pytest
+
+from tests.conftest import ROOT
+
+HEADER = ROOT / "include" / "tqdne_b200.h"
+LIB = ROOT / "tqdne_b200" / "libtqdne_b200.so"
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    if not LIB.exists():
+        subprocess.run(["make", "-C", str(ROOT / "tqdne_b200" / "csrc"), "-j8"], check=True, capture_output=True)
+    assert LIB.exists()
+    return LIB
+
+
+def declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(tq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for must in ("tq_plan_add_conv", "tq_plan_add_groupnorm", "tq_plan_add_attention", "tq_plan_add_linear", "tq_plan_run",
+                 "tq_plan_add_memset", "tq_edm_euler", "tq_edm_heun", "tq_logspec_griffinlim", "tq_mavg_envelope_inverse",
+                 "tq_nchw_to_nhwc", "tq_nhwc_to_nchw", "tq_last_error", "tq_abi_version"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol_and_binding_matches(lib_path):
+    from tqdne_b200 import _lib
+
+    handle = ctypes.CDLL(str(lib_path))
+    syms = declared_symbols()
+    for s in syms:
+        assert hasattr(handle, s), f"{s} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes binding table and header disagree"
+    handle.tq_abi_version.restype = ctypes.c_int
+    m = re.search(r"#define\s+TQ_ABI_VERSION\s+(\d+)", HEADER.read_text())
+    assert handle.tq_abi_version() == int(m.group(1)) == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_the_header_field_for_field():
+    """ctypes mirrors of the descriptor structs list the header's fields in the header's order."""
+    from tqdne_b200 import _lib
+
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    bodies = {name: body for body, name in re.findall(r"typedef struct \{([^{}]*)\}\s*(\w+)\s*;", text)}
+    for cname, cls in (("tq_conv_desc", _lib.TqConvDesc), ("tq_gn_desc", _lib.TqGnDesc), ("tq_attn_desc", _lib.TqAttnDesc),
+                       ("tq_linear_desc", _lib.TqLinearDesc), ("tq_src", _lib.TqSrc), ("tq_slice", _lib.TqSlice)):
+        body = bodies[cname]
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?[A-Za-z_0-9]+\s*\*?", "", decl, count=1)  # drop the type
+            for part in decl.split(","):
+                names.append(re.sub(r"[\*\s]|\[.*\]", "", part))
+        assert names == [f[0] for f in cls._fields_], cname
+
+
+def test_product_path_fails_loudly_without_the_library(monkeypatch, tmp_path):
+    from tqdne_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "missing.so")
+    with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
+        _lib.lib()

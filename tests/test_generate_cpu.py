@@ -1,0 +1,61 @@
+"""CPU: host logic of the generate-waveforms drop-in (conditioning normalisation, CSV expansion, CLI surface,
+output schema) against the reference's constants and flags."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tqdne_b200 import generate_waveforms as gw
+
+REF_CLI = Path("/root/reference/tqdne/generate_waveforms.py")
+REF_FLAGS = ["--hypocentral_distance", "--magnitude", "--vs30", "--hypocentre_depth", "--azimuthal_gap", "--num_samples",
+             "--csv", "--outfile", "--edm_checkpoint", "--autoencoder_checkpoint", "--batch_size"]
+
+
+def test_cli_accepts_every_reference_flag_with_the_reference_defaults():
+    p = gw.build_parser()
+    a = p.parse_args(["--outfile", "o.h5"])
+    assert a.batch_size == 32 and a.csv is None and a.num_samples is None and a.edm_checkpoint is None
+    flags = {s for act in p._actions for s in act.option_strings}
+    assert set(REF_FLAGS) <= flags
+    if REF_CLI.exists():  # build container: the flag list is read from the reference itself
+        ref = set(re.findall(r'"(--[a-z0-9_]+)"', REF_CLI.read_text()))
+        assert ref == set(REF_FLAGS)
+
+
+def test_feature_normalisation_uses_the_reference_statistics():
+    c = gw.normalize_features([101.29891904350877, 142.08307872902394], [4.801697862929673] * 2, [384.7045105848187] * 2,
+                              [38.359214998072] * 2, [129.92139043457396 + 89.69479051949207] * 2)
+    assert c.shape == (2, 5) and c.dtype == np.float64
+    assert np.allclose(c, [[0, 0, 0, 0, 1], [1, 0, 0, 0, 1]], atol=1e-12)
+    if REF_CLI.exists():
+        stats = np.array([[float(a), float(b)] for a, b in re.findall(r"\[\s*([0-9.]+),\s*([0-9.]+)\s*\],", REF_CLI.read_text())][:5])
+        assert np.array_equal(stats, gw.SUMMARY_STATISTICS)
+
+
+def test_csv_rows_repeat_num_samples_times(tmp_path):
+    f = tmp_path / "grid.csv"
+    f.write_text("hypocentral_distance,hypocentre_depth,magnitude,vs30,azimuthal_gap,num_samples\n"
+                 "10.0,5.0,4.5,300.0,100.0,2\n50.0,8.0,6.0,700.0,130.0,3\n")
+    cols = gw.read_csv_features(f)
+    assert cols["magnitude"] == [4.5, 4.5, 6.0, 6.0, 6.0] and cols["vs30"][-1] == 700.0 and len(cols["azimuthal_gap"]) == 5
+    with pytest.raises(ValueError, match="CSV or a full parameter set"):
+        gw.generate(None, 5.0, None, None, None, 1, None, "x", 1, None, None)
+
+
+def test_output_schema(tmp_path):
+    feats = {"hypocentral_distance": [1.0, 2.0], "magnitude": [5.0, 5.0], "vs30": [300.0, 300.0],
+             "hypocentre_depth": [10.0, 10.0], "azimuthal_gap": [130.0, 130.0]}
+    w = np.random.default_rng(0).standard_normal((2, 3, 4064))
+    out = gw.write_outputs(tmp_path / "w.h5", feats, w)
+    if out.endswith(".npz"):
+        z = np.load(out)
+        keys = set(z.files)
+    else:
+        import h5py
+
+        z = h5py.File(out)
+        keys = set(z.keys())
+    assert keys == {"hypocentral_distance", "magnitude", "vs30s", "hypocentre_depth", "azimuthal_gap", "waveforms"}
+    assert z["waveforms"].shape == (2, 3, 4064) and z["waveforms"].dtype == np.float32

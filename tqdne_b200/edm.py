@@ -235,17 +235,28 @@ class LightningEDM(LightningModule):
         xin, dt_ = plan.xin.t, tq_dtype(plan.act_dtype)
         F, Cf, Cpad = plan.out.t, plan.out.C, plan.cin_pad
         nsteps = self.num_sampling_steps
-        co = [_Coeffs(self.edm, s) for s in sigmas]
         stochastic = not self.deterministic_sampling
-        if stochastic:
-            hats = [self.edm.sigma_hat(s, nsteps) for s in sigmas[:-1]]
-            co_hat = [_Coeffs(self.edm, s) for s in hats]
-        # all c_noise values of the run, resident on the device: the plan reads plan.t
-        tvals = []
-        for i in range(nsteps):
-            tvals.append(co_hat[i].c_noise if stochastic else co[i].c_noise)
-            tvals.append(co[i + 1].c_noise)
-        tdev = torch.tensor(tvals, dtype=torch.float32, device=dev)
+        # the scalar schedule (fp32 coefficients, rounded like the reference's 0-dim tensor arithmetic) depends only on
+        # the sigma ladder: computed once per ladder and kept with its device copy of the c_noise values
+        key = (tuple(float(v) for v in sigmas), stochastic, str(dev))
+        sched = self.__dict__.setdefault("_tq_sched", {}).get(key)
+        if sched is None:
+            co = [_Coeffs(self.edm, s) for s in sigmas]
+            hats, co_hat = None, None
+            if stochastic:
+                hats = [self.edm.sigma_hat(s, nsteps) for s in sigmas[:-1]]
+                co_hat = [_Coeffs(self.edm, s) for s in hats]
+            tvals = []
+            for i in range(nsteps):
+                tvals.append(co_hat[i].c_noise if stochastic else co[i].c_noise)
+                tvals.append(co[i + 1].c_noise)
+            if stochastic:
+                dts = [float((sigmas[i + 1] - hats[i]).to(torch.float32)) for i in range(nsteps)]
+            else:
+                dts = [float(sigmas[i + 1] - sigmas[i]) for i in range(nsteps)]  # fp32 subtraction, like the reference
+            sched = (co, hats, co_hat, torch.tensor(tvals, dtype=torch.float32, device=dev), dts)
+            self.__dict__["_tq_sched"][key] = sched
+        co, hats, co_hat, tdev, dts = sched
         st = current_stream_ptr()
 
         def denoise(k):
@@ -263,9 +274,7 @@ class LightningEDM(LightningModule):
                 nz = torch.randn(x.shape, device=dev, dtype=torch.float64)
                 _lib.check(lib.tq_edm_add_noise(x.data_ptr(), nz.data_ptr(), scale, x.numel(), st), "add_noise")
                 _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), dt_, NP, C_, Cpad, cur.c_in, st), "precondition")
-                dt = float((sigmas[i + 1] - hats[i]).to(torch.float32))
-            else:
-                dt = float(sigmas[i + 1] - sigmas[i])  # fp32 subtraction, like the reference's 0-dim tensors
+            dt = dts[i]
             last = i == nsteps - 1
             denoise(2 * i)
             _lib.check(lib.tq_edm_euler(x.data_ptr(), F.data_ptr(), Cf, d.data_ptr(), x1.data_ptr(), xin.data_ptr(), dt_,
