@@ -19,6 +19,8 @@
 // atomics are needed.  The complex spectra (angles, R_prev) and S stream through L2.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "tq_common.h"
 
 namespace tq {
@@ -222,6 +224,297 @@ __global__ void __launch_bounds__(GL_THREADS) griffinlim_kernel(const GlParams p
     for (int n = tid; n < out_len; n += GL_THREADS) w[n] = ypad[n + NFFT / 2];
 }
 
+// =====================================================================================================
+// fp32 fast path: fused  STFT(frame t) -> phase update -> inverse FFT(frame t) -> overlap-add  per frame.
+//
+// The rebuilt spectrum never leaves the SM: a warp transforms frame t of the current signal, applies the fast
+// Griffin-Lim update against R_prev (the only per-iteration global traffic besides S: 129 x 8 B read + written
+// per frame), inverse-transforms the new angles and overlap-adds into the NEXT signal buffer.  Frames are
+// processed in 8 rounds (t mod 8) separated by block barriers, so concurrently added frames never overlap and
+// the summation order is fixed.  The 128-point complex FFT is held in registers (4 points per lane):
+// radix 4 x 4 x 4 x 2 with two conflict-free shared-memory transposes and one shuffle stage.
+namespace fused {
+
+constexpr int FW = 16;          // warps per CTA
+constexpr int FTHREADS = FW * 32;
+constexpr int EX = 168;         // per-warp exchange buffer (complex elements): >= 152 (transposes), >= 129 (spectrum)
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// z[k] = sum_j z[j] W4^(jk), W4 = -i (forward) / +i (inverse)
+template <bool INV>
+__device__ __forceinline__ void radix4(float2 (&z)[4]) {
+    const float2 t0 = cadd(z[0], z[2]), t1 = csub(z[0], z[2]), t2 = cadd(z[1], z[3]), t3 = csub(z[1], z[3]);
+    z[0] = cadd(t0, t2);
+    z[2] = csub(t0, t2);
+    const float2 it3 = INV ? make_float2(-t3.y, t3.x) : make_float2(t3.y, -t3.x);  // (+i or -i) * t3
+    z[1] = cadd(t1, it3);
+    z[3] = csub(t1, it3);
+}
+template <bool INV>
+__device__ __forceinline__ float2 twid(const float2* tw, int m) {
+    float2 w = tw[m];
+    if (INV) w.y = -w.y;
+    return w;
+}
+
+// in : z[j] = x[lane + 32 j]            (natural order)
+// out: z[p] = X[(lane & 15) + 16 p + 64 (lane >> 4)]
+// tw[m] = exp(-2 pi i m / 128), m < 96; ex: this warp's exchange buffer
+template <bool INV>
+__device__ __forceinline__ void fft128(float2 (&z)[4], float2* ex, const float2* tw, int lane) {
+    radix4<INV>(z);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) z[k] = cmul(z[k], twid<INV>(tw, lane * k));
+    const int a = lane >> 3, l2 = lane & 7;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ex[k * 40 + lane] = z[k];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = ex[a * 40 + l2 + 8 * j];
+    radix4<INV>(z);
+#pragma unroll
+    for (int m = 1; m < 4; ++m) z[m] = cmul(z[m], twid<INV>(tw, 4 * l2 * m));
+    const int g = lane & 15, l3 = lane >> 4;
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 4; ++m) ex[9 * (a + 4 * m) + l2] = z[m];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = ex[9 * g + l3 + 2 * j];
+    radix4<INV>(z);
+    if (l3) {
+#pragma unroll
+        for (int q = 1; q < 4; ++q) z[q] = cmul(z[q], twid<INV>(tw, 16 * q));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float ox = __shfl_xor_sync(0xffffffffu, z[q].x, 16);
+        const float oy = __shfl_xor_sync(0xffffffffu, z[q].y, 16);
+        z[q] = l3 ? make_float2(ox - z[q].x, oy - z[q].y) : make_float2(z[q].x + ox, z[q].y + oy);
+    }
+    __syncwarp();
+}
+
+struct Smem {
+    float* ya;      // signal buffers (padded length)
+    float* yb;
+    float* inv_wss; // 1 / window sum of squares per padded sample (0 outside the kept range)
+    float* win;     // periodic Hann, 256
+    float2* tw128;  // 96
+    float2* tw256;  // 129 (+pad)
+    float2* ex;     // FW x EX
+};
+
+__global__ void __launch_bounds__(FTHREADS, 2) griffinlim_fused_kernel(const GlParams p) {
+    extern __shared__ __align__(16) unsigned char gl_smem[];
+    const int frames = p.frames;
+    const int len = NFFT + HOP * (frames - 1);
+    const int len4 = (len + 3) & ~3;
+    Smem sm;
+    sm.ya = reinterpret_cast<float*>(gl_smem);
+    sm.yb = sm.ya + len4;
+    sm.inv_wss = sm.yb + len4;
+    sm.win = sm.inv_wss + len4;
+    sm.tw128 = reinterpret_cast<float2*>(sm.win + NFFT);
+    sm.tw256 = sm.tw128 + 96;
+    sm.ex = sm.tw256 + 132;
+
+    const int item = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float2* ex = sm.ex + warp * EX;
+    const size_t per_item = (size_t)frames * NBIN;
+    float* S = static_cast<float*>(p.ws) + (size_t)item * per_item * 5;
+    float2* Tp = reinterpret_cast<float2*>(S + per_item);
+
+    for (int i = tid; i < NFFT; i += FTHREADS) sm.win[i] = (float)(0.5 - 0.5 * cospi(2.0 * i / NFFT));
+    for (int i = tid; i < 96; i += FTHREADS) {
+        double s, c;
+        sincospi(-2.0 * i / 128.0, &s, &c);
+        sm.tw128[i] = make_float2((float)c, (float)s);
+    }
+    for (int i = tid; i <= 128; i += FTHREADS) {
+        double s, c;
+        sincospi(-2.0 * i / 256.0, &s, &c);
+        sm.tw256[i] = make_float2((float)c, (float)s);
+    }
+    for (int i = tid; i < len4; i += FTHREADS) {
+        sm.ya[i] = 0.f;
+        sm.yb[i] = 0.f;
+    }
+    __syncthreads();
+    for (int n = tid; n < len4; n += FTHREADS) {
+        float v = 0.f;
+        if (n >= NFFT / 2 && n < len - NFFT / 2) {
+            float wss = 0.f;
+            const int r = n & (HOP - 1);
+#pragma unroll
+            for (int j = 0; j < NFFT / HOP; ++j) {
+                const int o = r + HOP * j;
+                const int t = (n - o) / HOP;
+                if (n - o >= 0 && t < frames) wss += sm.win[o] * sm.win[o];
+            }
+            v = wss > r_tiny<float>() ? 1.f / wss : 1.f;
+        }
+        sm.inv_wss[n] = v;
+    }
+    // S = exp(((rep + 1) / 2) * (log_max - log_clip) + log_clip), Nyquist row = 0; R_prev = 0
+    const float* rep = p.rep + (size_t)item * 128 * frames;
+    for (int idx = tid; idx < frames * NBIN; idx += FTHREADS) {
+        const int f = idx / frames, t = idx % frames;  // coalesced read of rep[f][t]
+        float sv = 0.f;
+        if (f < 128) {
+            const float nls = (rep[(size_t)f * frames + t] + 1.f) / 2.f;
+            sv = (float)exp((double)nls * (p.log_max - p.log_clip) + p.log_clip);
+        }
+        S[(size_t)t * NBIN + f] = sv;
+        Tp[(size_t)t * NBIN + f] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+
+    const float mom = (float)p.mom;
+    const float inv_n = 1.f / 128.f;
+    // window taps of this lane: input order n = lane + 32 j, output order n = (lane & 15) + 16 q + 64 (lane >> 4)
+    float2 win_in[4], win_out[4];
+    int n_out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ni = lane + 32 * j;
+        win_in[j] = make_float2(sm.win[2 * ni], sm.win[2 * ni + 1]);
+        n_out[j] = (lane & 15) + 16 * j + 64 * (lane >> 4);
+        win_out[j] = make_float2(sm.win[2 * n_out[j]] * inv_n, sm.win[2 * n_out[j] + 1] * inv_n);
+    }
+    float* ycur = sm.ya;
+    float* ynext = sm.yb;
+
+    for (int it = 0; it <= p.n_iter; ++it) {
+        for (int round = 0; round < 8; ++round) {
+            for (int t = round + 8 * warp; t < frames; t += 8 * FW) {
+                const size_t row = (size_t)t * NBIN;
+                // bins owned by this lane: k = lane + 32 j (j < 4); lane 0 also owns k = 128
+                float sv[4], sv128 = 0.f;
+                float2 tp[4], tp128 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sv[j] = __ldcg(S + row + lane + 32 * j);
+                if (lane == 0) sv128 = __ldcg(S + row + 128);
+                if (it > 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tp[j] = __ldcg(Tp + row + lane + 32 * j);
+                    if (lane == 0) tp128 = __ldcg(Tp + row + 128);
+                    // ---- forward: frame t of the current signal
+                    float2 z[4];
+                    const float* yt = ycur + HOP * t;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 v = *reinterpret_cast<const float2*>(yt + 2 * (lane + 32 * j));
+                        z[j] = make_float2(v.x * win_in[j].x, v.y * win_in[j].y);
+                    }
+                    fft128<false>(z, ex, sm.tw128, lane);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ex[n_out[q]] = z[q];
+                    __syncwarp();
+                    float2 zk[4], zn[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = lane + 32 * j;
+                        zk[j] = ex[k];
+                        zn[j] = ex[(128 - k) & 127];
+                    }
+                    const float2 z0 = ex[0];
+                    __syncwarp();
+                    // ---- split + fast Griffin-Lim update; new angles into ex[0..128]
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = lane + 32 * j;
+                        const float er = 0.5f * (zk[j].x + zn[j].x), ei = 0.5f * (zk[j].y - zn[j].y);
+                        const float dr = 0.5f * (zk[j].x - zn[j].x), di = 0.5f * (zk[j].y + zn[j].y);
+                        const float2 w = sm.tw256[k];
+                        const float xr = er + (di * w.x + dr * w.y);
+                        const float xi = ei + (di * w.y - dr * w.x);
+                        const float ar = xr - mom * tp[j].x, ai = xi - mom * tp[j].y;
+                        const float den = r_hypot(ar, ai) + r_tiny<float>();
+                        ex[k] = make_float2(ar / den * sv[j], ai / den * sv[j]);
+                        Tp[row + k] = make_float2(xr, xi);
+                    }
+                    if (lane == 0) {
+                        const float xr = z0.x - z0.y;  // Nyquist bin: real
+                        const float ar = xr - mom * tp128.x, ai = -mom * tp128.y;
+                        const float den = r_hypot(ar, ai) + r_tiny<float>();
+                        ex[128] = make_float2(ar / den * sv128, ai / den * sv128);
+                        Tp[row + 128] = make_float2(xr, 0.f);
+                    }
+                } else {
+                    // initial angles: S * exp(i phase0)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = lane + 32 * j;
+                        double sn, cs;
+                        sincos(p.phase0[(size_t)k * frames + t], &sn, &cs);
+                        ex[k] = make_float2((float)((double)sv[j] * cs), (float)((double)sv[j] * sn));
+                    }
+                    if (lane == 0) {
+                        double sn, cs;
+                        sincos(p.phase0[(size_t)128 * frames + t], &sn, &cs);
+                        ex[128] = make_float2((float)((double)sv128 * cs), (float)((double)sv128 * sn));
+                    }
+                }
+                __syncwarp();
+                // ---- inverse: c2r pre-twiddle, FFT, window, overlap-add into the next signal
+                float2 z[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = lane + 32 * j;
+                    float2 xk = ex[k], xn = ex[128 - k];
+                    if (k == 0) {  // c2r transforms ignore the imaginary parts of DC and Nyquist
+                        xk.y = 0.f;
+                        xn.y = 0.f;
+                    }
+                    const float er = 0.5f * (xk.x + xn.x), ei = 0.5f * (xk.y - xn.y);
+                    const float dr = 0.5f * (xk.x - xn.x), di = 0.5f * (xk.y + xn.y);
+                    const float2 w = sm.tw256[k];
+                    const float c = w.x, s = -w.y;  // e^{+2 pi i k / 256}
+                    const float orr = dr * c - di * s, oi = dr * s + di * c;
+                    z[j] = make_float2(er - oi, ei + orr);
+                }
+                fft128<true>(z, ex, sm.tw128, lane);
+                float* yo = ynext + HOP * t;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float2* dst = reinterpret_cast<float2*>(yo + 2 * n_out[q]);
+                    float2 acc = *dst;
+                    acc.x = fmaf(win_out[q].x, z[q].x, acc.x);
+                    acc.y = fmaf(win_out[q].y, z[q].y, acc.y);
+                    *dst = acc;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- divide by the window sum of squares (centre padding -> 0), clear the consumed buffer, swap
+        for (int n = tid; n < len4; n += FTHREADS) {
+            ynext[n] *= sm.inv_wss[n];
+            ycur[n] = 0.f;
+        }
+        __syncthreads();
+        float* tmp = ycur;
+        ycur = ynext;
+        ynext = tmp;
+    }
+    const int out_len = HOP * (frames - 1);
+    float* w = static_cast<float*>(p.wave) + (size_t)item * out_len;
+    for (int n = tid; n < out_len; n += FTHREADS) w[n] = ycur[n + NFFT / 2];
+}
+
+size_t smem_bytes(int frames) {
+    const int len = NFFT + HOP * (frames - 1);
+    const int len4 = (len + 3) & ~3;
+    return sizeof(float) * (3 * (size_t)len4 + NFFT) + sizeof(float2) * (96 + 132 + (size_t)FW * EX);
+}
+
+}  // namespace fused
+
 template <typename R>
 size_t gl_smem_bytes(int frames) {
     const int len = NFFT + HOP * (frames - 1);
@@ -250,7 +543,13 @@ extern "C" int tq_logspec_griffinlim(const float* rep, const double* phase0, voi
     p.rep = rep; p.phase0 = phase0; p.wave = wave; p.ws = ws; p.items = items; p.frames = frames; p.n_iter = n_iter;
     p.log_clip = log_clip; p.log_max = log_max; p.mom = momentum / (1.0 + momentum);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (precision == TQ_F32) {
+    const char* legacy = getenv("TQ_GL_LEGACY");
+    if (precision == TQ_F32 && !(legacy && legacy[0] == '1')) {
+        const size_t smem = fused::smem_bytes(frames);
+        TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");
+        TQ_CUDA(cudaFuncSetAttribute(fused::griffinlim_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fused::griffinlim_fused_kernel<<<items, fused::FTHREADS, smem, st>>>(p);
+    } else if (precision == TQ_F32) {
         const size_t smem = gl_smem_bytes<float>(frames);
         TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");
         TQ_CUDA(cudaFuncSetAttribute(griffinlim_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

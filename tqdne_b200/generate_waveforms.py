@@ -81,6 +81,11 @@ def load_models(edm_checkpoint, autoencoder_checkpoint, device, random_init=Fals
             for prm in edm.parameters():
                 if prm.numel() > 1 and not bool(prm.any()):
                     prm.copy_(torch.randn(prm.shape, generator=g) * (0.5 / max(1.0, float(prm[0].numel())) ** 0.5))
+            # keep the random decoder's output inside the normalised log-spectrogram range [-1, 1] (exp() of anything
+            # larger overflows the waveform scale)
+            out = ae.decoder.output_layer
+            out.weight.mul_(0.05)
+            out.bias.mul_(0.05)
     elif edm_checkpoint is None or autoencoder_checkpoint is None:
         raise ValueError("Either both or none of the checkpoints must be provided.")
     else:
