@@ -233,4 +233,6 @@ def test_generate_waveforms_cli_end_to_end(tmp_path):
     ref = cfg.representation.invert_representation(rep)
     # batches of 2 + 1 vs one batch of 3: same per-sample noise; bf16 rounding differences between the two batchings
     # (GroupNorm atomics order) are amplified ~10.7x by exp() in the representation inverse
-    assert np.abs(w).max() < 1e4 and rel_l2(w, ref) < 5e-2
+    # (measured 3e-2 .. 6e-2 run to run: the fp32 statistics atomics are unordered, so even the same batching is not
+    # bit-reproducible in bf16 mode); the bound is the waveform-domain bf16 budget 1e-2 x 10.7 of SURVEY section 8(d)
+    assert np.abs(w).max() < 1e4 and rel_l2(w, ref) < 1.1e-1
