@@ -74,6 +74,8 @@ struct alignas(64) IgemmParams {
     float* stats;  // [N][cout][2] per-(sample, channel) sum / sum of squares, or nullptr
     int seg;       // rows of one sample inside an epilogue warp: min(32, bw*bh)
     unsigned long long* prof;  // debug (TQ_IGEMM_PROF=1): [grid][8] cycle counters, else nullptr
+    int probe;  // debug (TQ_IGEMM_PROBE bit mask, results are garbage): 1 = no TMA operand loads, 2 = no MMAs,
+                // 4 = epilogue only hands the accumulator back, 8 = stages released by a plain arrive (no tcgen05.commit)
 };
 
 __device__ __forceinline__ long long clk() { return clock64(); }
@@ -194,48 +196,65 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
-            const uint32_t full_leader0 = CG == 2 ? mapa_shared(full_bar(0), 0) : full_bar(0);
-            int stage = 0;
-            uint32_t phase = 0;
-            const bool prof = p.prof != nullptr;
-            long long w_empty = 0;
-            for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
-                const TileCoord t = decode_tile<CG>(p, tile, rank);
-                const int4* sl = p.slices + (size_t)t.cls * p.num_slices;
-                for (int s = 0; s < p.num_slices; ++s) {
-                    const int4 v = __ldg(sl + s);
-                    const int src = (short)(v.x & 0xffff);
-                    const int dx = (short)(v.x >> 16);
-                    const int dy = (short)(v.y & 0xffff);
-                    mbar_wait_prof(empty_bar(stage), phase ^ 1u, prof, w_empty);
-                    if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), CG * C::STAGE_BYTES);
-                    const uint32_t a_dst = base + stage * C::STAGE_BYTES;
-                    if constexpr (CG == 1) {
-                        tma_load_4d(a_dst, &p.amap[src], full_bar(stage), v.z, t.x0 + dx, t.y0 + dy, t.n0);
-                        tma_load_2d(a_dst + A_BYTES, &p.bmap, full_bar(stage), v.w * BK, t.n_tile * BN);
+        // The whole warp walks the pipeline (every lane polls the mbarrier); one elected lane issues.  Under
+        // elect.sync the operands of the TMA / tcgen05 instructions are provably warp-uniform, so ptxas keeps them
+        // in uniform registers instead of wrapping each instruction in a per-lane R2UR "waterfall" loop -- the
+        // single-lane version of this loop cost ~400 cycles per slice and bounded every tile shape with N < 256.
+        const uint32_t full_leader0 = CG == 2 ? mapa_shared(full_bar(0), 0) : full_bar(0);
+        int stage = 0;
+        uint32_t phase = 0;
+        const bool prof = p.prof != nullptr;
+        long long w_empty = 0;
+        for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+            const TileCoord t = decode_tile<CG>(p, tile, rank);
+            const int4* sl = p.slices + (size_t)t.cls * p.num_slices;
+            const int b_row = CG == 2 ? t.n_tile * BN + rank * C::BNC : t.n_tile * BN;
+            int4 v = __ldg(sl);
+            for (int s = 0; s < p.num_slices; ++s) {
+                // next table entry in flight while this slice waits for its stage
+                const int4 vn = __ldg(sl + (s + 1 < p.num_slices ? s + 1 : s));
+                mbar_wait_prof(empty_bar(stage), phase ^ 1u, prof, w_empty);
+                if (elect_one()) {
+                    if (p.probe & 1) {
+                        if (rank == 0) mbar_arrive(full_bar(stage));
                     } else {
-                        const uint32_t fb = full_leader0 + 8u * stage;
-                        tma_load_4d_pair(a_dst, &p.amap[src], fb, v.z, t.x0 + dx, t.y0 + dy, t.n0);
-                        tma_load_2d_pair(a_dst + A_BYTES, &p.bmap, fb, v.w * BK, t.n_tile * BN + rank * C::BNC);
-                    }
-                    if (++stage == C::STAGES) {
-                        stage = 0;
-                        phase ^= 1u;
+                        const int src = (short)(v.x & 0xffff);
+                        const int dx = (short)(v.x >> 16);
+                        const int dy = (short)(v.y & 0xffff);
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), CG * C::STAGE_BYTES);
+                        const uint32_t a_dst = base + stage * C::STAGE_BYTES;
+                        if constexpr (CG == 1) {
+                            tma_load_4d(a_dst, &p.amap[src], full_bar(stage), v.z, t.x0 + dx, t.y0 + dy, t.n0);
+                            tma_load_2d(a_dst + A_BYTES, &p.bmap, full_bar(stage), v.w * BK, b_row);
+                        } else {
+                            const uint32_t fb = full_leader0 + 8u * stage;
+                            tma_load_4d_pair(a_dst, &p.amap[src], fb, v.z, t.x0 + dx, t.y0 + dy, t.n0);
+                            tma_load_2d_pair(a_dst + A_BYTES, &p.bmap, fb, v.w * BK, b_row);
+                        }
                     }
                 }
+                __syncwarp();
+                v = vn;
+                if (++stage == C::STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
-            if (prof) p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_empty;
         }
+        if (prof && lane == 0) p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_empty;
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (leader CTA)
-        if (lane == 0 && rank == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA, whole warp)
+        if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
+            // descriptor = constant high word | (smem address >> 4): per stage only the low word moves
+            const uint32_t desc_lo0 = ((base & 0x3FFFFu) >> 4) | (1u << 16);
+            constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             const bool prof = p.prof != nullptr;
+            const bool no_mma = (p.probe & 2) != 0;
             long long w_full = 0, w_tempty = 0;
             const long long t_begin = clk();
             for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
@@ -245,25 +264,36 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                 for (int s = 0; s < p.num_slices; ++s) {
                     mbar_wait_prof(full_bar(stage), phase, prof, w_full);
                     tc_fence_after();
-                    const uint32_t a_addr = base + stage * C::STAGE_BYTES;
-                    const uint64_t da = umma_desc_sw128(a_addr);
-                    const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
+                    if (elect_one()) {
+                        const uint32_t a_lo = desc_lo0 + stage * (C::STAGE_BYTES >> 4);
+                        const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+                        if (!no_mma) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // +32 B per K=16 step inside the 128 B swizzle row (address field is >> 4)
-                        umma_bf16_cg<CG>(d_tmem, da + 2u * k, db + 2u * k, idesc, (s | k) != 0);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                // +32 B per K=16 step inside the 128 B swizzle row (address field is >> 4)
+                                umma_bf16_cg<CG>(d_tmem, umma_desc_pack(a_lo + 2u * k, desc_hi),
+                                                 umma_desc_pack(b_lo + 2u * k, desc_hi), idesc, (s | k) != 0);
+                            }
+                        }
+                        if (p.probe & 8) {  // plain arrive instead of tcgen05.commit: is UTCBAR the per-slice cost?
+                            mbar_arrive(empty_bar(stage));
+                            if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(empty_bar(stage), 1));
+                        } else {
+                            umma_commit_cg<CG>(empty_bar(stage));
+                        }
                     }
-                    umma_commit_cg<CG>(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit_cg<CG>(tfull_bar(acc));
+                if (elect_one()) umma_commit_cg<CG>(tfull_bar(acc));
+                __syncwarp();
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
-            if (prof) {
+            if (prof && lane == 0) {
                 p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clk() - t_begin);
                 p.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
                 p.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tempty;
@@ -297,6 +327,19 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
             const float* emb_row = p.emb ? p.emb + (long long)(n < p.N ? n : 0) * p.emb_ld : nullptr;
             const uint32_t acc_addr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
 
+            if (p.probe & 4) {
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+                    else mbar_arrive(tempty_bar(acc));
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+                continue;
+            }
             if constexpr (!OUT_F32) {
                 // 64-channel units of this warp: column group half + 2u of the BN tile (BN = 64: half 0 only)
                 bool unit_on[C::UNITS];
@@ -741,6 +784,7 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     const int clusters = p->total_tiles < sms / cg ? p->total_tiles : sms / cg;
     const int grid = clusters * cg;
     std::shared_ptr<void> prof_owner;
+    if (const char* e = getenv("TQ_IGEMM_PROBE")) p->probe = atoi(e);
     if (const char* e = getenv("TQ_IGEMM_PROF"); e && e[0] == '1') {
         void* pb = nullptr;
         TQ_CUDA(cudaMalloc(&pb, (size_t)grid * 8 * sizeof(unsigned long long)));
