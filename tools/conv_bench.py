@@ -53,7 +53,7 @@ if __name__ == "__main__":
         # one N H W cin cout k res emb stats bn cg   (H = 1 -> 1D)
         a = [int(v) for v in sys.argv[2:]]
         sp = (a[1], a[2]) if a[1] > 1 else (a[2],)
-        bench(a[0], sp, a[3], a[4], a[5], res=bool(a[6]), emb=bool(a[7]), stats=bool(a[8]), block_n=a[9], cta_group=a[10], reps=2)
+        bench(a[0], sp, a[3], a[4], a[5], res=bool(a[6]), emb=bool(a[7]), stats=bool(a[8]), block_n=a[9], cta_group=a[10], reps=6)
         sys.exit(0)
     shapes = [(256, (32, 32), 128, 128, 3), (64, (128, 128), 64, 64, 3), (256, (16, 16), 256, 256, 3),
               (256, (4, 4), 512, 512, 3), (256, (8, 8), 512, 512, 3)]

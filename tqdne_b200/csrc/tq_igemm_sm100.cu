@@ -73,9 +73,9 @@ struct alignas(64) IgemmParams {
     long long out_class_off[4];
     float* stats;  // [N][cout][2] per-(sample, channel) sum / sum of squares, or nullptr
     int seg;       // rows of one sample inside an epilogue warp: min(32, bw*bh)
-    unsigned long long* prof;  // debug (TQ_IGEMM_PROF=1): [grid][8] cycle counters, else nullptr
+    unsigned long long* prof;  // debug (TQ_IGEMM_PROF=1): [grid][16] cycle counters, else nullptr
     int probe;  // debug (TQ_IGEMM_PROBE bit mask, results are garbage): 1 = no TMA operand loads, 2 = no MMAs,
-                // 4 = epilogue only hands the accumulator back, 8 = stages released by a plain arrive (no tcgen05.commit)
+                // 4 = epilogue only hands the accumulator back
 };
 
 __device__ __forceinline__ long long clk() { return clock64(); }
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                 }
             }
         }
-        if (prof && lane == 0) p.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_empty;
+        if (prof && lane == 0) p.prof[blockIdx.x * 16 + 3] = (unsigned long long)w_empty;
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA, whole warp)
         if (rank == 0) {
@@ -275,12 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                                                  umma_desc_pack(b_lo + 2u * k, desc_hi), idesc, (s | k) != 0);
                             }
                         }
-                        if (p.probe & 8) {  // plain arrive instead of tcgen05.commit: is UTCBAR the per-slice cost?
-                            mbar_arrive(empty_bar(stage));
-                            if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(empty_bar(stage), 1));
-                        } else {
-                            umma_commit_cg<CG>(empty_bar(stage));
-                        }
+                        umma_commit_cg<CG>(empty_bar(stage));
                     }
                     __syncwarp();
                     if (++stage == C::STAGES) {
@@ -294,9 +289,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                 if (acc == 0) acc_phase ^= 1u;
             }
             if (prof && lane == 0) {
-                p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clk() - t_begin);
-                p.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
-                p.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tempty;
+                p.prof[blockIdx.x * 16 + 0] = (unsigned long long)(clk() - t_begin);
+                p.prof[blockIdx.x * 16 + 1] = (unsigned long long)w_full;
+                p.prof[blockIdx.x * 16 + 2] = (unsigned long long)w_tempty;
             }
         }
     } else if (warp >= 4) {
@@ -319,8 +314,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
         uint32_t acc_phase = 0;
         const bool prof = p.prof != nullptr && ew == 0;
         long long w_tfull = 0, w_res = 0, w_store = 0;
+        uint32_t et[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;  // prof: pre / waits / ld+math+sts / hand-back / store / statistics
+#define TQ_EPI_T(i) do { if (prof) { const uint32_t n_ = (uint32_t)clock(); et[i] += n_ - tlast; tlast = n_; } } while (0)
         const long long e_begin = clk();
         for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+            if (prof) tlast = (uint32_t)clock();
             const TileCoord t = decode_tile<CG>(p, tile, rank);
             const int n = t.n0 + dnr, y = t.y0 + dyr, x = t.x0 + dxr;
             const bool valid = (n < p.N) && (y < p.H) && (x < p.W);
@@ -368,12 +366,23 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                             tma_load_4d(ebuf + u * EPI_BUF_BYTES, &p.rmap, rbar, t.n_tile * BN + unit_col[u], t.x0 + sx0,
                                         t.y0 + sy0, t.n0 + sn0);
                 }
+                if (emb_row) {
+                    // the per-sample embedding row is an L2 round trip: start it before the accumulator wait
+#pragma unroll
+                    for (int u = 0; u < C::UNITS; ++u)
+                        if (unit_on[u]) {
+                            prefetch_l1(emb_row + t.n_tile * BN + unit_col[u]);
+                            prefetch_l1(emb_row + t.n_tile * BN + unit_col[u] + 32);
+                        }
+                }
+                TQ_EPI_T(0);
                 mbar_wait_prof(tfull_bar(acc), acc_phase, prof, w_tfull);
                 tc_fence_after();
                 if (res) {
                     mbar_wait_prof(rbar, rphase, prof, w_res);
                     rphase ^= 1u;
                 }
+                TQ_EPI_T(1);
                 int done = 0;
 #pragma unroll
                 for (int u = 0; u < C::UNITS; ++u) {
@@ -425,6 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                             sts128(a16, make_uint4(w[0], w[1], w[2], w[3]));
                         }
                     }
+                    TQ_EPI_T(2);
                     if (++done == n_on) {
                         // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
                         tc_fence_before();
@@ -434,33 +444,40 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                             else mbar_arrive(tempty_bar(acc));
                         }
                     }
+                    TQ_EPI_T(3);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
                         tma_store_4d(&p.omap[t.cls], buf, cg0, t.x0 + sx0, t.y0 + sy0, t.n0 + sn0);
                         bulk_commit();
                     }
+                    TQ_EPI_T(4);
                     if (p.stats != nullptr) {
                         // GroupNorm statistics of the consumer: lane l owns channels cg0 + 2l, 2l+1 (one 32-bit word
                         // per row of the staging buffer); rows of one sample are p.seg consecutive rows
-                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        // (bw, bh are powers of two, so a warp's 32 rows are 32 / seg whole-sample segments)
                         const uint32_t wsel = lane >> 2, wlo = (lane & 3) << 2;
-#pragma unroll
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const uint32_t word = lds32(buf + rr * 128 + (((wsel ^ (rr & 7)) << 4) | wlo));
-                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&word);
-                            const float f0 = __low2float(b2), f1 = __high2float(b2);
-                            s0 += f0; q0 = fmaf(f0, f0, q0);
-                            s1 += f1; q1 = fmaf(f1, f1, q1);
-                            if (((rr + 1) & (p.seg - 1)) == 0) {
-                                const int ns = t.n0 + (q * 32 + rr) / rows_per_sample;
-                                if (ns < p.N)
-                                    atomicAdd(reinterpret_cast<float4*>(p.stats + ((long long)ns * p.cout + cg0 + 2 * lane) * 2),
-                                              make_float4(s0, q0, s1, q1));
-                                s0 = s1 = q0 = q1 = 0.f;
+                        const int ns0 = t.n0 + (q * 32) / rows_per_sample;
+                        const int nseg = 32 / p.seg;
+                        for (int sg = 0; sg < nseg; ++sg) {
+                            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                            const int r0 = sg * p.seg;
+#pragma unroll 8
+                            for (int r2 = 0; r2 < p.seg; ++r2) {
+                                const int rr = r0 + r2;
+                                const uint32_t word = lds32(buf + rr * 128 + (((wsel ^ (rr & 7)) << 4) | wlo));
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&word);
+                                const float f0 = __low2float(b2), f1 = __high2float(b2);
+                                s0 += f0; q0 = fmaf(f0, f0, q0);
+                                s1 += f1; q1 = fmaf(f1, f1, q1);
                             }
+                            const int ns = ns0 + (nseg > 1 ? sg : 0);
+                            if (ns < p.N)
+                                atomicAdd(reinterpret_cast<float4*>(p.stats + ((long long)ns * p.cout + cg0 + 2 * lane) * 2),
+                                          make_float4(s0, q0, s1, q1));
                         }
                     }
+                    TQ_EPI_T(5);
                 }
                 if (n_on == 0) {
                     tc_fence_before();
@@ -539,10 +556,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
             if (lane == 0) bulk_wait_read<0>();  // smem must stay alive until the last TMA stores have read it
         }
         if (prof && lane == 0) {
-            p.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clk() - e_begin);
-            p.prof[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull;
-            p.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_res;
-            p.prof[blockIdx.x * 8 + 7] = (unsigned long long)w_store;
+            p.prof[blockIdx.x * 16 + 4] = (unsigned long long)(clk() - e_begin);
+            p.prof[blockIdx.x * 16 + 5] = (unsigned long long)w_tfull;
+            p.prof[blockIdx.x * 16 + 6] = (unsigned long long)w_res;
+            p.prof[blockIdx.x * 16 + 7] = (unsigned long long)w_store;
+            for (int i = 0; i < 6; ++i) p.prof[blockIdx.x * 16 + 8 + i] = (unsigned long long)et[i];
         }
     }
 
@@ -787,8 +805,8 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     if (const char* e = getenv("TQ_IGEMM_PROBE")) p->probe = atoi(e);
     if (const char* e = getenv("TQ_IGEMM_PROF"); e && e[0] == '1') {
         void* pb = nullptr;
-        TQ_CUDA(cudaMalloc(&pb, (size_t)grid * 8 * sizeof(unsigned long long)));
-        TQ_CUDA(cudaMemset(pb, 0, (size_t)grid * 8 * sizeof(unsigned long long)));
+        TQ_CUDA(cudaMalloc(&pb, (size_t)grid * 16 * sizeof(unsigned long long)));
+        TQ_CUDA(cudaMemset(pb, 0, (size_t)grid * 16 * sizeof(unsigned long long)));
         prof_owner.reset(pb, [](void* q) { cudaFree(q); });
         p->prof = static_cast<unsigned long long*>(pb);
     }
@@ -808,14 +826,14 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
                 cudaStreamIsCapturing(st, &cs);
                 if (cs != cudaStreamCaptureStatusNone) return;
                 cudaStreamSynchronize(st);
-                std::vector<unsigned long long> h((size_t)grid * 8);
+                std::vector<unsigned long long> h((size_t)grid * 16);
                 cudaMemcpy(h.data(), p->prof, h.size() * 8, cudaMemcpyDeviceToHost);
-                double a[8] = {};
+                double a[16] = {};
                 int nl = 0;
                 for (int b = 0; b < grid; ++b) {
-                    for (int k = 3; k < 8; ++k) a[k] += (double)h[b * 8 + k] / grid;
+                    for (int k = 3; k < 16; ++k) a[k] += (double)h[b * 16 + k] / grid;
                     if (b % cg == 0) {
-                        for (int k = 0; k < 3; ++k) a[k] += (double)h[b * 8 + k];
+                        for (int k = 0; k < 3; ++k) a[k] += (double)h[b * 16 + k];
                         ++nl;
                     }
                 }
@@ -825,6 +843,9 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
                         "producer wait empty %.0f | epi warp total %.0f (wait tfull %.0f, wait res %.0f, wait store %.0f) | "
                         "%.2f tiles/cluster -> %.0f cyc/tile, %.0f cyc/slice\n", name->c_str(), a[0], a[1], a[2], a[3], a[4], a[5],
                         a[6], a[7], tiles_per, a[0] / tiles_per, a[0] / tiles_per / p->num_slices);
+                fprintf(stderr, "[igemm prof]   epilogue warp 0, cycles per tile: pre %.0f | waits %.0f | tmem ld + math + sts %.0f | "
+                        "hand-back %.0f | fence + TMA store %.0f | statistics %.0f\n", a[8] / tiles_per, a[9] / tiles_per,
+                        a[10] / tiles_per, a[11] / tiles_per, a[12] / tiles_per, a[13] / tiles_per);
             }
         } dump{p.get(), grid, cg, st, &opname};
         if (cg == 2) {

@@ -56,6 +56,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // ---- TMA --------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
@@ -141,7 +145,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (.release.cta): the hand-offs that use this order tensor memory through tcgen05 fences, and
+    // an explicit .release.cluster lowers to MEMBAR.ALL.GPU + ERRBAR (it drained the statistics atomics: ~1600 cycles)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair; the transaction bytes land on the barrier at `bar_cluster`
 // (a shared::cluster address: the leader CTA's full barrier)
