@@ -94,12 +94,16 @@ template <int BN, int CG>
 struct Cfg {
     static constexpr int BNC = BN / CG;  // weight rows staged per CTA
     static constexpr int B_BYTES = BNC * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SLICE_BYTES = A_BYTES + B_BYTES;
+    // K slices per pipeline stage: with N <= 128 one slice is only <= 256 tensor-pipe cycles, on par with the
+    // ~170-cycle mbarrier round trip per stage (tools/pipe_probe.cu), so two slices share one full/empty handshake
+    static constexpr int KS = BN >= 256 ? 1 : 2;
+    static constexpr int STAGE_BYTES = KS * SLICE_BYTES;
     static constexpr int UNITS = BN >= 128 ? BN / 128 : 1;  // 64-channel groups per epilogue warp
     static constexpr int EPI_BYTES = kEpiWarps * UNITS * EPI_BUF_BYTES;
     static constexpr int AUX_BYTES = 512;
     static constexpr int STAGES_FIT = (MAX_SMEM - 1024 - EPI_BYTES - AUX_BYTES) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
     static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + AUX_BYTES;
     static_assert(STAGES >= 3, "pipeline too shallow");
@@ -209,32 +213,46 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
             const TileCoord t = decode_tile<CG>(p, tile, rank);
             const int4* sl = p.slices + (size_t)t.cls * p.num_slices;
             const int b_row = CG == 2 ? t.n_tile * BN + rank * C::BNC : t.n_tile * BN;
-            int4 v = __ldg(sl);
-            for (int s = 0; s < p.num_slices; ++s) {
-                // next table entry in flight while this slice waits for its stage
-                const int4 vn = __ldg(sl + (s + 1 < p.num_slices ? s + 1 : s));
+            int4 v[C::KS];
+#pragma unroll
+            for (int j = 0; j < C::KS; ++j) v[j] = __ldg(sl + (j < p.num_slices ? j : 0));
+            for (int s = 0; s < p.num_slices; s += C::KS) {
+                // next table entries in flight while this group waits for its stage
+                int4 vn[C::KS];
+#pragma unroll
+                for (int j = 0; j < C::KS; ++j) {
+                    const int sn = s + C::KS + j;
+                    vn[j] = __ldg(sl + (sn < p.num_slices ? sn : s));
+                }
+                const int n_in = p.num_slices - s < C::KS ? p.num_slices - s : C::KS;
                 mbar_wait_prof(empty_bar(stage), phase ^ 1u, prof, w_empty);
                 if (elect_one()) {
                     if (p.probe & 1) {
                         if (rank == 0) mbar_arrive(full_bar(stage));
                     } else {
-                        const int src = (short)(v.x & 0xffff);
-                        const int dx = (short)(v.x >> 16);
-                        const int dy = (short)(v.y & 0xffff);
-                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), CG * C::STAGE_BYTES);
-                        const uint32_t a_dst = base + stage * C::STAGE_BYTES;
-                        if constexpr (CG == 1) {
-                            tma_load_4d(a_dst, &p.amap[src], full_bar(stage), v.z, t.x0 + dx, t.y0 + dy, t.n0);
-                            tma_load_2d(a_dst + A_BYTES, &p.bmap, full_bar(stage), v.w * BK, b_row);
-                        } else {
-                            const uint32_t fb = full_leader0 + 8u * stage;
-                            tma_load_4d_pair(a_dst, &p.amap[src], fb, v.z, t.x0 + dx, t.y0 + dy, t.n0);
-                            tma_load_2d_pair(a_dst + A_BYTES, &p.bmap, fb, v.w * BK, b_row);
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), n_in * CG * C::SLICE_BYTES);
+#pragma unroll
+                        for (int j = 0; j < C::KS; ++j) {
+                            if (j < n_in) {
+                                const int src = (short)(v[j].x & 0xffff);
+                                const int dx = (short)(v[j].x >> 16);
+                                const int dy = (short)(v[j].y & 0xffff);
+                                const uint32_t a_dst = base + stage * C::STAGE_BYTES + j * C::SLICE_BYTES;
+                                if constexpr (CG == 1) {
+                                    tma_load_4d(a_dst, &p.amap[src], full_bar(stage), v[j].z, t.x0 + dx, t.y0 + dy, t.n0);
+                                    tma_load_2d(a_dst + A_BYTES, &p.bmap, full_bar(stage), v[j].w * BK, b_row);
+                                } else {
+                                    const uint32_t fb = full_leader0 + 8u * stage;
+                                    tma_load_4d_pair(a_dst, &p.amap[src], fb, v[j].z, t.x0 + dx, t.y0 + dy, t.n0);
+                                    tma_load_2d_pair(a_dst + A_BYTES, &p.bmap, fb, v[j].w * BK, b_row);
+                                }
+                            }
                         }
                     }
                 }
                 __syncwarp();
-                v = vn;
+#pragma unroll
+                for (int j = 0; j < C::KS; ++j) v[j] = vn[j];
                 if (++stage == C::STAGES) {
                     stage = 0;
                     phase ^= 1u;
@@ -261,18 +279,24 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                 mbar_wait_prof(tempty_bar(acc), acc_phase ^ 1u, prof, w_tempty);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int s = 0; s < p.num_slices; ++s) {
+                for (int s = 0; s < p.num_slices; s += C::KS) {
+                    const int n_in = p.num_slices - s < C::KS ? p.num_slices - s : C::KS;
                     mbar_wait_prof(full_bar(stage), phase, prof, w_full);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_lo = desc_lo0 + stage * (C::STAGE_BYTES >> 4);
-                        const uint32_t b_lo = a_lo + (A_BYTES >> 4);
                         if (!no_mma) {
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                // +32 B per K=16 step inside the 128 B swizzle row (address field is >> 4)
-                                umma_bf16_cg<CG>(d_tmem, umma_desc_pack(a_lo + 2u * k, desc_hi),
-                                                 umma_desc_pack(b_lo + 2u * k, desc_hi), idesc, (s | k) != 0);
+                            for (int j = 0; j < C::KS; ++j) {
+                                if (j < n_in) {
+                                    const uint32_t a_lo = desc_lo0 + ((stage * C::STAGE_BYTES + j * C::SLICE_BYTES) >> 4);
+                                    const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+#pragma unroll
+                                    for (int k = 0; k < BK / 16; ++k) {
+                                        // +32 B per K=16 step inside the 128 B swizzle row (address field is >> 4)
+                                        umma_bf16_cg<CG>(d_tmem, umma_desc_pack(a_lo + 2u * k, desc_hi),
+                                                         umma_desc_pack(b_lo + 2u * k, desc_hi), idesc, (s | j | k) != 0);
+                                    }
+                                }
                             }
                         }
                         umma_commit_cg<CG>(empty_bar(stage));
@@ -406,6 +430,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                             }
                             add[j] = b.x; add[j + 1] = b.y; add[j + 2] = b.z; add[j + 3] = b.w;
                         }
+                        // the four residual chunks of this row half: all loads issued back to back, ahead of the wait
+                        uint4 rq[4];
+                        if (res) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) rq[j] = lds128(rowp + (((h2 * 4 + j) ^ (lane & 7)) << 4));
+                        }
                         tmem_ld_wait();
                         float v[32];
 #pragma unroll
@@ -415,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                             // 16 B chunk (h2*4 + j) of this row sits at chunk position (.. ^ (row & 7)): SWIZZLE_128B
                             const uint32_t a16 = rowp + (((h2 * 4 + j) ^ (lane & 7)) << 4);
                             if (res) {
-                                const uint4 u4 = lds128(a16);
+                                const uint4 u4 = rq[j];
                                 const uint32_t rw[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
@@ -462,14 +492,25 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                         for (int sg = 0; sg < nseg; ++sg) {
                             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
                             const int r0 = sg * p.seg;
-#pragma unroll 8
-                            for (int r2 = 0; r2 < p.seg; ++r2) {
-                                const int rr = r0 + r2;
-                                const uint32_t word = lds32(buf + rr * 128 + (((wsel ^ (rr & 7)) << 4) | wlo));
-                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&word);
-                                const float f0 = __low2float(b2), f1 = __high2float(b2);
-                                s0 += f0; q0 = fmaf(f0, f0, q0);
-                                s1 += f1; q1 = fmaf(f1, f1, q1);
+                            // seg is a power of two: groups of min(seg, 8) rows, the loads of a group issued together
+                            // (one destination register per load, or ptxas serialises them on LDS latency)
+                            const int grp = p.seg < 8 ? p.seg : 8;
+                            for (int r2 = 0; r2 < p.seg; r2 += grp) {
+                                uint32_t wv[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int rr = r0 + r2 + (k < grp ? k : 0);
+                                    wv[k] = lds32(buf + rr * 128 + (((wsel ^ (rr & 7)) << 4) | wlo));
+                                }
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    if (k < grp) {
+                                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&wv[k]);
+                                        const float f0 = __low2float(b2), f1 = __high2float(b2);
+                                        s0 += f0; q0 = fmaf(f0, f0, q0);
+                                        s1 += f1; q1 = fmaf(f1, f1, q1);
+                                    }
+                                }
                             }
                             const int ns = ns0 + (nseg > 1 ? sg : 0);
                             if (ns < p.N)
