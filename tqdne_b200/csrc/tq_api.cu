@@ -80,6 +80,14 @@ int tq_plan_run(tq_plan* p, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int n = (int)p->ops.size();
     if (!p->use_graph) return run_ops(p, 0, n, st);
+    {
+        // inside a caller-owned stream capture a graph launch is not permitted: record the plan's kernels into the
+        // caller's graph instead.  (Tried for the sampler: one graph over all 49 denoiser calls + update kernels is
+        // NOT faster than 49 per-call graph launches at batch 256 or 32 -- the step is power-capped, not gap-bound.)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        TQ_CUDA(cudaStreamIsCapturing(st, &cs));
+        if (cs != cudaStreamCaptureStatusNone) return run_ops(p, 0, n, st);
+    }
     if (p->graph_exec == nullptr || p->graph_ops != p->ops.size()) {
         drop_graph(p);
         // one eager pass first: cudaFuncSetAttribute calls are not capturable

@@ -317,12 +317,21 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
     p->gamma = d.gamma; p->beta = d.beta; p->eps = d.eps; p->silu = d.silu; p->y = d.y; p->ws = d.ws;
     p->st0 = have_stats ? d.stats0 : d.ws;
     p->st1 = have_stats ? d.stats1 : (d.C1 > 0 ? d.ws + (size_t)d.N * d.C0 * 2 : nullptr);
-    int chunks = (8 * device_sm_count() + d.N - 1) / d.N;
+    // position chunks per sample: the grid (chunks x N CTAs) should fill whole waves of the resident-CTA slots
+    // (4 CTAs/SM for bf16, 2 for fp32) -- N = 256 with 5 chunks was 2.16 waves, i.e. a third wave at 16 % occupancy
+    const bool f32 = d.dtype == TQ_F32;
+    const int slots = device_sm_count() * (f32 ? 2 : 4);
     const int max_chunks = (d.P + 31) / 32;
+    // one wave of large chunks: every extra chunk repeats the statistics prologue (an L2 round trip + barrier)
+    // before it streams; measured over the 51 norms of a UNet call at N = 256: 2 chunks 0.93 ms, 5 chunks 1.03 ms
+    int chunks = slots / (d.N > 0 ? d.N : 1);
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
+    if (const char* e = getenv("TQ_GN_CHUNKS")) {  // experiments only
+        const int c = atoi(e);
+        if (c >= 1 && c <= max_chunks) chunks = c;
+    }
     p->chunks = chunks;
-    const bool f32 = d.dtype == TQ_F32;
     const size_t ws_bytes = (size_t)d.N * Ct * 2 * sizeof(float);
     const size_t smem = 0;
     dim3 grid(chunks, d.N);
