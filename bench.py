@@ -376,7 +376,16 @@ def run_engine(args) -> None:
             "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
             "peak_source": f"{pk['source']} bf16 burst (MEASURED_PEAKS.json)", "traffic": None,
             "launches_per_call": conv["launches"], "share_of_denoiser_call": conv["ms"] / tot_ms,
+            "frac_of_sustained_peak": ach / pk["bf16_tflops_sustained"],
         }
+        # DRAM bytes per launch from the committed ncu capture of the same launches (tools/summarize_dram.py)
+        tfile = ROOT / "profiles" / "igemm_dram_traffic.json"
+        if tfile.exists():
+            tj = json.loads(tfile.read_text())
+            if tj.get("launches") == conv["launches"]:
+                line["roofline"]["traffic"] = tj["bytes_per_launch"]
+                line["roofline"]["traffic_unit"] = "DRAM bytes per launch (read + write), ncu"
+                line["roofline"]["algorithmic_bytes_per_launch"] = conv.get("bytes", 0) / conv["launches"] or None
         gn = {k: agg[k] for k in agg if k.startswith("gn_")}
         if gn:
             gb = sum(a["bytes"] for a in gn.values())

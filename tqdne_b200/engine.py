@@ -358,7 +358,12 @@ class Plan:
             out.stats = self._stats_alloc(N * pc.cout * 2)
             d.stats = out.stats.data_ptr()
         _lib.check(self.lib.tq_plan_add_conv(self.h, C.byref(d)), "plan_add_conv")
-        self.op_meta.append(("conv", 2 * N * Ho * Wo * pc.cout * pc.macs_per_out, 0))
+        # algorithmic bytes: every source once, weights once, output once (+ residual once)
+        io_bytes = sum(n_ * h_ * w_ * c_ for (_, _, n_, h_, w_, c_, _, _, _) in src_views) * esz
+        io_bytes += pc.weights.numel() * pc.weights.element_size() + out.t.numel() * out.t.element_size()
+        if residual is not None:
+            io_bytes += residual.t.numel() * residual.t.element_size()
+        self.op_meta.append(("conv", 2 * N * Ho * Wo * pc.cout * pc.macs_per_out, io_bytes))
         self.keep += [pc.weights, pc.bias, emb, out.t] + [v[0] for v in src_views]
         if residual is not None:
             self.keep.append(residual.t)
