@@ -206,6 +206,22 @@ int tq_logspec_griffinlim(const float* rep, const double* phase0, void* wave, in
 int tq_mavg_envelope_inverse(const float* rep, float* wave, int32_t N, int32_t Cw, int64_t L,
                              double log_eps, double eps, void* stream);
 
+
+/* ---- forward representations (the step before the path: SURVEY 8(f) rank 2) ------------------------- *
+ * tq_logspec_forward replaces LogSpectrogram.get_representation (tqdne/representation.py:140-150,
+ * 163-169) with librosa 0.11 stft(x, n_fft, hop_length) semantics (center=True, zero padding, periodic
+ * Hann): wave:[items, L] fp32 -> rep:[items, n_fft/2, frames] (Nyquist row dropped), frames = 1 + L/hop,
+ * rep = 2*(log(max(|S|, clip)) - log(clip)) / (log_max - log(clip)) - 1.  precision: arithmetic
+ * (TQ_F32 like librosa on float32 input, TQ_F64 like float64 input); rep_dtype: TQ_F32 or TQ_F64.      */
+int tq_logspec_forward(const float* wave, void* rep, int32_t rep_dtype, int32_t items, int32_t n_fft,
+                       int32_t hop, int64_t L, int32_t frames, double clip, double log_max,
+                       int32_t precision, void* stream);
+/* tq_mavg_envelope_forward replaces MovingAverageEnvelope.get_representation (representation.py:47-55):
+ * wave:[N,Cw,L] fp32 -> rep:[N,2*Cw,L] fp32 = cat(x/(env+eps), log(env+log_eps) - log(log_eps)/2),
+ * env = np.convolve(|x|, ones(window)/window, mode="same").                                              */
+int tq_mavg_envelope_forward(const float* wave, float* rep, int32_t N, int32_t Cw, int64_t L,
+                             int32_t window, double log_eps, double eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,27 @@ def logspec_inverse(rep: np.ndarray, clip: float = 1e-8, log_max: float = 3, n_f
     return out.reshape(shape[:-2] + out.shape[1:])
 
 
+# ---- forward representations (tqdne/representation.py:47-55 and :140-150,163-169) --------------------------------
+def logspec_forward(wave: np.ndarray, clip: float = 1e-8, log_max: float = 3, n_fft: int = 256, hop: int = 32) -> np.ndarray:
+    """LogSpectrogram.get_representation with librosa.stft restated by `stft` above: wave [.., L] -> [.., n_fft/2, frames].
+    The arithmetic precision follows wave.dtype, like librosa (float32 in -> complex64)."""
+    wave = np.asarray(wave)
+    shape = wave.shape
+    flat = wave.reshape(-1, shape[-1])
+    spec = np.array([stft(x, n_fft, hop) for x in flat])[:, :-1]      # drop the Nyquist row
+    spec = np.abs(spec.reshape(shape[:-1] + spec.shape[1:]))
+    log_clip = np.log(clip)
+    log_spec = np.log(np.clip(spec, clip, None))
+    return (log_spec - log_clip) / (log_max - log_clip) * 2 - 1
+
+
+def mavg_forward(wave: np.ndarray, window: int = 128, log_eps: float = 1e-6, eps: float = 1e-6) -> np.ndarray:
+    """MovingAverageEnvelope.get_representation: [.., C, L] -> [.., 2C, L]."""
+    wave = np.asarray(wave)
+    env = np.apply_along_axis(lambda x: np.convolve(x, np.ones(window) / window, mode="same"), axis=-1, arr=np.abs(wave))
+    return np.concatenate([wave / (env + eps), np.log(env + log_eps) - np.log(log_eps) / 2], axis=-2)
+
+
 # ---- a line-by-line NumPy model of the CUDA kernel's FFT decomposition (csrc/tq_griffinlim.cu) -----------
 def kernel_model_rfft256(x: np.ndarray) -> np.ndarray:
     """rfft-256 via one 128-point complex FFT + even/odd split, as the kernel computes it."""

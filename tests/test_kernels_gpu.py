@@ -493,3 +493,62 @@ def test_griffinlim_full_iterations_and_golden():
         return np.linalg.norm(np.abs(griffinlim_ref.stft(wave.astype(np.float64)))[:-1] - S) / np.linalg.norm(S)
 
     assert abs(inconsistency(w32[0, 0]) - inconsistency(ref[0, 0])) < 2e-2
+
+
+# ---- forward representations ---------------------------------------------------------------
+def test_mavg_envelope_forward_matches_golden_and_oracle():
+    import tqdne_b200 as tq
+    from oracle import griffinlim_ref
+    from tests.helpers import golden
+
+    rep = tq.MovingAverageEnvelope()
+    g = golden("mavg_forward")
+    out = rep.get_representation(g["wave"].cuda())
+    assert out.shape == tuple(g["rep"].shape) and out.dtype == np.float32
+    assert rel_l2(out, g["rep"]) < 1e-6
+    # ragged length, window longer than the signal's edge regions, and the round trip through the inverse kernel
+    rng = np.random.default_rng(7)
+    w = rng.standard_normal((3, 3, 777)).astype(np.float32)
+    out = rep.get_representation(w)
+    assert rel_l2(out, griffinlim_ref.mavg_forward(w)) < 1e-6
+    assert rel_l2(rep.invert_representation(out), w) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_logspec_forward_matches_golden_and_oracle(precision):
+    import tqdne_b200 as tq
+    from oracle import griffinlim_ref
+    from tests.helpers import golden
+
+    ls = tq.LogSpectrogram(stft_channels=256, hop_size=32, precision=precision)  # SpectrogramConfig
+    g = golden("logspec_forward")
+    out = ls.get_representation(g["wave"].cuda())
+    assert out.shape == (1, 3, 128, 128)
+    ref = g["rep64" if precision == "fp64" else "rep32"].numpy()
+    # values live in [-1, 1]; a float32 STFT of O(1) magnitudes leaves ~1e-6 on the log-magnitudes
+    assert np.abs(out - ref).max() < (1e-9 if precision == "fp64" else 2e-5)
+    rng = np.random.default_rng(8)
+    w = rng.standard_normal((5, 3, 4064)).astype(np.float32)
+    w[0, 0] = 0.0            # silent channel: every bin clips to the floor -> -1
+    out = ls.get_representation(w)
+    ref = griffinlim_ref.logspec_forward(w.astype(np.float64) if precision == "fp64" else w)
+    assert np.abs(out - ref).max() < (1e-9 if precision == "fp64" else 2e-5)
+    assert np.all(out[0, 0] == -1.0)
+
+
+def test_logspec_forward_full_batch_scaling_property():
+    """Full bench size (256 x 3 items): scaling a waveform by a shifts every unclipped log-magnitude by
+    2 log(a) / (log_max - log_clip) -- a size-independent check of all 768 CTAs."""
+    import tqdne_b200 as tq
+
+    ls = tq.LogSpectrogram(stft_channels=256, hop_size=32)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    w = torch.randn(256, 3, 4064, device="cuda", generator=gen)
+    a = 3.5
+    r1 = ls.get_representation_device(w)
+    r2 = ls.get_representation_device(w * a)
+    shift = 2 * np.log(a) / (ls.log_max - ls.log_clip)
+    assert r1.shape == (256, 3, 128, 128)
+    err = (r2 - r1 - shift).abs()
+    # fp32 STFT: bins where the frame nearly cancels carry a larger relative error, which the log amplifies
+    assert float(err.max()) < 5e-3 and float((err > 1e-4).float().mean()) < 1e-4

@@ -149,3 +149,15 @@ def test_griffinlim_properties():
     e4 = inconsistency(griffinlim_ref.griffinlim(S, n_iter=4))
     e32 = inconsistency(griffinlim_ref.griffinlim(S, n_iter=32))
     assert e32 < e4 < 1.0
+
+
+def test_forward_representations_match_reference_golden():
+    """oracle restatements of get_representation vs the reference's own methods (oracle/make_golden_forward.py)."""
+    g = golden("mavg_forward")
+    assert rel_l2(griffinlim_ref.mavg_forward(g["wave"].numpy()), g["rep"]) < 1e-12
+    g = golden("logspec_forward")
+    w = g["wave"].numpy()
+    r64 = griffinlim_ref.logspec_forward(w.astype(np.float64))
+    assert r64.shape == (1, 3, 128, 128) and np.abs(r64 - g["rep64"].numpy()).max() < 1e-12
+    r32 = griffinlim_ref.logspec_forward(w)
+    assert np.abs(r32 - g["rep32"].numpy()).max() < 1e-5

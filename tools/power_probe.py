@@ -66,7 +66,48 @@ def sustained(name, plan, flop, seconds=2.0):
     print(f"{name:44s} {flop / ms / 1e9:8.1f} TF/s sustained | SM {smi.mhz:6.0f} MHz | {smi.watt:6.0f} W", flush=True)
 
 
+def gn_plan(N, sp, C, reps=20):
+    H, W = sp
+    x = torch.randn(N * H * W * C, device=dev).to(torch.bfloat16)
+    plan = Plan(dev, torch.bfloat16)
+    xa = Act(x, N, H, W, C)
+    g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    for _ in range(reps):
+        plan.groupnorm([xa], g, b, True)   # stand-alone statistics pass + apply (no producing conv here)
+    plan.enable_graph(True)
+    return plan, N * H * W * C * 2 * reps
+
+
+def sustained_bytes(name, plan, nbytes, seconds=2.0):
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            plan.run()
+        s.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 0
+        with Smi() as smi:
+            t0 = time.perf_counter()
+            e0.record(s)
+            while time.perf_counter() - t0 < seconds:
+                for _ in range(10):
+                    plan.run()
+                n += 10
+                s.synchronize()
+            e1.record(s)
+            s.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"{name:44s} {3 * nbytes / ms / 1e6:8.1f} GB/s (stats read + apply read/write) | SM {smi.mhz:6.0f} MHz | {smi.watt:6.0f} W",
+          flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gn":
+        for nm, a in [("gn 128ch @32^2 (67 MB)", (256, (32, 32), 128)), ("gn 256ch @32^2 (134 MB)", (256, (32, 32), 256)),
+                      ("gn 512ch @8^2 (17 MB)", (256, (8, 8), 512)), ("gn 512ch @4^2 (4 MB)", (256, (4, 4), 512))]:
+            plan, nb = gn_plan(*a)
+            sustained_bytes(nm, plan, nb)
+        sys.exit(0)
     a = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
     b = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
 

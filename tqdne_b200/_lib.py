@@ -117,6 +117,8 @@ SIGNATURES = {
     "tq_griffinlim_ws_bytes": (_I64, [_I32, _I32, _I32, _I32]),
     "tq_logspec_griffinlim": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _D, _D, _D, _I32, _VP, _VP]),
     "tq_mavg_envelope_inverse": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _D, _D, _VP]),
+    "tq_logspec_forward": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I64, _I32, _D, _D, _I32, _VP]),
+    "tq_mavg_envelope_forward": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _I32, _D, _D, _VP]),
 }
 
 _lib = None

@@ -44,6 +44,17 @@ static int run_ops(tq_plan* p, int first, int last, cudaStream_t st) {
     return 0;
 }
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        // off unless TQ_PDL=1: measured on the latent UNet plan at batch 256 (tools/ab_env.py TQ_PDL 0 1) the
+        // programmatic edges are 1.3 % SLOWER (4.745 vs 4.685 ms) -- the step is power-capped, so filling the
+        // inter-kernel gaps only lowers the clock
+        const char* e = getenv("TQ_PDL");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 }  // namespace tq
 
 using namespace tq;

@@ -33,6 +33,8 @@ __device__ __forceinline__ void st_f(__nv_bfloat16* p, float v) { *p = __float2b
 template <typename T, int D>
 __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     extern __shared__ float sm[];
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int PITCH = D + 1;
     float* Ks = sm;                       // [KBLK][PITCH]
     float* Vs = Ks + KBLK * PITCH;        // [KBLK][PITCH]
@@ -156,6 +158,8 @@ __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float
 template <typename T, int D>
 __global__ void __launch_bounds__(128) attention_small_kernel(const AttnParams p) {
     extern __shared__ float sm[];
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int PITCH = D + 1;
     const int Tn = p.T;
     float* Qs = sm;                  // [T][PITCH]
@@ -224,7 +228,7 @@ int launch_attn(const AttnParams& p, cudaStream_t st) {
             TQ_CUDA(cudaFuncSetAttribute(attention_small_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             attr_small = true;
         }
-        attention_small_kernel<T, D><<<p.N * p.heads, 128, smem, st>>>(p);
+        TQ_CUDA(launch_pdl(attention_small_kernel<T, D>, dim3(p.N * p.heads), dim3(128), smem, st, p));
         TQ_CUDA(cudaGetLastError());
         count_launch();
         return 0;
@@ -236,7 +240,7 @@ int launch_attn(const AttnParams& p, cudaStream_t st) {
         attr_set = true;
     }
     const int qblocks = (p.T + QB - 1) / QB;
-    attention_kernel<T, D><<<p.N * p.heads * qblocks, 128, smem, st>>>(p);
+    TQ_CUDA(launch_pdl(attention_kernel<T, D>, dim3(p.N * p.heads * qblocks), dim3(128), smem, st, p));
     TQ_CUDA(cudaGetLastError());
     count_launch();
     return 0;

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <functional>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/tqdne_b200.h"
@@ -40,6 +41,30 @@ struct Op {
 };
 
 int device_sm_count();
+// Programmatic dependent launch (opt-in: TQ_PDL=1): consecutive kernels of a plan overlap the next kernel's
+// launch latency and prologue with the previous kernel's drain; every kernel launched this way executes
+// griddepcontrol.wait before it touches memory a predecessor may still be writing.
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // builders implemented in the kernel translation units; each appends >= 1 Op
 int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d);

@@ -44,6 +44,8 @@ __device__ __forceinline__ void linear_epilogue(const LinParams& p, float a, int
 // one warp per dot product; with a single shared input row (x_rows == 1: every sample of a sampler step has the
 // same noise level) the dot product is computed once per output column and the epilogue fans out over the rows
 __global__ void __launch_bounds__(256) linear_kernel(const LinParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const bool shared_row = p.x_rows == 1;
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(256) linear_kernel(const LinParams p) {
 // Reference: GaussianFourierProjection.forward (tqdne/blocks.py:22-26): h = x[:,None]*W[None,:]*2*pi;
 // cat([sin h, cos h]).
 __global__ void fourier_kernel(const float* t, const float* W, int M, int half, float* feat) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * half) return;
     const int m = i / half, k = i % half;
@@ -294,6 +298,28 @@ __global__ void mavg_inverse_kernel(const float* rep, float* wave, int Cw, long 
     wave[i] = (float)(sw * (exp(le + half_log_eps) + eps));
 }
 
+// Reference: MovingAverageEnvelope.get_representation (tqdne/representation.py:47-55).  np.convolve(|x|, ones(w)/w,
+// mode="same") = mean of |x| over [n - w/2, n + (w-1)/2 ... ] -- for even w: indices n - w/2 .. n + w/2 - 1, zero outside;
+// rep = cat([x / (env + eps), log(env + log_eps) - log(log_eps)/2], axis=-2)
+__global__ void mavg_forward_kernel(const float* wave, float* rep, int Cw, long long L, long long total, int window,
+                                    double log_eps, double half_log_eps, double eps) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long l = i % L;
+    const long long r = i / L;
+    const int c = (int)(r % Cw);
+    const long long n = r / Cw;
+    const float* x = wave + r * L;
+    // 'same' keeps full[(w-1)/2 : (w-1)/2 + L]:  env[l] = sum_{k = l + (w-1)/2 - (w-1)}^{l + (w-1)/2} |x[k]| / w
+    const long long hi = l + (window - 1) / 2, lo = hi - (window - 1);
+    double acc = 0.0;
+    const double inv = 1.0 / (double)window;
+    for (long long kk = (lo < 0 ? 0 : lo); kk <= hi && kk < L; ++kk) acc += fabs((double)x[kk]) * inv;
+    const double xv = (double)x[l];
+    rep[(n * 2 * Cw + c) * L + l] = (float)(xv / (acc + eps));
+    rep[(n * 2 * Cw + Cw + c) * L + l] = (float)(log(acc + log_eps) - half_log_eps);
+}
+
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -311,7 +337,7 @@ int build_linear(std::vector<Op>& ops, const tq_linear_desc& d) {
     op.name = "linear_f32";
     op.launch = [p](cudaStream_t st) -> int {
         const long long warps = p->x_rows == 1 ? p->Nout : (long long)p->M * p->Nout;
-        linear_kernel<<<blocks_for(warps * 32, 256), 256, 0, st>>>(*p);
+        TQ_CUDA(launch_pdl(linear_kernel, dim3(blocks_for(warps * 32, 256)), dim3(256), 0, st, *p));
         TQ_CUDA(cudaGetLastError());
         count_launch();
         return 0;
@@ -325,7 +351,7 @@ int build_fourier(std::vector<Op>& ops, const float* t, const float* W, int M, i
     Op op;
     op.name = "fourier_features";
     op.launch = [=](cudaStream_t st) -> int {
-        fourier_kernel<<<blocks_for((long long)M * half, 128), 128, 0, st>>>(t, W, M, half, feat);
+        TQ_CUDA(launch_pdl(fourier_kernel, dim3(blocks_for((long long)M * half, 128)), dim3(128), 0, st, t, W, M, half, feat));
         TQ_CUDA(cudaGetLastError());
         count_launch();
         return 0;
@@ -478,6 +504,17 @@ extern "C" int tq_mavg_envelope_inverse(const float* rep, float* wave, int32_t N
     const long long total = (long long)N * Cw * L;
     mavg_inverse_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rep, wave, Cw, L, total,
                                                                                               log(log_eps) / 2.0, eps);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int tq_mavg_envelope_forward(const float* wave, float* rep, int32_t N, int32_t Cw, int64_t L, int32_t window,
+                                        double log_eps, double eps, void* stream) {
+    TQ_CHECK(wave && rep && N > 0 && Cw > 0 && L > 0 && window > 0, "mavg_envelope_forward: bad arguments");
+    const long long total = (long long)N * Cw * L;
+    mavg_forward_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        wave, rep, Cw, L, total, window, log_eps, log(log_eps) / 2.0, eps);
     TQ_CUDA(cudaGetLastError());
     count_launch();
     return 0;

@@ -225,6 +225,76 @@ __global__ void __launch_bounds__(GL_THREADS) griffinlim_kernel(const GlParams p
 }
 
 // =====================================================================================================
+// Forward representation: LogSpectrogram.get_representation (tqdne/representation.py:140-150,163-169) with
+// librosa 0.11 stft(x, n_fft=256, hop_length=32) semantics (center=True, zero padding, periodic Hann):
+//   rep[f][t] = 2 * (log(max(|STFT(x)[f][t]|, clip)) - log_clip) / (log_max - log_clip) - 1,   f < n_fft/2
+// One CTA per (sample, component): the padded signal sits in shared memory, a warp owns a frame (the same
+// 128-point complex FFT + even/odd split as the inverse), and the [128 x frames] tile leaves coalesced.
+template <typename R, typename TO>
+__global__ void __launch_bounds__(GL_THREADS) logspec_forward_kernel(const float* wave, TO* rep, long long L, int frames,
+                                                                     double clip, double log_clip, double log_max) {
+    extern __shared__ __align__(16) unsigned char gl_smem[];
+    const int len = NFFT + HOP * (frames - 1);
+    R* ypad = reinterpret_cast<R*>(gl_smem);
+    R* win = ypad + ((len + 3) & ~3);
+    Cx<R>* tw128 = reinterpret_cast<Cx<R>*>(win + NFFT);
+    Cx<R>* tw256 = tw128 + 64;
+    Cx<R>* bufs = tw256 + 132;
+    TO* tile = reinterpret_cast<TO*>(bufs + GL_WARPS * 128);  // [128][frames + 1]
+    const int item = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Cx<R>* buf = bufs + warp * 128;
+    const float* x = wave + (size_t)item * L;
+    for (int i = tid; i < len; i += GL_THREADS) {
+        const long long j = (long long)i - NFFT / 2;
+        ypad[i] = (j >= 0 && j < L) ? (R)x[j] : (R)0;
+    }
+    for (int i = tid; i < NFFT; i += GL_THREADS) win[i] = (R)(0.5 - 0.5 * cospi(2.0 * i / NFFT));
+    for (int i = tid; i < 64; i += GL_THREADS) {
+        double sn, cs;
+        sincospi(-2.0 * i / 128.0, &sn, &cs);
+        tw128[i] = Cx<R>{(R)cs, (R)sn};
+    }
+    for (int i = tid; i <= 128; i += GL_THREADS) {
+        double sn, cs;
+        sincospi(-2.0 * i / 256.0, &sn, &cs);
+        tw256[i] = Cx<R>{(R)cs, (R)sn};
+    }
+    __syncthreads();
+    const int pitch = frames + 1;
+    const double scale = 2.0 / (log_max - log_clip);
+    for (int t = warp; t < frames; t += GL_WARPS) {
+        const R* yt = ypad + HOP * t;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int n = lane + 32 * i;
+            buf[bitrev7(n)] = Cx<R>{yt[2 * n] * win[2 * n], yt[2 * n + 1] * win[2 * n + 1]};
+        }
+        __syncwarp();
+        fft128<R, false>(buf, tw128, lane);
+        for (int k = lane; k < 128; k += 32) {
+            const Cx<R> zk = buf[k & 127];
+            const Cx<R> zn = buf[(128 - k) & 127];
+            const R er = (R)0.5 * (zk.x + zn.x), ei = (R)0.5 * (zk.y - zn.y);
+            const R dr = (R)0.5 * (zk.x - zn.x), di = (R)0.5 * (zk.y + zn.y);
+            const R c = tw256[k].x, sn = tw256[k].y;  // e^{-2 pi i k / 256}
+            const R xr = er + (di * c + dr * sn);
+            const R xi = ei + (di * sn - dr * c);
+            double mag = (double)r_hypot(xr, xi);
+            mag = mag < clip ? clip : mag;
+            tile[k * pitch + t] = (TO)((log(mag) - log_clip) * scale - 1.0);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    TO* out = rep + (size_t)item * 128 * frames;
+    for (int idx = tid; idx < 128 * frames; idx += GL_THREADS) {
+        const int f = idx / frames, t = idx - f * frames;
+        out[idx] = tile[f * pitch + t];
+    }
+}
+
+// =====================================================================================================
 // fp32 fast path: fused  STFT(frame t) -> phase update -> inverse FFT(frame t) -> overlap-add  per frame.
 //
 // The rebuilt spectrum never leaves the SM: a warp transforms frame t of the current signal, applies the fast
@@ -560,6 +630,33 @@ extern "C" int tq_logspec_griffinlim(const float* rep, const double* phase0, voi
         TQ_CUDA(cudaFuncSetAttribute(griffinlim_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         griffinlim_kernel<double><<<items, GL_THREADS, smem, st>>>(p);
     }
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int tq_logspec_forward(const float* wave, void* rep, int32_t rep_dtype, int32_t items, int32_t n_fft, int32_t hop,
+                                  int64_t L, int32_t frames, double clip, double log_max, int32_t precision, void* stream) {
+    TQ_CHECK(n_fft == NFFT && hop == HOP, "logspec_forward: only n_fft=256, hop=32 is built (reference SpectrogramConfig)");
+    TQ_CHECK(wave && rep && items > 0 && L > 0, "logspec_forward: bad arguments");
+    TQ_CHECK(frames == 1 + (int)(L / HOP), "logspec_forward: frames must be 1 + L / hop (center=True)");
+    TQ_CHECK(precision == TQ_F32 || precision == TQ_F64, "logspec_forward: precision must be TQ_F32 or TQ_F64");
+    TQ_CHECK(rep_dtype == TQ_F32 || rep_dtype == TQ_F64, "logspec_forward: rep_dtype must be TQ_F32 or TQ_F64");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double log_clip = log(clip);
+#define TQ_LSF(R, TO)                                                                                                   \
+    do {                                                                                                                \
+        const size_t smem = gl_smem_bytes<R>(frames) + (size_t)128 * (frames + 1) * sizeof(TO);                                                          \
+        TQ_CHECK(smem <= 227 * 1024, "logspec_forward: too many frames for shared memory");                             \
+        TQ_CUDA(cudaFuncSetAttribute(logspec_forward_kernel<R, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        logspec_forward_kernel<R, TO><<<items, GL_THREADS, smem, st>>>(wave, static_cast<TO*>(rep), L, frames, clip, log_clip, \
+                                                                      log_max);                                        \
+    } while (0)
+    if (precision == TQ_F32 && rep_dtype == TQ_F32) TQ_LSF(float, float);
+    else if (precision == TQ_F32) TQ_LSF(float, double);
+    else if (rep_dtype == TQ_F32) TQ_LSF(double, float);
+    else TQ_LSF(double, double);
+#undef TQ_LSF
     TQ_CUDA(cudaGetLastError());
     count_launch();
     return 0;

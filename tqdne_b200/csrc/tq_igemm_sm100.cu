@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+    pdl_launch_dependents();  // the next kernel of the plan may take this SM as soon as this CTA leaves it
     const int cluster_id = blockIdx.x / CG;
     const int num_clusters = gridDim.x / CG;
 
@@ -197,6 +198,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
     if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must exist before anything remote targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, tensor memory, descriptor prefetch) overlapped the previous kernel's drain;
+    // from here on this kernel reads what its predecessors wrote
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -681,13 +685,15 @@ int launch_igemm(const IgemmParams& p, int grid, cudaStream_t st) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     TQ_CUDA(cudaLaunchKernelEx(&cfg, igemm_sm100_kernel<BN, CG, OUT_F32>, p));
     count_launch();
     return 0;

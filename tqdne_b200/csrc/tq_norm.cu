@@ -240,21 +240,23 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(c
     const int Ct = p.C0 + p.C1;
     const int cpg = Ct / 32;
     T* y = static_cast<T*>(p.y);
+    pdl_launch_dependents();
     SrcView<T> v0 = make_view<T>(static_cast<const T*>(p.x0), p.C0, 0, Ct, p.P, n, chunk, p.chunks, y);
-    // (1) everything that does not depend on the statistics goes out first: the first batch of activations
-    // and this thread's gamma / beta
-    Raw8<T> pre[GN_UNROLL];
-    const bool have_pre = v0.on && v0.pix + (GN_UNROLL - 1) * v0.lanes < v0.p1;
-    if (have_pre) {
-#pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) pre[u].load(v0.xb + (long long)(v0.pix + u * v0.lanes) * v0.C);
-    }
+    // (0) gamma / beta are weights: they do not wait for the producing kernel
     float4 g4[2], b4[2];
     if (v0.on) {
         g4[0] = __ldg(reinterpret_cast<const float4*>(p.gamma + v0.cvec0));
         g4[1] = __ldg(reinterpret_cast<const float4*>(p.gamma + v0.cvec0) + 1);
         b4[0] = __ldg(reinterpret_cast<const float4*>(p.beta + v0.cvec0));
         b4[1] = __ldg(reinterpret_cast<const float4*>(p.beta + v0.cvec0) + 1);
+    }
+    pdl_wait();
+    // (1) everything that does not depend on the statistics goes out first: the first batch of activations
+    Raw8<T> pre[GN_UNROLL];
+    const bool have_pre = v0.on && v0.pix + (GN_UNROLL - 1) * v0.lanes < v0.p1;
+    if (have_pre) {
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) pre[u].load(v0.xb + (long long)(v0.pix + u * v0.lanes) * v0.C);
     }
     // (2) group statistics from the per-channel sums: 8 threads per group, then a 3-step shuffle
     {
@@ -352,8 +354,8 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
     Op ap;
     ap.name = f32 ? "gn_apply<f32>" : "gn_apply<bf16>";
     ap.launch = [p, grid, f32, smem](cudaStream_t s) -> int {
-        if (f32) gn_apply_kernel<float><<<grid, 256, smem, s>>>(*p);
-        else gn_apply_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*p);
+        if (f32) TQ_CUDA(launch_pdl(gn_apply_kernel<float>, grid, dim3(256), smem, s, *p));
+        else TQ_CUDA(launch_pdl(gn_apply_kernel<__nv_bfloat16>, grid, dim3(256), smem, s, *p));
         TQ_CUDA(cudaGetLastError());
         count_launch();
         return 0;

@@ -6,8 +6,9 @@ multiprocessing)`, `MovingAverageEnvelope(window_size, log_eps, eps)`, `Identity
 
 `LogSpectrogram.invert_representation` (reference: representation.py:152-175 -> librosa.griffinlim in a pathos
 process pool) is ONE CUDA launch for the whole batch (csrc/tq_griffinlim.cu); a CUDA tensor input is consumed in
-place, so only the waveforms cross PCIe.  The forward maps (`get_representation`) are not on the sampling path
-and use torch.stft / NumPy.
+place, so only the waveforms cross PCIe.  The forward maps (`get_representation`) are device
+kernels too (tq_logspec_forward, tq_mavg_envelope_forward): inputs are taken as fp32 (the dataset's storage type),
+the arithmetic precision of the STFT follows `precision`.
 """
 
 from __future__ import annotations
@@ -74,12 +75,18 @@ class MovingAverageEnvelope(Representation):
     def __init__(self, window_size=128, log_eps=1e-6, eps=1e-6):
         self.window_size, self.log_eps, self.eps = window_size, log_eps, eps
 
+    def get_representation_device(self, waveform) -> torch.Tensor:
+        """[.., channels, L] -> [.., 2*channels, L] on the device (reference: representation.py:47-55)."""
+        w = _as_cuda_f32(waveform)
+        lead, (cw, L) = w.shape[:-2], w.shape[-2:]
+        n = int(math.prod(lead)) if lead else 1
+        out = torch.empty(*lead, 2 * cw, L, device=w.device, dtype=torch.float32)
+        _lib.check(_lib.lib().tq_mavg_envelope_forward(w.data_ptr(), out.data_ptr(), n, cw, L, self.window_size,
+                                                       self.log_eps, self.eps, current_stream_ptr()), "mavg_envelope_forward")
+        return out
+
     def get_representation(self, waveform):
-        w = _np(waveform)
-        kernel = np.full(self.window_size, 1.0 / self.window_size)
-        flat = np.abs(w).reshape(-1, w.shape[-1])
-        env = np.stack([np.convolve(row, kernel, mode="same") for row in flat]).reshape(w.shape)
-        return np.concatenate([w / (env + self.eps), np.log(env + self.log_eps) - np.log(self.log_eps) / 2], axis=-2)
+        return self.get_representation_device(waveform).cpu().numpy()
 
     def invert_representation_device(self, representation) -> torch.Tensor:
         rep = _as_cuda_f32(representation)
@@ -126,21 +133,28 @@ class LogSpectrogram(Representation):
     def disable_multiprocessing(self):
         """Kept for API compatibility (reference: representation.py:135-138); nothing to close."""
 
-    # ---- forward (not on the sampling path) ---------------------------------------------------------
-    def get_spectrogram(self, waveform):
-        w = torch.as_tensor(_np(waveform))
-        shape = w.shape
-        flat = w.reshape(-1, shape[-1]).to(torch.float64)
-        win = torch.hann_window(self.stft_channels, periodic=True, dtype=torch.float64)
-        spec = torch.stft(flat, n_fft=self.stft_channels, hop_length=self.hop_size, window=win, center=True,
-                          pad_mode="constant", return_complex=True)
-        spec = spec[:, :-1]  # drop the Nyquist row (representation.py:147)
-        return spec.reshape(*shape[:-1], *spec.shape[1:]).numpy()
+    # ---- forward (the step before the sampling path) ---------------------------------------------------
+    def get_representation_device(self, waveform) -> torch.Tensor:
+        """waveforms [.., L] -> normalised log-magnitude STFT [.., n_fft/2, 1 + L/hop] in [-1, 1] as a CUDA tensor
+        (reference: get_spectrogram + get_representation, representation.py:140-150,163-169; librosa stft semantics)."""
+        w = _as_cuda_f32(waveform)
+        lead, L = w.shape[:-1], w.shape[-1]
+        items = int(math.prod(lead)) if lead else 1
+        frames = 1 + L // self.hop_size
+        prec = TQ_F64 if self.precision == "fp64" else TQ_F32
+        odt = torch.float64 if prec == TQ_F64 else torch.float32
+        out = torch.empty(items, self.stft_channels // 2, frames, device=w.device, dtype=odt)
+        _lib.check(_lib.lib().tq_logspec_forward(w.reshape(items, L).data_ptr(), out.data_ptr(), prec, items, self.stft_channels,
+                                                 self.hop_size, L, frames, float(self.clip), float(self.log_max), prec,
+                                                 current_stream_ptr()), "logspec_forward")
+        return out.reshape(*lead, self.stft_channels // 2, frames)
 
     def get_representation(self, waveform):
-        mag = np.abs(self.get_spectrogram(waveform))
-        log_spec = np.log(np.clip(mag, self.clip, None))
-        return (log_spec - self.log_clip) / (self.log_max - self.log_clip) * 2 - 1
+        return self.get_representation_device(waveform).cpu().numpy()
+
+    def get_spectrogram(self, waveform):
+        raise NotImplementedError("tqdne_b200: the complex spectrogram is never materialised -- get_representation() goes "
+                                  "from waveforms to the normalised log-magnitudes in one kernel (tq_logspec_forward)")
 
     # ---- inverse (hot path) ----------------------------------------------------------------------------
     def _phase0(self, frames: int, device) -> torch.Tensor:
