@@ -155,17 +155,21 @@ __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float
     }
 }
 
+// T <= 32 (latent UNet: T = 16): one CTA per (sample, head), everything in shared memory.  The kernel is bound by
+// shared-memory instruction issue, so both contractions are register-blocked over 16 B loads: a thread owns a
+// (query, key pair) for QK^T and a (query, 4-channel group) for PV.
 template <typename T, int D>
 __global__ void __launch_bounds__(128) attention_small_kernel(const AttnParams p) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     pdl_launch_dependents();
     pdl_wait();
-    constexpr int PITCH = D + 1;
+    constexpr int PITCH = D + 4;     // rows stay 16 B aligned; 8 consecutive rows cover all 32 banks
     const int Tn = p.T;
-    float* Qs = sm;                  // [T][PITCH]
-    float* Ks = Qs + Tn * PITCH;     // [T][PITCH]
-    float* Vs = Ks + Tn * PITCH;     // [T][D]
-    float* Ps = Vs + Tn * D;         // [T][T+1]
+    const int Tp = (Tn + 1) & ~1;    // keys padded to a pair
+    float* Qs = sm;                  // [Tp][PITCH]
+    float* Ks = Qs + Tp * PITCH;     // [Tp][PITCH]
+    float* Vs = Ks + Tp * PITCH;     // [Tp][PITCH]
+    float* Ps = Vs + Tp * PITCH;     // [Tn][Tp + 1]
     const int C = p.heads * D;
     const int ld = 3 * C;
     const int h = blockIdx.x % p.heads;
@@ -174,29 +178,37 @@ __global__ void __launch_bounds__(128) attention_small_kernel(const AttnParams p
     const float scale = 1.f / sqrtf(sqrtf((float)D));
     const T* base = static_cast<const T*>(p.qkv) + (long long)n * Tn * ld + h * D;
     constexpr int VPR = D / 8;  // 16 B vectors per row
-    for (int i = tid; i < 3 * Tn * VPR; i += 128) {
-        const int which = i / (Tn * VPR);
-        const int r = (i / VPR) % Tn, vc = i % VPR;
-        float v[8];
-        ld8<T>(base + (long long)r * ld + which * C + vc * 8, v);
-        float* dst = which == 0 ? Qs + r * PITCH : (which == 1 ? Ks + r * PITCH : Vs + r * D);
+    for (int i = tid; i < 3 * Tp * VPR; i += 128) {
+        const int which = i / (Tp * VPR);
+        const int r = (i / VPR) % Tp, vc = i % VPR;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (r < Tn) ld8<T>(base + (long long)r * ld + which * C + vc * 8, v);
+        float* dst = (which == 0 ? Qs : (which == 1 ? Ks : Vs)) + r * PITCH + vc * 8;
         const float sc = which == 2 ? 1.f : scale;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[vc * 8 + j] = v[j] * sc;
+        reinterpret_cast<float4*>(dst)[0] = make_float4(v[0] * sc, v[1] * sc, v[2] * sc, v[3] * sc);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(v[4] * sc, v[5] * sc, v[6] * sc, v[7] * sc);
     }
     __syncthreads();
-    for (int i = tid; i < Tn * Tn; i += 128) {
-        const int qi = i / Tn, ki = i % Tn;
-        const float* q = Qs + qi * PITCH;
-        const float* k = Ks + ki * PITCH;
-        float a = 0.f;
-#pragma unroll 16
-        for (int c = 0; c < D; ++c) a = fmaf(q[c], k[c], a);
-        Ps[qi * (Tn + 1) + ki] = a;
+    // scores: item = (query, key pair)
+    const int kpairs = Tp / 2;
+    for (int i = tid; i < Tn * kpairs; i += 128) {
+        const int qi = i / kpairs, k0 = (i % kpairs) * 2;
+        const float4* q = reinterpret_cast<const float4*>(Qs + qi * PITCH);
+        const float4* ka = reinterpret_cast<const float4*>(Ks + k0 * PITCH);
+        const float4* kb = reinterpret_cast<const float4*>(Ks + (k0 + 1) * PITCH);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < D / 4; ++c) {
+            const float4 qv = q[c], x = ka[c], y = kb[c];
+            a0 = fmaf(qv.x, x.x, a0); a0 = fmaf(qv.y, x.y, a0); a0 = fmaf(qv.z, x.z, a0); a0 = fmaf(qv.w, x.w, a0);
+            a1 = fmaf(qv.x, y.x, a1); a1 = fmaf(qv.y, y.y, a1); a1 = fmaf(qv.z, y.z, a1); a1 = fmaf(qv.w, y.w, a1);
+        }
+        Ps[qi * (Tp + 1) + k0] = a0;
+        Ps[qi * (Tp + 1) + k0 + 1] = a1;
     }
     __syncthreads();
     if (tid < Tn) {
-        float* pr = Ps + tid * (Tn + 1);
+        float* pr = Ps + tid * (Tp + 1);
         float m = -INFINITY;
         for (int k = 0; k < Tn; ++k) m = fmaxf(m, pr[k]);
         float l = 0.f;
@@ -209,20 +221,27 @@ __global__ void __launch_bounds__(128) attention_small_kernel(const AttnParams p
         for (int k = 0; k < Tn; ++k) pr[k] *= inv;
     }
     __syncthreads();
+    // output: item = (query, 4-channel group)
     T* ob = static_cast<T*>(p.out) + (long long)n * Tn * C + h * D;
-    for (int i = tid; i < Tn * D; i += 128) {
-        const int qi = i / D, c = i % D;
-        const float* pr = Ps + qi * (Tn + 1);
-        float a = 0.f;
-        for (int k = 0; k < Tn; ++k) a = fmaf(pr[k], Vs[k * D + c], a);
-        st_f(ob + (long long)qi * C + c, a);
+    for (int i = tid; i < Tn * (D / 4); i += 128) {
+        const int qi = i / (D / 4), c4 = i % (D / 4);
+        const float* pr = Ps + qi * (Tp + 1);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < Tn; ++k) {
+            const float w = pr[k];
+            const float4 v = *reinterpret_cast<const float4*>(Vs + k * PITCH + c4 * 4);
+            a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+        }
+        T* o = ob + (long long)qi * C + c4 * 4;
+        st_f(o, a.x); st_f(o + 1, a.y); st_f(o + 2, a.z); st_f(o + 3, a.w);
     }
 }
 
 template <typename T, int D>
 int launch_attn(const AttnParams& p, cudaStream_t st) {
     if (p.T <= 32) {
-        const size_t smem = (size_t)(2 * p.T * (D + 1) + p.T * D + p.T * (p.T + 1)) * sizeof(float);
+        const int tp = (p.T + 1) & ~1;
+        const size_t smem = (size_t)(3 * tp * (D + 4) + p.T * (tp + 1)) * sizeof(float);
         static bool attr_small = false;
         if (!attr_small) {
             TQ_CUDA(cudaFuncSetAttribute(attention_small_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
