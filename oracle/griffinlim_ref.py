@@ -1,6 +1,6 @@
 """NumPy restatement of the log-spectrogram inverse -- TEST INFRASTRUCTURE (see oracle/__init__.py).
 
-PARITY UNPINNED at the librosa boundary: the reference calls librosa 0.11.0 (`uv.lock`, pyproject.toml:16)
+PARITY UNPINNED at the librosa boundary (narrowed, see below): the reference calls librosa 0.11.0 (`uv.lock`, pyproject.toml:16)
 `griffinlim(S, hop_length=32, n_fft=256, n_iter=128, random_state=0)` (tqdne/representation.py:103-108);
 librosa is a third-party dependency that is neither vendored under /root/reference nor installed here, and the
 reference has no test pinning its output.  This file restates librosa 0.11's published algorithm:
@@ -14,7 +14,11 @@ reference has no test pinning its output.  This file restates librosa 0.11's pub
                  angles /= |angles| + tiny; angles *= S; tprev = rebuilt
            return istft(angles)
 
-The STFT pair is pinned against torch.stft / torch.istft in tests/test_oracle.py.  The surrounding reference
+The STFT pair is pinned against torch.stft / torch.istft in tests/test_oracle.py, and the Griffin-Lim LOOP
+(momentum update, normalisation, stft/istft chaining) is pinned against torchaudio.functional.griffinlim -- an
+independent port of librosa's loop that is installed here -- in the configuration both can express (reflect padding,
+all-ones initial phase, eps 1e-16).  What remains unpinned is exactly librosa's three deviations from that port:
+zero padding, the RandomState(0) unit-phasor initial phase, eps = finfo.tiny.  The surrounding reference
 code (un-normalise, exp, append zero Nyquist row; representation.py:152-175) is pinned by executing the
 reference's own LogSpectrogram methods with this griffinlim plugged in (oracle/make_golden.py).
 """
@@ -28,9 +32,9 @@ def hann_periodic(n: int, dtype=np.float64):
     return (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n) / n)).astype(dtype)
 
 
-def stft(y: np.ndarray, n_fft: int = 256, hop: int = 32) -> np.ndarray:
+def stft(y: np.ndarray, n_fft: int = 256, hop: int = 32, pad_mode: str = "constant") -> np.ndarray:
     win = hann_periodic(n_fft, y.dtype)
-    yp = np.pad(y, n_fft // 2, mode="constant")
+    yp = np.pad(y, n_fft // 2, mode=pad_mode)
     n_frames = 1 + (len(yp) - n_fft) // hop
     idx = np.arange(n_fft)[None, :] + hop * np.arange(n_frames)[:, None]
     frames = yp[idx] * win[None, :]
@@ -60,17 +64,25 @@ def initial_phase(n_bins: int, n_frames: int, seed: int = 0) -> np.ndarray:
 
 
 def griffinlim(S: np.ndarray, n_iter: int = 128, hop: int = 32, n_fft: int = 256, momentum: float = 0.99,
-               seed: int = 0) -> np.ndarray:
-    """S: magnitudes [1 + n_fft/2, frames], float32 or float64 (sets the arithmetic precision)."""
+               seed: int = 0, pad_mode: str = "constant", init: str = "random", eps: float | None = None) -> np.ndarray:
+    """S: magnitudes [1 + n_fft/2, frames], float32 or float64 (sets the arithmetic precision).
+
+    The defaults are librosa 0.11's (zero padding, unit phasors from RandomState(seed), eps = tiny).  The three
+    keyword deviations exist so that the SAME loop can be pinned against an independent implementation that is
+    installed here: torchaudio.functional.griffinlim = (pad_mode="reflect", init="ones", eps=1e-16), see
+    tests/test_oracle.py::test_griffinlim_loop_pinned_against_torchaudio."""
     cdt = np.complex128 if S.dtype == np.float64 else np.complex64
-    eps = np.finfo(S.dtype).tiny
-    ph = initial_phase(*S.shape, seed=seed)
-    angles = (np.cos(ph) + 1j * np.sin(ph)).astype(cdt)
+    eps = np.finfo(S.dtype).tiny if eps is None else eps
+    if init == "random":
+        ph = initial_phase(*S.shape, seed=seed)
+        angles = (np.cos(ph) + 1j * np.sin(ph)).astype(cdt)
+    else:
+        angles = np.ones(S.shape, dtype=cdt)
     angles *= S
     tprev = None
     for _ in range(n_iter):
         inverse = istft(angles, n_fft, hop)
-        rebuilt = stft(inverse, n_fft, hop)
+        rebuilt = stft(inverse, n_fft, hop, pad_mode)
         angles[:] = rebuilt
         if tprev is not None:
             angles -= (momentum / (1 + momentum)) * tprev

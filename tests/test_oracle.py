@@ -161,3 +161,21 @@ def test_forward_representations_match_reference_golden():
     assert r64.shape == (1, 3, 128, 128) and np.abs(r64 - g["rep64"].numpy()).max() < 1e-12
     r32 = griffinlim_ref.logspec_forward(w)
     assert np.abs(r32 - g["rep32"].numpy()).max() < 1e-5
+
+
+def test_griffinlim_loop_pinned_against_torchaudio():
+    """torchaudio.functional.griffinlim is an independent port of librosa's fast Griffin-Lim loop: same
+    momentum update, normalisation and stft/istft chain, but reflect padding, all-ones initial phase and eps 1e-16.
+    The oracle run in THAT configuration must reproduce it; the default (librosa) configuration differs from it only by
+    those three switches."""
+    ta = pytest.importorskip("torchaudio")
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal(4064) * np.exp(-((np.arange(4064) - 1500.0) / 900.0) ** 2)
+    S = np.abs(griffinlim_ref.stft(y))                                      # [129, 128] float64, a consistent spectrogram
+    win = torch.hann_window(256, periodic=True, dtype=torch.float64)
+    for n_iter in (1, 6):
+        ref = ta.functional.griffinlim(torch.from_numpy(S), window=win, n_fft=256, hop_length=32, win_length=256, power=1.0,
+                                       n_iter=n_iter, momentum=0.99, length=4064, rand_init=False).numpy()
+        out = griffinlim_ref.griffinlim(S, n_iter=n_iter, pad_mode="reflect", init="ones", eps=1e-16)
+        assert out.shape == ref.shape == (4064,)
+        assert np.abs(out - ref).max() < 1e-9 * np.abs(ref).max()
