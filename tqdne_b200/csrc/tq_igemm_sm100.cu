@@ -35,7 +35,9 @@
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <memory>
+#include <vector>
 
 #include "tq_common.h"
 #include "tq_ptx.cuh"
@@ -57,8 +59,12 @@ struct alignas(64) IgemmParams {
     CUtensorMap bmap;
     CUtensorMap omap[4];  // bf16 output per parity class, box = one epilogue unit
     CUtensorMap rmap;     // residual, same geometry as omap[0]
-    const int4* slices;
+    CUtensorMap amap3[4];  // ROW3 stages: the same sources with a box of bh + 2 rows
+    const int4* slices;    // stage records, 3 x int4 each, [num_classes][num_stages]
     int num_slices, num_classes;
+    int num_stages;        // pipeline stages per tile (a stage = up to KS plain slices, or one ROW3 group)
+    int a3_bytes;          // bytes of a ROW3 activation buffer: (bh + 2) * bw * 128
+    int row_bytes;         // bw * 128: one image row of a tile inside a ROW3 buffer
     int N, H, W, bw, bh, bn;
     int tiles_x, tiles_y, m_tiles, m_groups, n_tiles, total_tiles;
     int cout;
@@ -98,6 +104,11 @@ struct Cfg {
     // K slices per pipeline stage: with N <= 128 one slice is only <= 256 tensor-pipe cycles, on par with the
     // ~170-cycle mbarrier round trip per stage (tools/pipe_probe.cu), so two slices share one full/empty handshake
     static constexpr int KS = BN >= 256 ? 1 : 2;
+    // ROW3 stage (3x3 stride-1 convs whose tile is bh >= 4 full-width rows of ONE sample, N <= 128): the three taps
+    // (dy = -1, 0, +1) of one (source, 64-channel block, dx) read the SAME activation buffer of bh + 2 rows -- tap dy
+    // is the UMMA descriptor advanced by (dy + 1) image rows -- so the L2 -> shared-memory traffic of the activation
+    // operand drops from 3 x 16 KB to 24 KB per three taps.  N = 128 tiles are co-bound by exactly that traffic
+    // (TMA-only 54 us, MMA-only 49 us, both 71 us on 128->128 3x3 @32^2).
     static constexpr int STAGE_BYTES = KS * SLICE_BYTES;
     static constexpr int UNITS = BN >= 128 ? BN / 128 : 1;  // 64-channel groups per epilogue warp
     static constexpr int EPI_BYTES = kEpiWarps * UNITS * EPI_BUF_BYTES;
@@ -215,48 +226,60 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
         long long w_empty = 0;
         for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
             const TileCoord t = decode_tile<CG>(p, tile, rank);
-            const int4* sl = p.slices + (size_t)t.cls * p.num_slices;
+            const int4* sl = p.slices + (size_t)t.cls * p.num_stages * 3;
             const int b_row = CG == 2 ? t.n_tile * BN + rank * C::BNC : t.n_tile * BN;
-            int4 v[C::KS];
-#pragma unroll
-            for (int j = 0; j < C::KS; ++j) v[j] = __ldg(sl + (j < p.num_slices ? j : 0));
-            for (int s = 0; s < p.num_slices; s += C::KS) {
-                // next table entries in flight while this group waits for its stage
-                int4 vn[C::KS];
-#pragma unroll
-                for (int j = 0; j < C::KS; ++j) {
-                    const int sn = s + C::KS + j;
-                    vn[j] = __ldg(sl + (sn < p.num_slices ? sn : s));
-                }
-                const int n_in = p.num_slices - s < C::KS ? p.num_slices - s : C::KS;
+            int4 r0 = __ldg(sl), r1 = __ldg(sl + 1), r2 = __ldg(sl + 2);
+            for (int g = 0; g < p.num_stages; ++g) {
+                // next stage record in flight while this stage waits for its buffer
+                const int gn = g + 1 < p.num_stages ? g + 1 : g;
+                const int4 n0 = __ldg(sl + 3 * gn), n1 = __ldg(sl + 3 * gn + 1), n2 = __ldg(sl + 3 * gn + 2);
                 mbar_wait_prof(empty_bar(stage), phase ^ 1u, prof, w_empty);
                 if (elect_one()) {
+                    const uint32_t s_dst = base + stage * C::STAGE_BYTES;
+                    const uint32_t fb = CG == 2 ? full_leader0 + 8u * stage : full_bar(stage);
                     if (p.probe & 1) {
                         if (rank == 0) mbar_arrive(full_bar(stage));
+                    } else if (r2.x == 1) {
+                        // ROW3: one activation buffer of bh + 2 rows, three weight blocks
+                        const int src = (short)(r0.x & 0xffff);
+                        const int dx = (short)(r0.x >> 16);
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), CG * (p.a3_bytes + 3 * C::B_BYTES));
+                        const uint32_t w_dst = s_dst + p.a3_bytes;
+                        if constexpr (CG == 1) {
+                            tma_load_4d(s_dst, &p.amap3[src], fb, r0.z, t.x0 + dx, t.y0 - 1, t.n0);
+                            tma_load_2d(w_dst, &p.bmap, fb, r0.w * BK, b_row);
+                            tma_load_2d(w_dst + C::B_BYTES, &p.bmap, fb, r1.x * BK, b_row);
+                            tma_load_2d(w_dst + 2 * C::B_BYTES, &p.bmap, fb, r1.y * BK, b_row);
+                        } else {
+                            tma_load_4d_pair(s_dst, &p.amap3[src], fb, r0.z, t.x0 + dx, t.y0 - 1, t.n0);
+                            tma_load_2d_pair(w_dst, &p.bmap, fb, r0.w * BK, b_row);
+                            tma_load_2d_pair(w_dst + C::B_BYTES, &p.bmap, fb, r1.x * BK, b_row);
+                            tma_load_2d_pair(w_dst + 2 * C::B_BYTES, &p.bmap, fb, r1.y * BK, b_row);
+                        }
                     } else {
+                        const int n_in = r2.y;
                         if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), n_in * CG * C::SLICE_BYTES);
 #pragma unroll
                         for (int j = 0; j < C::KS; ++j) {
                             if (j < n_in) {
-                                const int src = (short)(v[j].x & 0xffff);
-                                const int dx = (short)(v[j].x >> 16);
-                                const int dy = (short)(v[j].y & 0xffff);
-                                const uint32_t a_dst = base + stage * C::STAGE_BYTES + j * C::SLICE_BYTES;
+                                const int4 v = j == 0 ? r0 : r1;
+                                const int src = (short)(v.x & 0xffff);
+                                const int dx = (short)(v.x >> 16);
+                                const int dy = (short)(v.y & 0xffff);
+                                const uint32_t a_dst = s_dst + j * C::SLICE_BYTES;
                                 if constexpr (CG == 1) {
-                                    tma_load_4d(a_dst, &p.amap[src], full_bar(stage), v[j].z, t.x0 + dx, t.y0 + dy, t.n0);
-                                    tma_load_2d(a_dst + A_BYTES, &p.bmap, full_bar(stage), v[j].w * BK, b_row);
+                                    tma_load_4d(a_dst, &p.amap[src], fb, v.z, t.x0 + dx, t.y0 + dy, t.n0);
+                                    tma_load_2d(a_dst + A_BYTES, &p.bmap, fb, v.w * BK, b_row);
                                 } else {
-                                    const uint32_t fb = full_leader0 + 8u * stage;
-                                    tma_load_4d_pair(a_dst, &p.amap[src], fb, v[j].z, t.x0 + dx, t.y0 + dy, t.n0);
-                                    tma_load_2d_pair(a_dst + A_BYTES, &p.bmap, fb, v[j].w * BK, b_row);
+                                    tma_load_4d_pair(a_dst, &p.amap[src], fb, v.z, t.x0 + dx, t.y0 + dy, t.n0);
+                                    tma_load_2d_pair(a_dst + A_BYTES, &p.bmap, fb, v.w * BK, b_row);
                                 }
                             }
                         }
                     }
                 }
                 __syncwarp();
-#pragma unroll
-                for (int j = 0; j < C::KS; ++j) v[j] = vn[j];
+                r0 = n0; r1 = n1; r2 = n2;
                 if (++stage == C::STAGES) {
                     stage = 0;
                     phase ^= 1u;
@@ -283,22 +306,39 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                 mbar_wait_prof(tempty_bar(acc), acc_phase ^ 1u, prof, w_tempty);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int s = 0; s < p.num_slices; s += C::KS) {
-                    const int n_in = p.num_slices - s < C::KS ? p.num_slices - s : C::KS;
+                const int4* sl = p.slices + (size_t)(tile / (p.n_tiles * p.m_groups)) * p.num_stages * 3 + 2;
+                int4 r2 = __ldg(sl);
+                for (int g = 0; g < p.num_stages; ++g) {
+                    const int4 n2 = __ldg(sl + 3 * (g + 1 < p.num_stages ? g + 1 : g));
                     mbar_wait_prof(full_bar(stage), phase, prof, w_full);
                     tc_fence_after();
                     if (elect_one()) {
                         if (!no_mma) {
+                            const uint32_t s_lo = desc_lo0 + ((stage * C::STAGE_BYTES) >> 4);
+                            if (r2.x == 1) {
+                                const uint32_t w_lo = s_lo + (p.a3_bytes >> 4);
 #pragma unroll
-                            for (int j = 0; j < C::KS; ++j) {
-                                if (j < n_in) {
-                                    const uint32_t a_lo = desc_lo0 + ((stage * C::STAGE_BYTES + j * C::SLICE_BYTES) >> 4);
-                                    const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+                                for (int j = 0; j < 3; ++j) {
+                                    const uint32_t a_lo = s_lo + j * (p.row_bytes >> 4);
+                                    const uint32_t b_lo = w_lo + j * (C::B_BYTES >> 4);
 #pragma unroll
-                                    for (int k = 0; k < BK / 16; ++k) {
-                                        // +32 B per K=16 step inside the 128 B swizzle row (address field is >> 4)
+                                    for (int k = 0; k < BK / 16; ++k)
                                         umma_bf16_cg<CG>(d_tmem, umma_desc_pack(a_lo + 2u * k, desc_hi),
-                                                         umma_desc_pack(b_lo + 2u * k, desc_hi), idesc, (s | j | k) != 0);
+                                                         umma_desc_pack(b_lo + 2u * k, desc_hi), idesc, (g | j | k) != 0);
+                                }
+                            } else {
+                                const int n_in = r2.y;
+#pragma unroll
+                                for (int j = 0; j < C::KS; ++j) {
+                                    if (j < n_in) {
+                                        const uint32_t a_lo = s_lo + ((j * C::SLICE_BYTES) >> 4);
+                                        const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+#pragma unroll
+                                        for (int k = 0; k < BK / 16; ++k) {
+                                            // +32 B per K=16 step inside the 128 B swizzle row (address field is >> 4)
+                                            umma_bf16_cg<CG>(d_tmem, umma_desc_pack(a_lo + 2u * k, desc_hi),
+                                                             umma_desc_pack(b_lo + 2u * k, desc_hi), idesc, (g | j | k) != 0);
+                                        }
                                     }
                                 }
                             }
@@ -306,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                         umma_commit_cg<CG>(empty_bar(stage));
                     }
                     __syncwarp();
+                    r2 = n2;
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -808,10 +849,72 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
         TQ_CHECK(s.c0 % 64 == 0 && s.c0 + 64 <= d.srcs[s.src].C, "slice %zu: bad channel offset", i);
         TQ_CHECK(s.kb >= 0 && (s.kb + 1) * 64 <= d.ktot, "slice %zu: bad weight block", i);
     }
+    // ---- stage records (3 x int4 per stage): plain stages carry up to KS slices, a ROW3 stage the three dy taps of
+    // one (source, channel block, dx) over a shared activation buffer of bh + 2 rows
+    const int ks = bn_tile >= 256 ? 1 : 2;
+    const int b_bytes = (bn_tile / cg) * BK * 2;
+    const int stage_bytes = ks * (A_BYTES + b_bytes);
+    const int a3_bytes = (p->bh + 2) * p->bw * BK * 2;
+    bool row3 = bn_tile <= 128 && p->bn == 1 && p->bw == d.W && p->bh >= 2 && d.num_classes == 1 &&
+                a3_bytes + 3 * b_bytes <= stage_bytes && (p->bw * BK * 2) % 1024 == 0;
+    if (const char* e = getenv("TQ_ROW3"); e && e[0] == '0') row3 = false;
+    std::vector<int4> recs;
+    int num_stages = 0, row3_groups = 0;
+    auto pack = [](const tq_slice& sl) {
+        return make_int4((int)((uint32_t)(uint16_t)sl.src | ((uint32_t)(uint16_t)sl.dx << 16)), (int)(uint16_t)sl.dy, sl.c0, sl.kb);
+    };
+    for (int c = 0; c < d.num_classes; ++c) {
+        const tq_slice* sl = d.slices + (size_t)c * d.num_slices;
+        std::vector<int> group(d.num_slices, -1);  // slice -> ROW3 group leader (the dy = -1 slice), or -1
+        if (row3) {
+            for (int i = 0; i < d.num_slices; ++i) {
+                if (sl[i].dy != -1 || group[i] != -1) continue;
+                int mid = -1, bot = -1;
+                for (int j = 0; j < d.num_slices; ++j) {
+                    if (group[j] != -1 || sl[j].src != sl[i].src || sl[j].c0 != sl[i].c0 || sl[j].dx != sl[i].dx) continue;
+                    if (sl[j].dy == 0 && mid < 0) mid = j;
+                    if (sl[j].dy == 1 && bot < 0) bot = j;
+                }
+                if (mid >= 0 && bot >= 0) {
+                    group[i] = i; group[mid] = i; group[bot] = i;
+                    recs.push_back(pack(sl[i]));
+                    recs.push_back(make_int4(sl[mid].kb, sl[bot].kb, 0, 0));
+                    recs.push_back(make_int4(1, 3, 0, 0));
+                    ++row3_groups;
+                }
+            }
+        }
+        std::vector<int> plain;
+        for (int i = 0; i < d.num_slices; ++i)
+            if (group[i] == -1) plain.push_back(i);
+        for (size_t i = 0; i < plain.size(); i += ks) {
+            const int n_in = (int)std::min<size_t>(ks, plain.size() - i);
+            recs.push_back(pack(sl[plain[i]]));
+            recs.push_back(n_in > 1 ? pack(sl[plain[i + 1]]) : make_int4(0, 0, 0, -1));
+            recs.push_back(make_int4(0, n_in, 0, 0));
+        }
+        const int st = (int)recs.size() / 3 - num_stages * c;
+        if (c == 0) num_stages = st;
+        TQ_CHECK(st == num_stages, "conv classes must have the same stage count");
+    }
+    if (row3_groups > 0) {
+        for (int i = 0; i < d.num_srcs; ++i) {
+            const tq_src& sr = d.srcs[i];
+            if (encode_nhwc_map(&p->amap3[i], sr.ptr, sr.N, sr.H, sr.W, sr.C, sr.sn, sr.sy, sr.sx, p->bw, p->bh + 2, p->bn,
+                                "conv source (row3)"))
+                return 1;
+        }
+        for (int i = d.num_srcs; i < 4; ++i) p->amap3[i] = p->amap3[0];
+    } else {
+        for (int i = 0; i < 4; ++i) p->amap3[i] = p->amap[0];
+    }
+    p->num_stages = num_stages;
+    p->a3_bytes = a3_bytes;
+    p->row_bytes = p->bw * BK * 2;
     void* dsl = nullptr;
-    TQ_CUDA(cudaMalloc(&dsl, nsl * sizeof(tq_slice)));
+    TQ_CUDA(cudaMalloc(&dsl, recs.size() * sizeof(int4)));
     std::shared_ptr<void> dsl_owner(dsl, [](void* q) { cudaFree(q); });
-    TQ_CUDA(cudaMemcpy(dsl, d.slices, nsl * sizeof(tq_slice), cudaMemcpyHostToDevice));
+    TQ_CUDA(cudaMemcpy(dsl, recs.data(), recs.size() * sizeof(int4), cudaMemcpyHostToDevice));
     static_assert(sizeof(tq_slice) == sizeof(int4), "tq_slice must be 16 bytes");
 
     p->slices = static_cast<const int4*>(dsl);
@@ -860,8 +963,8 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
 
     Op op;
     char nm[112];
-    snprintf(nm, sizeof nm, "igemm_sm100<BN=%d,CG=%d,%s> tiles=%d slices=%d", bn_tile, cg, f32 ? "f32" : "bf16",
-             p->total_tiles, d.num_slices);
+    snprintf(nm, sizeof nm, "igemm_sm100<BN=%d,CG=%d,%s> tiles=%d slices=%d%s", bn_tile, cg, f32 ? "f32" : "bf16",
+             p->total_tiles, d.num_slices, row3_groups > 0 ? " row3" : "");
     op.name = nm;
     const std::string opname = nm;
     op.launch = [p, dsl_owner, prof_owner, opname, grid, bn_tile, cg, f32](cudaStream_t st) -> int {
