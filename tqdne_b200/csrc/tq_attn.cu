@@ -9,6 +9,7 @@
 // (pixel / 1D configs) run through the same kernel.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <memory>
 
 #include "tq_common.h"
@@ -271,6 +272,11 @@ int build_attention(std::vector<Op>& ops, const tq_attn_desc& d) {
     TQ_CHECK(d.dtype == TQ_BF16 || d.dtype == TQ_F32, "attention: bad dtype");
     TQ_CHECK(d.d == 64 || d.d == 128 || d.d == 32, "attention: head dim must be 32, 64 or 128 (got %d)", d.d);
     TQ_CHECK(d.N > 0 && d.T > 0 && d.heads > 0 && d.qkv && d.out, "attention: bad arguments");
+    {
+        // T > 32 in bf16 runs on the tensor cores; TQ_ATTN_SIMT=1 keeps the FFMA kernel (A/B and cross-check)
+        const char* simt = getenv("TQ_ATTN_SIMT");
+        if (attention_tc_supported(d) && !(simt && simt[0] == '1')) return build_attention_tc(ops, d);
+    }
     auto p = std::make_shared<AttnParams>();
     p->qkv = d.qkv; p->out = d.out; p->N = d.N; p->T = d.T; p->heads = d.heads; p->d = d.d;
     const bool f32 = d.dtype == TQ_F32;

@@ -1,0 +1,320 @@
+// tq_attn_sm100.cu -- attention core on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), bf16, 32 < T <= 512.
+// Reference: QKVAttention.forward (tqdne/blocks.py:156-190): q,k,v = qkv.chunk(3, dim=1), heads split inside each
+// third, w = softmax_fp32((q*s)^T (k*s)) with s = d^-1/4, a = w v.  No mask (off in every shipped config).
+// Serves the pixel-space 2D UNet (T = 256, d = 128) and the 1D UNet (T = 508 / 512, d = 64); the latent UNet
+// (T = 16) stays on attention_small_kernel and the fp32 parity mode on the FFMA kernel (tcgen05 has no fp32 MMA).
+//
+// One CTA = (sample, head, 128 queries), 256 threads.  All keys of the head are resident, so there is no online
+// softmax and no rescaling of the accumulator:
+//   TMA      Q [128 x d], K [Tk x d], V [Tk x d] boxes of 128 rows x 64 channels (SWIZZLE_128B) straight out of the
+//            channels-last qkv tensor (rows >= T are zero-filled by the TMA unit), Tk = T rounded up to 128
+//   MMA 1    S[128 x Tk] = Q K^T   (both operands K-major), fp32 in Tk tensor-memory columns
+//   softmax  thread = (query row, half of the keys): row max, p = 2^((s - m) * d^-1/2 * log2 e), bf16 P written into
+//            the (now dead) K buffer in the K-major SWIZZLE_128B layout the second MMA reads
+//   MMA 2    O[128 x d] = P V      (P K-major; V is read as it lies, keys x channels, through an MN-major
+//            descriptor), accumulated over the S columns that the softmax has finished reading
+//   epilogue O / row sum -> bf16 -> out[n, t, head*d + c]
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
+#include <memory>
+
+#include "tq_common.h"
+#include "tq_ptx.cuh"
+
+namespace tq {
+namespace {
+
+constexpr int kQB = 128;        // queries per CTA (= TMEM lanes)
+constexpr int kThreadsTc = 256;
+
+struct AttnTcParams {
+    CUtensorMap map;   // qkv as [N][T][3C] bf16, box {64, 128, 1}
+    __nv_bfloat16* out;
+    int N, T, heads, Tk;
+    float scale_log2;  // d^-1/2 * log2(e)
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreadsTc, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
+    constexpr int DC = D / 64;                 // 64-channel slabs per operand
+    constexpr uint32_t Q_BYTES = DC * 16384u;  // 128 rows x 128 B per slab
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ float red_max[2][kQB];
+    __shared__ float red_sum[2][kQB];
+    __shared__ __align__(8) uint64_t bars[3];
+    __shared__ uint32_t tmem_slot;
+
+    const int Tk = p.Tk;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_smem = base;
+    const uint32_t kp_smem = q_smem + Q_BYTES;                 // K [DC][Tk x 128 B], later P [Tk/64][128 x 128 B]
+    const uint32_t v_smem = kp_smem + (uint32_t)Tk * 256u;     // V [DC][Tk x 128 B]
+    const uint32_t slab = (uint32_t)Tk * 128u;                 // one 64-channel slab of K or V
+    const uint32_t bar_qk = smem_u32(&bars[0]), bar_v = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qblocks = (p.T + kQB - 1) / kQB;
+    const int qb = blockIdx.x % qblocks;
+    const int h = (blockIdx.x / qblocks) % p.heads;
+    const int n = blockIdx.x / (qblocks * p.heads);
+    const int C = p.heads * D;
+    const uint32_t tmem_cols = Tk <= 128 ? 128u : (Tk <= 256 ? 256u : 512u);
+
+    pdl_launch_dependents();
+    if (warp == 1 && lane == 0) {
+        tma_prefetch_desc(&p.map);
+        mbar_init(bar_qk, 1);
+        mbar_init(bar_v, 1);
+        mbar_init(bar_mma, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(smem_u32(&tmem_slot), tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+    pdl_wait();
+
+    const int rblocks = Tk / 128;
+    if (warp == 0) {
+        if (elect_one()) {
+            // ---- loads: Q + K on one barrier (needed first), V on its own
+            mbar_arrive_expect_tx(bar_qk, Q_BYTES + (uint32_t)rblocks * DC * 16384u);
+            for (int c = 0; c < DC; ++c) tma_load_3d(q_smem + c * 16384u, &p.map, bar_qk, h * D + 64 * c, qb * kQB, n);
+            for (int c = 0; c < DC; ++c)
+                for (int b = 0; b < rblocks; ++b)
+                    tma_load_3d(kp_smem + c * slab + b * 16384u, &p.map, bar_qk, C + h * D + 64 * c, b * 128, n);
+            mbar_arrive_expect_tx(bar_v, (uint32_t)rblocks * DC * 16384u);
+            for (int c = 0; c < DC; ++c)
+                for (int b = 0; b < rblocks; ++b)
+                    tma_load_3d(v_smem + c * slab + b * 16384u, &p.map, bar_v, 2 * C + h * D + 64 * c, b * 128, n);
+        }
+        __syncwarp();
+        // ---- MMA 1: S = Q K^T, at most 256 keys (N) per instruction
+        mbar_wait(bar_qk, 0);
+        tc_fence_after();
+        if (elect_one()) {
+            constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
+            const uint32_t q_lo = ((q_smem & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t k_lo = ((kp_smem & 0x3FFFFu) >> 4) | (1u << 16);
+            for (int k0 = 0; k0 < Tk; k0 += 256) {
+                const int nk = min(256, Tk - k0);
+                const uint32_t idesc = umma_idesc_bf16(kQB, nk);
+#pragma unroll
+                for (int c = 0; c < DC; ++c) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t a_lo = q_lo + ((c * 16384u) >> 4) + 2u * kk;
+                        const uint32_t b_lo = k_lo + ((c * slab + (uint32_t)k0 * 128u) >> 4) + 2u * kk;
+                        umma_bf16(tmem_base + k0, umma_desc_pack(a_lo, desc_hi), umma_desc_pack(b_lo, desc_hi), idesc,
+                                  (c | kk) != 0);
+                    }
+                }
+            }
+            umma_commit(bar_mma);
+        }
+        __syncwarp();
+    }
+
+    // ---- softmax over the resident score row; thread = (row, half of the key columns)
+    const int row = (warp & 3) * 32 + lane;
+    const int half = warp >> 2;
+    const uint32_t t_row = tmem_base + (uint32_t((warp & 3) * 32) << 16);
+    const int cols = Tk / 2;
+    const int col0 = half * cols;
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < cols; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + col0 + c, r);
+        tmem_ld_wait();
+        const int lim = p.T - (col0 + c);  // columns >= T are padding keys
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < lim) m = fmaxf(m, __uint_as_float(r[j]));
+    }
+    red_max[half][row] = m;
+    __syncthreads();
+    m = fmaxf(red_max[0][row], red_max[1][row]);
+    const float sc = p.scale_log2;
+    const float msc = m * sc;
+    float l = 0.f;
+    const uint32_t p_row = kp_smem + (uint32_t)row * 128u;
+    const uint32_t xr = (uint32_t)(row & 7);
+#pragma unroll 1
+    for (int c = 0; c < cols; c += 32) {
+        uint32_t r[32];
+        const int col = col0 + c;
+        tmem_ld_32x32(t_row + col, r);
+        tmem_ld_wait();
+        const int lim = p.T - col;
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float e0 = (2 * j < lim) ? ex2_approx(fmaf(__uint_as_float(r[2 * j]), sc, -msc)) : 0.f;
+            const float e1 = (2 * j + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), sc, -msc)) : 0.f;
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
+            l += __low2float(b2) + __high2float(b2);  // the row sum of the weights the MMA really applies
+            pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        const uint32_t sl = p_row + (uint32_t)(col >> 6) * 16384u;  // 64-key slab of P
+        const uint32_t ch = (uint32_t)((col & 63) >> 3);             // first 16 B chunk inside the 128 B row
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            sts128(sl + (((ch + q) ^ xr) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+    red_sum[half][row] = l;
+    fence_proxy_async();  // P was written through the generic proxy; the MMA reads it through the async proxy
+    tc_fence_before();    // orders this thread's tcgen05.ld of S before the MMA that overwrites those columns
+    __syncthreads();
+
+    // ---- MMA 2: O = P V into columns [0, D)
+    if (warp == 0) {
+        mbar_wait(bar_v, 0);
+        tc_fence_after();
+        if (elect_one()) {
+            constexpr uint32_t p_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t p_lo = ((kp_smem & 0x3FFFFu) >> 4) | (1u << 16);
+            // V [keys][64 channels] per slab: channels (N) contiguous = MN-major; 8-key groups 1024 B apart (SBO),
+            // the next 64 channels one slab further (LBO)
+            const uint32_t v_lo = ((v_smem & 0x3FFFFu) >> 4) | ((slab >> 4) << 16);
+            constexpr uint32_t idesc = umma_idesc_bf16(kQB, D) | (1u << 16);  // B operand MN-major
+            const int kslabs = Tk / 64;
+#pragma unroll 1
+            for (int j = 0; j < kslabs; ++j) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t a_lo = p_lo + ((j * 16384u) >> 4) + 2u * kk;
+                    const uint32_t b_lo = v_lo + (((uint32_t)(j * 64 + kk * 16) * 128u) >> 4);
+                    umma_bf16(tmem_base, umma_desc_pack(a_lo, p_hi), umma_desc_pack(b_lo, p_hi), idesc, (j | kk) != 0);
+                }
+            }
+            umma_commit(bar_mma);
+        }
+        __syncwarp();
+    }
+    mbar_wait(bar_mma, 1);
+    tc_fence_after();
+    {
+        const float inv = 1.f / (red_sum[0][row] + red_sum[1][row]);
+        const int t = qb * kQB + row;
+        constexpr int OC = D / 2;  // output channels per thread
+        __nv_bfloat16* o = p.out + ((long long)n * p.T + t) * C + h * D + half * OC;
+#pragma unroll
+        for (int c = 0; c < OC; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + half * OC + c, r);
+            tmem_ld_wait();
+            if (t < p.T) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[8 * q + 2 * j]) * inv,
+                                                                        __uint_as_float(r[8 * q + 2 * j + 1]) * inv);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(o + c + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn) return fn;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+    return fn;
+}
+
+size_t attn_tc_smem(int Tk, int d) { return 1024 + (size_t)(d / 64) * 16384 + (size_t)Tk * 256 + (size_t)Tk * d * 2; }
+
+template <int D>
+int launch_attn_tc(const AttnTcParams& p, cudaStream_t st) {
+    const size_t smem = attn_tc_smem(p.Tk, D);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        TQ_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const int qblocks = (p.T + kQB - 1) / kQB;
+    TQ_CUDA(launch_pdl(attention_tc_kernel<D>, dim3(p.N * p.heads * qblocks), dim3(kThreadsTc), smem, st, p));
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace
+
+bool attention_tc_supported(const tq_attn_desc& d) {
+    if (d.dtype != TQ_BF16 || (d.d != 64 && d.d != 128) || d.T <= 32 || d.T > 512) return false;
+    if ((reinterpret_cast<uintptr_t>(d.qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(d.out) & 15) != 0) return false;
+    const int Tk = (d.T + 127) / 128 * 128;
+    return attn_tc_smem(Tk, d.d) <= 224 * 1024;  // + ~2 KB of static shared memory
+}
+
+int build_attention_tc(std::vector<Op>& ops, const tq_attn_desc& d) {
+    auto enc = encode_fn();
+    TQ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    auto p = std::make_shared<AttnTcParams>();
+    const int C = d.heads * d.d;
+    p->out = static_cast<__nv_bfloat16*>(d.out);
+    p->N = d.N; p->T = d.T; p->heads = d.heads;
+    p->Tk = (d.T + 127) / 128 * 128;
+    p->scale_log2 = 1.4426950408889634f / sqrtf((float)d.d);
+    cuuint64_t dims[3] = {(cuuint64_t)(3 * C), (cuuint64_t)d.T, (cuuint64_t)d.N};
+    cuuint64_t strides[2] = {(cuuint64_t)(3 * C) * 2, (cuuint64_t)d.T * (3 * C) * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&p->map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d.qkv), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TQ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(qkv) failed with CUresult %d", (int)r);
+    const int dd = d.d;
+    Op op;
+    char nm[64];
+    snprintf(nm, sizeof nm, "attention_tc<bf16,d=%d> T=%d", dd, d.T);
+    op.name = nm;
+    op.launch = [p, dd](cudaStream_t st) -> int {
+        return dd == 128 ? launch_attn_tc<128>(*p, st) : launch_attn_tc<64>(*p, st);
+    };
+    ops.push_back(std::move(op));
+    return 0;
+}
+
+}  // namespace tq
