@@ -339,9 +339,10 @@ def test_conv_epilogue_statistics_feed_groupnorm(case, dtype):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 @pytest.mark.parametrize("N,T,heads,d", [(3, 16, 4, 128), (2, 100, 4, 64), (1, 508, 4, 64), (2, 256, 2, 32),
                                          (2, 256, 4, 128), (3, 512, 4, 64), (1, 300, 2, 64), (2, 33, 1, 128),
-                                         (1, 129, 3, 64), (1, 600, 2, 64)])
+                                         (1, 129, 3, 64), (1, 600, 2, 64), (5, 32, 3, 64), (9, 16, 2, 64), (2, 20, 2, 64)])
 def test_attention_matches_reference_formula(N, T, heads, d, dtype):
-    """T <= 32: shared-memory kernel; bf16 with d in {64, 128} and 32 < T <= 512: tcgen05 kernel (tq_attn_sm100.cu,
+    """bf16 with d in {64, 128}: T in {16, 32} packed tcgen05 kernel (128 / T pairs per tile; 12, 15 and 18 pairs leave a
+    ragged last CTA), 32 < T <= 512: tcgen05 kernel (tq_attn_sm100.cu,
     ragged T exercises the TMA zero fill and the key mask, T = 300 the 256 + 128 key split, 129 the half-empty
     softmax split); everything else (fp32, d = 32, T > 512): FFMA kernel."""
     from tqdne_b200.engine import Act
@@ -351,7 +352,7 @@ def test_attention_matches_reference_formula(N, T, heads, d, dtype):
     qkv = torch.randn(N, T, 3 * C, device="cuda", generator=g)
     plan = _plan(dtype)
     out = plan.attention(Act(qkv.to(dtype).reshape(-1), N, 1, T, 3 * C), heads)
-    tc = dtype == torch.bfloat16 and d in (64, 128) and 32 < T <= 512
+    tc = dtype == torch.bfloat16 and d in (64, 128) and (32 < T <= 512 or T in (16, 32))
     assert ("attention_tc" in plan.op_names()[-1]) == tc, plan.op_names()
     plan.run()
     torch.cuda.synchronize()

@@ -250,6 +250,194 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attention_tc_kernel(const __gri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// T = 16 or 32 (latent UNet: 4 x 4 = 16 tokens): 128 / T (sample, head) pairs share one CTA and ONE pair of 128-row
+// MMAs.  S[128 x 128] = Q_packed K_packed^T holds the T x T score blocks of the pairs on its diagonal (the
+// off-diagonal products are computed and ignored: the tensor pipe is idle anyway and the kernel is bound by the
+// 3 x 128 rows it loads); P is written block-diagonal, so O = P V_packed is exact.
+struct AttnPackParams {
+    CUtensorMap map;   // qkv as [N][T][3C] bf16, box {64, T, 1}
+    __nv_bfloat16* out;
+    int N, heads, pairs;  // pairs = N * heads
+    float scale_log2;
+};
+
+template <int D, int T>
+__global__ void __launch_bounds__(128) attention_tc_packed_kernel(const __grid_constant__ AttnPackParams p) {
+    constexpr int DC = D / 64;
+    constexpr int PP = 128 / T;                  // (sample, head) pairs per CTA
+    constexpr uint32_t OPB = DC * 16384u;        // one packed operand: DC slabs of 128 rows x 128 B
+    constexpr uint32_t BOX = (uint32_t)T * 128u;  // one TMA box: T rows x 64 channels
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[3];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_smem = base;
+    const uint32_t kp_smem = q_smem + OPB;       // K, later P [2 slabs][128 x 128 B]
+    const uint32_t v_smem = kp_smem + 32768u;
+    const uint32_t bar_qk = smem_u32(&bars[0]), bar_v = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C = p.heads * D;
+    constexpr uint32_t tmem_cols = D > 128 ? 256u : 128u;
+
+    pdl_launch_dependents();
+    if (warp == 1 && lane == 0) {
+        tma_prefetch_desc(&p.map);
+        mbar_init(bar_qk, 1);
+        mbar_init(bar_v, 1);
+        mbar_init(bar_mma, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(smem_u32(&tmem_slot), tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+    pdl_wait();
+
+    const int pair0 = blockIdx.x * PP;
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(bar_qk, 2u * OPB);
+            for (int which = 0; which < 3; ++which) {
+                if (which == 2) mbar_arrive_expect_tx(bar_v, OPB);
+                const uint32_t dst0 = which == 0 ? q_smem : (which == 1 ? kp_smem : v_smem);
+                const uint32_t bar = which == 2 ? bar_v : bar_qk;
+                for (int j = 0; j < PP; ++j) {
+                    const int pr = min(pair0 + j, p.pairs - 1);  // a ragged last CTA re-loads a valid pair (never stored)
+                    const int n = pr / p.heads, h = pr % p.heads;
+#pragma unroll
+                    for (int c = 0; c < DC; ++c)
+                        tma_load_3d(dst0 + c * 16384u + j * BOX, &p.map, bar, which * C + h * D + 64 * c, 0, n);
+                }
+            }
+        }
+        __syncwarp();
+        mbar_wait(bar_qk, 0);
+        tc_fence_after();
+        if (elect_one()) {
+            constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t q_lo = ((q_smem & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t k_lo = ((kp_smem & 0x3FFFFu) >> 4) | (1u << 16);
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+#pragma unroll
+            for (int c = 0; c < DC; ++c)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem_base, umma_desc_pack(q_lo + ((c * 16384u) >> 4) + 2u * kk, desc_hi),
+                              umma_desc_pack(k_lo + ((c * 16384u) >> 4) + 2u * kk, desc_hi), idesc, (c | kk) != 0);
+            umma_commit(bar_mma);
+        }
+        __syncwarp();
+    }
+
+    // ---- softmax of this row's T x T diagonal block
+    const int row = warp * 32 + lane;
+    const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    float sv[T];
+    {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + warp * 32, r);   // the 32 key columns of this warp's 32 / T pairs
+        tmem_ld_wait();
+        if constexpr (T == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(r[j]);
+        } else {
+            const bool hi = lane >= 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sv[j] = __uint_as_float(hi ? r[16 + j] : r[j]);
+        }
+    }
+    float m = sv[0];
+#pragma unroll
+    for (int j = 1; j < T; ++j) m = fmaxf(m, sv[j]);
+    const float sc = p.scale_log2, msc = m * sc;
+    float l = 0.f;
+    uint32_t pk[T / 2];
+#pragma unroll
+    for (int j = 0; j < T / 2; ++j) {
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(ex2_approx(fmaf(sv[2 * j], sc, -msc)), ex2_approx(fmaf(sv[2 * j + 1], sc, -msc)));
+        l += __low2float(b2) + __high2float(b2);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    {
+        // block-diagonal P row: 16 chunks of 8 keys, non-zero only for this pair's keys [k0, k0 + T)
+        const uint32_t p_row = kp_smem + (uint32_t)row * 128u;
+        const uint32_t xr = (uint32_t)(row & 7);
+        const int ch0 = (row / T) * (T / 8);
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+            const uint32_t addr = p_row + (uint32_t)(ch >> 3) * 16384u + ((((uint32_t)ch & 7u) ^ xr) << 4);
+            const int q = ch - ch0;
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+            for (int qq = 0; qq < T / 8; ++qq)
+                if (q == qq) { w0 = pk[4 * qq]; w1 = pk[4 * qq + 1]; w2 = pk[4 * qq + 2]; w3 = pk[4 * qq + 3]; }
+            sts128(addr, w0, w1, w2, w3);
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    if (warp == 0) {
+        mbar_wait(bar_v, 0);
+        tc_fence_after();
+        if (elect_one()) {
+            constexpr uint32_t p_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t p_lo = ((kp_smem & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t v_lo = ((v_smem & 0x3FFFFu) >> 4) | ((16384u >> 4) << 16);
+            constexpr uint32_t idesc = umma_idesc_bf16(128, D) | (1u << 16);  // B operand (V) MN-major
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem_base, umma_desc_pack(p_lo + ((j * 16384u) >> 4) + 2u * kk, p_hi),
+                              umma_desc_pack(v_lo + (((uint32_t)(j * 64 + kk * 16) * 128u) >> 4), p_hi), idesc, (j | kk) != 0);
+            umma_commit(bar_mma);
+        }
+        __syncwarp();
+    }
+    mbar_wait(bar_mma, 1);
+    tc_fence_after();
+    {
+        const float inv = 1.f / l;
+        const int pr = pair0 + row / T, t = row % T;
+        const int n = pr / p.heads, h = pr % p.heads;
+        __nv_bfloat16* o = p.out + ((long long)n * T + t) * C + h * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + c, r);
+            tmem_ld_wait();
+            if (pr < p.pairs) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[8 * q + 2 * j]) * inv,
+                                                                        __uint_as_float(r[8 * q + 2 * j + 1]) * inv);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(o + c + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (fn) return fn;
@@ -279,11 +467,27 @@ int launch_attn_tc(const AttnTcParams& p, cudaStream_t st) {
     return 0;
 }
 
+template <int D, int T>
+int launch_attn_packed(const AttnPackParams& p, cudaStream_t st) {
+    constexpr size_t smem = 1024 + (size_t)(D / 64) * 16384 * 2 + 32768;
+    static bool attr = false;
+    if (!attr) {
+        TQ_CUDA(cudaFuncSetAttribute(attention_tc_packed_kernel<D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    constexpr int PP = 128 / T;
+    TQ_CUDA(launch_pdl(attention_tc_packed_kernel<D, T>, dim3((p.pairs + PP - 1) / PP), dim3(128), smem, st, p));
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 }  // namespace
 
 bool attention_tc_supported(const tq_attn_desc& d) {
-    if (d.dtype != TQ_BF16 || (d.d != 64 && d.d != 128) || d.T <= 32 || d.T > 512) return false;
+    if (d.dtype != TQ_BF16 || (d.d != 64 && d.d != 128) || d.T > 512) return false;
     if ((reinterpret_cast<uintptr_t>(d.qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(d.out) & 15) != 0) return false;
+    if (d.T <= 32) return d.T == 16 || d.T == 32;  // packed kernel: whole (sample, head) pairs per 128-row tile
     const int Tk = (d.T + 127) / 128 * 128;
     return attn_tc_smem(Tk, d.d) <= 224 * 1024;  // + ~2 KB of static shared memory
 }
@@ -299,7 +503,8 @@ int build_attention_tc(std::vector<Op>& ops, const tq_attn_desc& d) {
     p->scale_log2 = 1.4426950408889634f / sqrtf((float)d.d);
     cuuint64_t dims[3] = {(cuuint64_t)(3 * C), (cuuint64_t)d.T, (cuuint64_t)d.N};
     cuuint64_t strides[2] = {(cuuint64_t)(3 * C) * 2, (cuuint64_t)d.T * (3 * C) * 2};
-    cuuint32_t box[3] = {64, 128, 1};
+    const bool packed = d.T <= 32;
+    cuuint32_t box[3] = {64, packed ? (cuuint32_t)d.T : 128u, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&p->map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d.qkv), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -308,6 +513,20 @@ int build_attention_tc(std::vector<Op>& ops, const tq_attn_desc& d) {
     const int dd = d.d;
     Op op;
     char nm[64];
+    if (packed) {
+        auto q = std::make_shared<AttnPackParams>();
+        q->map = p->map; q->out = p->out; q->N = d.N; q->heads = d.heads; q->pairs = d.N * d.heads;
+        q->scale_log2 = p->scale_log2;
+        const int tt = d.T;
+        snprintf(nm, sizeof nm, "attention_tc_packed<bf16,d=%d> T=%d", dd, d.T);
+        op.name = nm;
+        op.launch = [q, dd, tt](cudaStream_t st) -> int {
+            if (dd == 128) return tt == 16 ? launch_attn_packed<128, 16>(*q, st) : launch_attn_packed<128, 32>(*q, st);
+            return tt == 16 ? launch_attn_packed<64, 16>(*q, st) : launch_attn_packed<64, 32>(*q, st);
+        };
+        ops.push_back(std::move(op));
+        return 0;
+    }
     snprintf(nm, sizeof nm, "attention_tc<bf16,d=%d> T=%d", dd, d.T);
     op.name = nm;
     op.launch = [p, dd](cudaStream_t st) -> int {
