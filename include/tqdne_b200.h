@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 2
+#define TQ_ABI_VERSION 3
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -156,6 +156,9 @@ typedef struct {
 int tq_plan_add_linear(tq_plan* p, const tq_linear_desc* d);
 /* feat[M, 2*half] = [sin(2*pi*t*W), cos(2*pi*t*W)],  t:[M] read from device                      */
 int tq_plan_add_fourier(tq_plan* p, const float* t, const float* W, int32_t M, int32_t half, float* feat);
+/* y[N, C] = mean over the P positions of x[N, P, ld] (fp32 channels-last, first C channels).
+ * Replaces: th.mean(h, dim=spatial) in LithningClassifier.embed (tqdne/classifier.py:51-53).      */
+int tq_plan_add_spatial_mean(tq_plan* p, const float* x, int32_t N, int32_t P, int32_t C, int32_t ld, float* y);
 
 /* ---- sampler element-wise steps ------------------------------------------------------------------ *
  * Replaces: LightningEDM.forward pre/post scaling (tqdne/edm.py:105-113) and the Heun/Euler

@@ -157,6 +157,36 @@ def encoder_forward(sd: dict, cfg: dict, x, prefix: str = ""):
     return _conv(x, sd[prefix + "output_layer.weight"], sd[prefix + "output_layer.bias"])
 
 
+def classifier_embed(sd: dict, enc_cfg: dict, x):
+    """LithningClassifier.embed (tqdne/classifier.py:51-55): Encoder -> mean over the spatial dims -> SiLU, Linear,
+    SiLU, Linear (output_MLP, classifier.py:39-44)."""
+    h = encoder_forward(sd, enc_cfg, x, prefix="encoder.")
+    h = h.mean(dim=list(range(2, h.dim())))
+    h = F.linear(F.silu(h), sd["output_MLP.1.weight"], sd["output_MLP.1.bias"])
+    return F.linear(F.silu(h), sd["output_MLP.3.weight"], sd["output_MLP.3.bias"])
+
+
+def classifier_forward(sd: dict, enc_cfg: dict, x):
+    """LithningClassifier.forward (tqdne/classifier.py:57-59)."""
+    return F.linear(classifier_embed(sd, enc_cfg, x), sd["output_layer.weight"], sd["output_layer.bias"])
+
+
+def frechet_distance(x, y, eps: float = 1e-6):
+    """tqdne.metric.frechet_distance (tqdne/metric.py:13-44), non-isotropic branch, NumPy / SciPy like the reference."""
+    import numpy as np
+    from scipy import linalg
+
+    mu_x, mu_y = x.mean(0), y.mean(0)
+    cov_x, cov_y = np.cov(x, rowvar=False), np.cov(y, rowvar=False)
+    covmean = linalg.sqrtm(cov_x @ cov_y)
+    if not np.isfinite(covmean).all():
+        off = np.eye(cov_x.shape[0]) * eps
+        covmean = linalg.sqrtm((cov_x + off) @ (cov_y + off))
+    if np.iscomplexobj(covmean):
+        covmean = covmean.real
+    return float(np.sum((mu_x - mu_y) ** 2) + np.trace(cov_x) + np.trace(cov_y) - 2 * np.trace(covmean))
+
+
 # ---- EDM (tqdne/edm.py) ----------------------------------------------------------------------------
 SIGMA_MIN, SIGMA_MAX, RHO, SIGMA_DATA = 0.002, 80.0, 7.0, 0.5
 S_CHURN, S_MIN, S_MAX, S_NOISE = 40, 0.05, 50, 1.003

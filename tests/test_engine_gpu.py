@@ -238,3 +238,36 @@ def test_generate_waveforms_cli_end_to_end(tmp_path):
     # (measured 3e-2 .. 6e-2 run to run: the fp32 statistics atomics are unordered, so even the same batching is not
     # bit-reproducible in bf16 mode); the bound is the waveform-domain bf16 budget 1e-2 x 10.7 of SURVEY section 8(d)
     assert np.abs(w).max() < 1e4 and rel_l2(w, ref) < 1.1e-1
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_classifier_embed_and_metrics_match_reference_golden(mode):
+    """LithningClassifier.embed / forward on the engine (encoder plan -> spatial mean -> dense layers) against the
+    reference classifier's outputs; Frechet distance / inception score of the embeddings against the oracle's."""
+    from tests.test_oracle import CLASSIFIER_ENCODER
+    from tqdne_b200.classifier import LithningClassifier
+    from tqdne_b200.metric import FrechetInceptionDistance, InceptionScore
+    from tqdne_b200.representation import Identity
+
+    g = golden("classifier")
+    clf = seeded(LithningClassifier(CLASSIFIER_ENCODER, 5), 21).cuda().eval()
+    clf.encoder.engine_dtype = DT[mode]
+    x = g["x"].cuda()
+    emb, logits = clf.embed(x), clf(x)
+    assert emb.shape == (3, 256) and logits.shape == (3, 5)
+    assert rel_l2(emb.cpu(), g["emb"]) < TOL[mode] and rel_l2(logits.cpu(), g["logits"]) < TOL[mode]
+    # ragged batching through the metric front-ends: 7 inputs in batches of 3
+    gen = torch.Generator().manual_seed(5)
+    pred, target = torch.randn(7, 3, 64, 64, generator=gen), torch.randn(7, 3, 64, 64, generator=gen) * 1.5
+    sd = {k: v.cpu() for k, v in clf.state_dict().items()}
+    with torch.no_grad():
+        ep = torch_ref.classifier_embed(sd, CLASSIFIER_ENCODER, pred)
+        lp = torch_ref.classifier_forward(sd, CLASSIFIER_ENCODER, pred)
+    fid = FrechetInceptionDistance(clf, Identity(), batch_size=3)
+    got = fid._batched(clf.embed, pred.cuda())
+    assert rel_l2(torch.from_numpy(got), ep) < TOL[mode]
+    isc = InceptionScore(clf, Identity(), batch_size=3)
+    prob = torch.softmax(lp, -1).numpy()
+    want = np.exp(np.sum(prob * (np.log(prob) - np.log(prob.mean(0))), -1).mean())
+    assert abs(float(isc(pred.numpy())) - want) < (5e-2 if mode == "bf16" else 1e-4) * want
+    assert np.isfinite(float(fid(pred.numpy(), target.numpy())))

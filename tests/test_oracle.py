@@ -179,3 +179,26 @@ def test_griffinlim_loop_pinned_against_torchaudio():
         out = griffinlim_ref.griffinlim(S, n_iter=n_iter, pad_mode="reflect", init="ones", eps=1e-16)
         assert out.shape == ref.shape == (4064,)
         assert np.abs(out - ref).max() < 1e-9 * np.abs(ref).max()
+
+
+CLASSIFIER_ENCODER = {"in_channels": 3, "model_channels": 64, "channel_mult": (1, 2, 4, 4), "out_channels": 256,
+                      "num_res_blocks": 2, "attention_resolutions": (8,), "dims": 2, "conv_kernel_size": 3, "num_heads": 4,
+                      "dropout": 0.1, "flash_attention": False}   # experiments/train_classifier.py:70-82
+
+
+def test_classifier_embedding_and_frechet_distance_restatement():
+    """oracle classifier_embed / classifier_forward / frechet_distance against the reference's own
+    LithningClassifier and tqdne.metric.frechet_distance (oracle/make_golden_classifier.py)."""
+    from tqdne_b200.classifier import LithningClassifier
+    from tqdne_b200.metric import frechet_distance
+
+    g = golden("classifier")
+    sd = _sd(LithningClassifier(CLASSIFIER_ENCODER, 5), 21)
+    with torch.no_grad():
+        emb = torch_ref.classifier_embed(sd, CLASSIFIER_ENCODER, g["x"])
+        logits = torch_ref.classifier_forward(sd, CLASSIFIER_ENCODER, g["x"])
+    assert rel_l2(emb, g["emb"]) < TOL and rel_l2(logits, g["logits"]) < TOL
+    a, b = g["fid_a"].numpy(), g["fid_b"].numpy()
+    ref = float(g["fid"])
+    assert abs(torch_ref.frechet_distance(a, b) - ref) < 1e-9 * abs(ref)
+    assert abs(float(frechet_distance(a, b)) - ref) < 1e-9 * abs(ref)   # the product's host-side reduction

@@ -15,6 +15,7 @@ from .architectures import (  # noqa: F401
 )
 from .autoencoder import LightningAutoencoder  # noqa: F401
 from .blocks import Decoder, Encoder  # noqa: F401
+from .classifier import LithningClassifier  # noqa: F401
 from .edm import EDM, LightningEDM  # noqa: F401
 from .representation import Identity, LogSpectrogram, MovingAverageEnvelope, Normalization  # noqa: F401
 from .unet import UNetModel  # noqa: F401

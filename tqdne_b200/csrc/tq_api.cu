@@ -169,5 +169,10 @@ int tq_plan_add_fourier(tq_plan* p, const float* t, const float* W, int32_t M, i
     drop_graph(p);
     return build_fourier(p->ops, t, W, M, half, feat);
 }
+int tq_plan_add_spatial_mean(tq_plan* p, const float* x, int32_t N, int32_t P, int32_t C, int32_t ld, float* y) {
+    TQ_CHECK(p != nullptr, "null argument");
+    drop_graph(p);
+    return build_spatial_mean(p->ops, x, N, P, C, ld, y);
+}
 
 }  // extern "C"

@@ -360,6 +360,42 @@ int build_fourier(std::vector<Op>& ops, const float* t, const float* W, int M, i
     return 0;
 }
 
+// mean over the positions of a channels-last fp32 tensor: y[n][c] = mean_p x[n][p][c]   (row stride ld >= C)
+// one CTA per (sample, 32-channel slab): 8 position lanes x 32 channels, coalesced 128 B rows, smem tree at the end
+__global__ void __launch_bounds__(256) spatial_mean_kernel(const float* __restrict__ x, int P, int C, int ld, float* __restrict__ y) {
+    __shared__ float red[8][33];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int n = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
+    float a = 0.f;
+    if (c < C) {
+        const float* xb = x + (long long)n * P * ld + c;
+        for (int p = pl; p < P; p += 8) a += __ldg(xb + (long long)p * ld);
+    }
+    red[pl][threadIdx.x & 31] = a;
+    __syncthreads();
+    if (pl == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        y[(long long)n * C + c] = t / (float)P;
+    }
+}
+
+int build_spatial_mean(std::vector<Op>& ops, const float* x, int N, int P, int C, int ld, float* y) {
+    TQ_CHECK(x && y && N > 0 && P > 0 && C > 0 && ld >= C, "spatial_mean: bad arguments");
+    Op op;
+    op.name = "spatial_mean";
+    op.launch = [=](cudaStream_t st) -> int {
+        TQ_CUDA(launch_pdl(spatial_mean_kernel, dim3((C + 31) / 32, N), dim3(256), 0, st, x, P, C, ld, y));
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    };
+    ops.push_back(std::move(op));
+    return 0;
+}
+
 }  // namespace tq
 
 using namespace tq;

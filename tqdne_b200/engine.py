@@ -434,6 +434,11 @@ class Plan:
         self.op_meta.append(("fourier", 0, 0))
         self.keep += [t, Wf, feat]
 
+    def spatial_mean(self, x: torch.Tensor, N: int, P: int, Cc: int, ld: int, y: torch.Tensor):
+        _lib.check(self.lib.tq_plan_add_spatial_mean(self.h, x.data_ptr(), N, P, Cc, ld, y.data_ptr()), "plan_add_spatial_mean")
+        self.op_meta.append(("spatial_mean", 0, 4 * N * P * Cc))
+        self.keep += [x, y]
+
     # -- execution ------------------------------------------------------------------------------
     def enable_graph(self, on: bool = True) -> None:
         _lib.check(self.lib.tq_plan_enable_graph(self.h, 1 if on else 0), "plan_enable_graph")
