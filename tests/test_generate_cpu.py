@@ -49,16 +49,45 @@ def test_output_schema(tmp_path):
              "hypocentre_depth": [10.0, 10.0], "azimuthal_gap": [130.0, 130.0]}
     w = np.random.default_rng(0).standard_normal((2, 3, 4064))
     out = gw.write_outputs(tmp_path / "w.h5", feats, w)
-    if out.endswith(".npz"):
-        z = np.load(out)
-        keys = set(z.files)
-    else:
-        import h5py
-
-        z = h5py.File(out)
-        keys = set(z.keys())
-    assert keys == {"hypocentral_distance", "magnitude", "vs30s", "hypocentre_depth", "azimuthal_gap", "waveforms"}
+    assert out.endswith("w.h5") and open(out, "rb").read(8) == b"\x89HDF\r\n\x1a\n"
+    z = gw.read_outputs(out)
+    assert set(z) == {"hypocentral_distance", "magnitude", "vs30s", "hypocentre_depth", "azimuthal_gap", "waveforms"}
     assert z["waveforms"].shape == (2, 3, 4064) and z["waveforms"].dtype == np.float32
+    assert np.array_equal(z["waveforms"], w.astype(np.float32))
+    assert z["magnitude"].dtype == np.float64 and list(z["vs30s"]) == [300.0, 300.0]
+
+
+def test_minimal_hdf5_writer_structures(tmp_path):
+    """hdf5_min writes the version-0 superblock / version-1 group structures of the HDF5 file format specification
+    (no libhdf5 in this image to open the file with: the reader below follows the addresses in the file)."""
+    import struct
+
+    from tqdne_b200 import hdf5_min
+
+    rng = np.random.default_rng(1)
+    data = {f"d{i:02d}": rng.standard_normal((i + 1, 3)).astype(np.float32 if i % 2 else np.float64) for i in range(11)}
+    data["counts"] = np.arange(7, dtype=np.int64)
+    data["empty_tail"] = np.zeros((0, 4), np.float32)
+    data["bytes"] = np.arange(5, dtype=np.uint8)
+    path = tmp_path / "m.h5"
+    hdf5_min.write(path, data)           # 14 datasets: two symbol-table nodes under the group B-tree
+    raw = open(path, "rb").read()
+    assert raw[:8] == hdf5_min.SIGNATURE and raw[8] == 0 and raw[13] == 8 and raw[14] == 8
+    leaf_k, internal_k = struct.unpack_from("<HH", raw, 16)
+    assert (leaf_k, internal_k) == (4, 16)
+    base, free, eof, drv = struct.unpack_from("<QQQQ", raw, 24)
+    assert base == 0 and free == hdf5_min.UNDEF and drv == hdf5_min.UNDEF and eof == len(raw)
+    btree, heap = struct.unpack_from("<QQ", raw, 80)
+    assert raw[btree:btree + 4] == b"TREE" and raw[heap:heap + 4] == b"HEAP"
+    assert struct.unpack_from("<H", raw, btree + 6)[0] == 2      # two children
+    back = hdf5_min.read(path)
+    assert list(back) == sorted(data)                              # symbol-table order = byte order of the names
+    for k, v in data.items():
+        assert back[k].dtype == v.dtype and back[k].shape == v.shape and np.array_equal(back[k], v)
+    with pytest.raises(TypeError):
+        hdf5_min.write(tmp_path / "bad.h5", {"c": np.zeros(2, np.complex64)})
+    with pytest.raises(ValueError):
+        hdf5_min.write(tmp_path / "bad.h5", {"a/b": np.zeros(2)})
 
 
 def test_reference_checkpoint_loads_without_the_reference_package(monkeypatch):

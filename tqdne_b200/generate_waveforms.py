@@ -11,8 +11,8 @@ Differences, all explicit:
     contiguously over the ranks and rank 0 gathers and writes (no collective on the data path);
   * no network: checkpoints are never downloaded.  Without checkpoints `--random_init` builds the named
     architecture with seeded random weights (useful for benchmarking only);
-  * HDF5 needs h5py; when it is not installed the same datasets are written to `<outfile>.npz` and the
-    program says so.
+  * the HDF5 file is written with h5py when it is installed, otherwise by the built-in minimal HDF5 writer
+    (`tqdne_b200/hdf5_min.py`: same datasets, dtypes and names, readable by any HDF5 library).
 Engine extras: `--precision {bf16,fp32}`, `--seed`, `--num_sampling_steps`, `--random_init`.
 """
 
@@ -97,21 +97,35 @@ def load_models(edm_checkpoint, autoencoder_checkpoint, device, random_init=Fals
 
 
 def write_outputs(outfile, features: dict, waveforms: np.ndarray) -> str:
-    """HDF5 with the reference's dataset names (:177-184; note the key "vs30s"); .npz when h5py is absent."""
+    """HDF5 with the reference's dataset names and dtypes (:177-184; note the key "vs30s"): 1-D float64 features,
+    `waveforms` float32 -- through h5py when installed, else through the built-in writer (hdf5_min)."""
     names = {"hypocentral_distance": "hypocentral_distance", "magnitude": "magnitude", "vs30": "vs30s",
              "hypocentre_depth": "hypocentre_depth", "azimuthal_gap": "azimuthal_gap"}
+    data = {names[k]: np.array(v) for k, v in features.items()}
+    data["waveforms"] = np.asarray(waveforms, dtype=np.float32)
     try:
         import h5py
     except ImportError:
-        out = str(outfile) + ".npz"
-        np.savez(out, waveforms=waveforms.astype(np.float32), **{names[k]: np.array(v) for k, v in features.items()})
-        print(f"h5py is not installed: wrote the same datasets to {out}")
-        return out
+        from . import hdf5_min
+
+        hdf5_min.write(outfile, data)
+        return str(outfile)
     with h5py.File(outfile, "w") as f:
-        for k, v in features.items():
-            f.create_dataset(names[k], data=np.array(v))
-        f.create_dataset("waveforms", data=waveforms.astype(np.float32))
+        for k, v in data.items():
+            f.create_dataset(k, data=v)
     return str(outfile)
+
+
+def read_outputs(path) -> dict:
+    """{dataset name: array} of a generate-waveforms output file (h5py when installed, else hdf5_min.read)."""
+    try:
+        import h5py
+    except ImportError:
+        from . import hdf5_min
+
+        return hdf5_min.read(path)
+    with h5py.File(path) as f:
+        return {k: f[k][:] for k in f.keys()}
 
 
 @torch.no_grad()
