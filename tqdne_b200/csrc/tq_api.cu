@@ -6,6 +6,10 @@
 
 #include "tq_common.h"
 
+#ifndef TQ_PDL_DEFAULT
+#define TQ_PDL_DEFAULT 2
+#endif
+
 namespace tq {
 
 static thread_local char g_err[512] = "";
@@ -37,23 +41,34 @@ static void drop_graph(tq_plan* p) {
     p->graph_ops = 0;
 }
 
+static thread_local bool g_pdl_current = false;
+void pdl_set_current(bool on) { g_pdl_current = on; }
+
 static int run_ops(tq_plan* p, int first, int last, cudaStream_t st) {
+    const int mode = pdl_mode();
     for (int i = first; i < last; ++i) {
-        if (p->ops[i].launch(st)) return 1;
+        // mode 2: a programmatic edge only INTO a small (latency-bound) op that follows another op of this run; the
+        // big, power-bound kernels keep full stream serialisation (overlapping them measured slower)
+        pdl_set_current(mode == 1 || (mode == 2 && i > first && p->ops[i].small));
+        const int rc = p->ops[i].launch(st);
+        pdl_set_current(false);
+        if (rc) return 1;
     }
     return 0;
 }
 
-bool pdl_enabled() {
-    static const bool on = [] {
-        // off unless TQ_PDL=1: measured on the latent UNet plan at batch 256 (tools/ab_env.py TQ_PDL 0 1) the
-        // programmatic edges are 1.3 % SLOWER (4.745 vs 4.685 ms) -- the step is power-capped, so filling the
-        // inter-kernel gaps only lowers the clock
+int pdl_mode() {
+    static const int mode = [] {
+        // TQ_PDL=1 (every kernel) measured 1.3 % SLOWER on the latent UNet plan at batch 256 (4.745 vs 4.685 ms,
+        // tools/ab_env.py): the big kernels are power-capped, so filling their inter-kernel gaps only lowers the clock.
+        // TQ_PDL=2 restricts the programmatic edges to the small single-wave launches of the 4x4 / 8x8 levels.
         const char* e = getenv("TQ_PDL");
-        return e && e[0] == '1';
+        if (!e || !e[0]) return TQ_PDL_DEFAULT;
+        return (e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : TQ_PDL_DEFAULT;
     }();
-    return on;
+    return mode;
 }
+bool pdl_enabled() { return g_pdl_current; }
 
 }  // namespace tq
 

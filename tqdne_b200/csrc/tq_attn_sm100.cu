@@ -520,6 +520,7 @@ int build_attention_tc(std::vector<Op>& ops, const tq_attn_desc& d) {
         const int tt = d.T;
         snprintf(nm, sizeof nm, "attention_tc_packed<bf16,d=%d> T=%d", dd, d.T);
         op.name = nm;
+        op.small = true;
         op.launch = [q, dd, tt](cudaStream_t st) -> int {
             if (dd == 128) return tt == 16 ? launch_attn_packed<128, 16>(*q, st) : launch_attn_packed<128, 32>(*q, st);
             return tt == 16 ? launch_attn_packed<64, 16>(*q, st) : launch_attn_packed<64, 32>(*q, st);

@@ -38,6 +38,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 struct Op {
     std::string name;
     std::function<int(cudaStream_t)> launch;
+    bool small = false;  // latency-bound launch (single wave, few microseconds): a candidate for a programmatic edge
 };
 
 int device_sm_count();
@@ -45,6 +46,10 @@ int device_sm_count();
 // launch latency and prologue with the previous kernel's drain; every kernel launched this way executes
 // griddepcontrol.wait before it touches memory a predecessor may still be writing.
 bool pdl_enabled();
+// TQ_PDL: 0 = never, 1 = every kernel of a plan, 2 = only where a small op follows another op (set per op by the plan
+// runner through pdl_set_current)
+int pdl_mode();
+void pdl_set_current(bool on);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -335,6 +335,7 @@ int build_linear(std::vector<Op>& ops, const tq_linear_desc& d) {
     TQ_CHECK(!d.y_act || d.y_act_dtype == TQ_F32 || d.y_act_dtype == TQ_BF16, "linear: bad y_act_dtype");
     Op op;
     op.name = "linear_f32";
+    op.small = true;
     op.launch = [p](cudaStream_t st) -> int {
         const long long warps = p->x_rows == 1 ? p->Nout : (long long)p->M * p->Nout;
         TQ_CUDA(launch_pdl(linear_kernel, dim3(blocks_for(warps * 32, 256)), dim3(256), 0, st, *p));
@@ -350,6 +351,7 @@ int build_fourier(std::vector<Op>& ops, const float* t, const float* W, int M, i
     TQ_CHECK(t && W && feat && M > 0 && half > 0, "fourier: bad arguments");
     Op op;
     op.name = "fourier_features";
+    op.small = true;
     op.launch = [=](cudaStream_t st) -> int {
         TQ_CUDA(launch_pdl(fourier_kernel, dim3(blocks_for((long long)M * half, 128)), dim3(128), 0, st, t, W, M, half, feat));
         TQ_CUDA(cudaGetLastError());

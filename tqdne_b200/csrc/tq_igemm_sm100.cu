@@ -965,6 +965,8 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     char nm[112];
     snprintf(nm, sizeof nm, "igemm_sm100<BN=%d,CG=%d,%s> tiles=%d slices=%d%s", bn_tile, cg, f32 ? "f32" : "bf16",
              p->total_tiles, d.num_slices, row3_groups > 0 ? " row3" : "");
+    // tile FLOPs (padding included) under ~40 GFLOP: a launch of <= ~35 us that is bound by its fill / drain latency
+    op.small = 2.0 * p->total_tiles * (128.0 * cg) * bn_tile * d.num_slices * 64.0 < 40e9;
     op.name = nm;
     const std::string opname = nm;
     op.launch = [p, dsl_owner, prof_owner, opname, grid, bn_tile, cg, f32](cudaStream_t st) -> int {

@@ -381,6 +381,7 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
     }
     Op ap;
     ap.name = f32 ? "gn_apply<f32>" : "gn_apply<bf16>";
+    ap.small = (double)d.N * d.P * Ct * (f32 ? 8 : 4) < 40e6;  // < 40 MB moved: latency-bound
     ap.launch = [p, grid, f32, smem](cudaStream_t s) -> int {
         if (f32) TQ_CUDA(launch_pdl(gn_apply_kernel<float>, grid, dim3(256), smem, s, *p));
         else TQ_CUDA(launch_pdl(gn_apply_kernel<__nv_bfloat16>, grid, dim3(256), smem, s, *p));
