@@ -295,7 +295,7 @@ def run_engine(args) -> None:
     cond_dev = cond_host.to(dev)
     noise_dev = noise_host.to(dev)
     h2d = cond_host.numel() * 4 + noise_host.numel() * 8
-    d2h = (hi - lo) * 3 * cfg.t * 4
+    d2h = total * 3 * cfg.t * 4   # rank 0 reads the gathered waveforms of ALL ranks back
 
     def step_resident():
         rep = edm.sample((hi - lo, 3, 128, 128), cond=cond_dev, noise=noise_dev)
@@ -308,8 +308,8 @@ def run_engine(args) -> None:
         wav = rep_inv.invert_representation_device(rep)
         if world > 1:
             full = sharding.gather_waveforms(wav, total)   # the one collective: final gather to rank 0
-            return full.cpu() if full is not None else None
-        return wav.cpu()
+            return sharding.to_host(full) if full is not None else None
+        return sharding.to_host(wav)       # D2H into a pinned buffer, synchronised (what generate() does before writing)
 
     def barrier():
         if world > 1:

@@ -51,3 +51,7 @@ rep = timed("decode (4 micro-batches of 64)", decode2)
 timed("griffin-lim (768 items, 128 iterations)", lambda: rep_inv.invert_representation_device(rep))
 timed("whole step through sample()", lambda: rep_inv.invert_representation_device(
     edm.sample((B, 3, 128, 128), cond=cond, noise=noise)))
+for mp in [int(a) for a in sys.argv[2:]]:
+    edm.max_positions_per_pass = mp * 1024
+    timed(f"whole step, Heun micro-batch {mp}", lambda: rep_inv.invert_representation_device(
+        edm.sample((B, 3, 128, 128), cond=cond, noise=noise)))

@@ -166,7 +166,7 @@ def generate(hypocentral_distance, magnitude, vs30, hypocentre_depth, azimuthal_
         local[i - lo:j - lo] = config.representation.invert_representation_device(sample)
     full = sharding.gather_waveforms(local, n_total)
     if full is not None and rank == 0:
-        out = write_outputs(outfile, features, full.cpu().numpy())
+        out = write_outputs(outfile, features, sharding.to_host(full).numpy())
         print(f"done! -> {out}")
         return out
     return None

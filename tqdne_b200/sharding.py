@@ -49,10 +49,38 @@ def gather_waveforms(local: torch.Tensor, n_total: int, dst: int = 0) -> torch.T
         return local
     sizes = [shard_bounds(n_total, r, ws) for r in range(ws)]
     max_n = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros((max_n, *local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(ws)] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst)
+    even = all(hi - lo == max_n for lo, hi in sizes)
+    if even:
+        pad = local.contiguous()
+    else:
+        pad = torch.zeros((max_n, *local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+    # the receive buffers are the rows of ONE [ws, max_n, ...] tensor: equal shards need no concatenation afterwards
+    stacked = torch.empty((ws, max_n, *local.shape[1:]), dtype=local.dtype, device=local.device) if rank == dst else None
+    dist.gather(pad, list(stacked.unbind(0)) if rank == dst else None, dst=dst)
     if rank != dst:
         return None
-    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+    if even:
+        return stacked.view(ws * max_n, *local.shape[1:])
+    return torch.cat([stacked[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+_PINNED: dict = {}
+
+
+def to_host(t: torch.Tensor) -> torch.Tensor:
+    """Device -> host copy into a cached PINNED buffer (a fresh pageable `t.cpu()` of the gathered waveforms costs
+    first-touch page faults on ~50 KB per waveform every call).  The returned tensor is reused by the next call with the
+    same shape: consume (or copy) it before calling again."""
+    if t.device.type != "cuda":
+        return t
+    key = (tuple(t.shape), t.dtype)
+    buf = _PINNED.get(key)
+    if buf is None:
+        if len(_PINNED) > 8:
+            _PINNED.clear()
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        _PINNED[key] = buf
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return buf
