@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 3
+#define TQ_ABI_VERSION 4
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -159,6 +159,17 @@ int tq_plan_add_fourier(tq_plan* p, const float* t, const float* W, int32_t M, i
 /* y[N, C] = mean over the P positions of x[N, P, ld] (fp32 channels-last, first C channels).
  * Replaces: th.mean(h, dim=spatial) in LithningClassifier.embed (tqdne/classifier.py:51-53).      */
 int tq_plan_add_spatial_mean(tq_plan* p, const float* x, int32_t N, int32_t P, int32_t C, int32_t ld, float* y);
+
+/* ---- convolution weight gradient (first kernel of the training-step row) ---- *
+ * Replaces: the weight / bias gradient autograd computes for nn.Conv1d (tqdne/nn.py:16-24, stride 1,
+ * padding "same") inside LightningEDM.step (tqdne/edm.py:115-134).
+ *   x  : [N, L, cin]  bf16 channels-last (the layer input that the forward plan kept)
+ *   dy : [N, L, cout] bf16 channels-last (gradient of the layer output)
+ *   dw : [cout, taps, cin] fp32, db : [cout] fp32 or NULL -- ACCUMULATED INTO (zero them first):
+ *        dw[co][t][ci] += sum_{n,l} dy[n][l][co] * x[n][l + t - taps/2][ci],  db[co] += sum_{n,l} dy[n][l][co]
+ * cin and cout must be multiples of 64, taps odd and <= 7.                                          */
+int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* db, int32_t N, int64_t L, int32_t cin,
+                    int32_t cout, int32_t taps, void* stream);
 
 /* ---- sampler element-wise steps ------------------------------------------------------------------ *
  * Replaces: LightningEDM.forward pre/post scaling (tqdne/edm.py:105-113) and the Heun/Euler

@@ -560,3 +560,33 @@ def test_logspec_forward_full_batch_scaling_property():
     err = (r2 - r1 - shift).abs()
     # fp32 STFT: bins where the frame nearly cancels carry a larger relative error, which the log amplifies
     assert float(err.max()) < 5e-3 and float((err > 1e-4).float().mean()) < 1e-4
+
+
+@pytest.mark.parametrize("N,L,cin,cout,taps", [(3, 200, 128, 192, 5), (2, 64, 64, 64, 1), (2, 1016, 256, 256, 5),
+                                                (1, 77, 64, 128, 3), (4, 508, 512, 256, 5), (2, 130, 64, 64, 7)])
+def test_conv1d_wgrad_matches_autograd(N, L, cin, cout, taps):
+    """tq_conv1d_wgrad (tcgen05, MN-major operands, taps through descriptor row offsets of one halo buffer) against
+    the weight / bias gradient torch autograd computes for F.conv1d(padding='same') in fp32 on the same bf16-rounded
+    tensors; ragged L exercises the TMA zero fill at both ends of a sample."""
+    from tqdne_b200 import _lib
+    from tqdne_b200.engine import current_stream_ptr
+
+    g = torch.Generator(device="cuda").manual_seed(L + taps)
+    x = torch.randn(N, L, cin, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(N, L, cout, device="cuda", generator=g).to(torch.bfloat16)
+    dw = torch.zeros(cout, taps, cin, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    _lib.check(_lib.lib().tq_conv1d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), N, L, cin, cout, taps,
+                                          current_stream_ptr()), "conv1d_wgrad")
+    torch.cuda.synchronize()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        w = torch.zeros(cout, cin, taps, device="cuda", dtype=torch.float64, requires_grad=True)
+        b = torch.zeros(cout, device="cuda", dtype=torch.float64, requires_grad=True)
+        y = F.conv1d(x.double().permute(0, 2, 1), w, b, padding=taps // 2)
+        y.backward(dy.double().permute(0, 2, 1))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel_l2(dw, w.grad.permute(0, 2, 1)) < 2e-5
+    assert rel_l2(db, b.grad) < 2e-5
