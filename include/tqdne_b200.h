@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 4
+#define TQ_ABI_VERSION 5
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -170,6 +170,23 @@ int tq_plan_add_spatial_mean(tq_plan* p, const float* x, int32_t N, int32_t P, i
  * cin and cout must be multiples of 64, taps odd and <= 7.                                          */
 int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* db, int32_t N, int64_t L, int32_t cin,
                     int32_t cout, int32_t taps, void* stream);
+
+/* ---- GroupNorm(32) [+ SiLU] backward (training-step row) --------------------- *
+ * Replaces: autograd through GroupNorm32 + nn.SiLU (tqdne/nn.py:11-13,90-105, tqdne/unet.py:85-88,100-103).
+ * Same tensors as tq_gn_desc (virtual concat of x0 [N,P,C0] and x1 [N,P,C1], stats0/stats1 = the forward
+ * per-(sample, channel) sum / sum of squares), plus dy [N,P,C0+C1]; writes dx0 / dx1 and ACCUMULATES
+ * dgamma / dbeta [C0+C1] (either may be NULL).  ws: [N][C0+C1][2] fp32 scratch (cleared by the call).   */
+typedef struct {
+    int32_t dtype; int32_t N, P, C0, C1;
+    const void* x0; const void* x1; const void* dy;
+    const float* gamma; const float* beta;
+    float eps; int32_t silu;
+    const float* stats0; const float* stats1;
+    float* ws;
+    void* dx0; void* dx1;
+    float* dgamma; float* dbeta;
+} tq_gn_bwd_desc;
+int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream);
 
 /* ---- sampler element-wise steps ------------------------------------------------------------------ *
  * Replaces: LightningEDM.forward pre/post scaling (tqdne/edm.py:105-113) and the Heun/Euler

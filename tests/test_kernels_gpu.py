@@ -590,3 +590,64 @@ def test_conv1d_wgrad_matches_autograd(N, L, cin, cout, taps):
         torch.backends.cudnn.allow_tf32 = old
     assert rel_l2(dw, w.grad.permute(0, 2, 1)) < 2e-5
     assert rel_l2(db, b.grad) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("N,P,C0,C1,silu", [(3, 200, 64, 0, True), (2, 1016, 256, 0, True), (2, 300, 256, 128, True),
+                                            (2, 64, 128, 64, False), (5, 16, 512, 512, True), (1, 4064, 64, 128, True)])
+def test_groupnorm_silu_backward_matches_autograd(N, P, C0, C1, silu, dtype):
+    """tq_gn_silu_backward against autograd through silu(group_norm(cat[x0, x1])) on the same (rounded) tensors; C = 384
+    and 192 have groups that straddle the concat boundary."""
+    from tqdne_b200.backward import groupnorm_silu_backward
+    from tqdne_b200.engine import Act
+
+    g = torch.Generator(device="cuda").manual_seed(P + C0)
+    Ct = C0 + C1
+    x = _rt(torch.randn(N, P, Ct, device="cuda", generator=g) * 1.3 + 0.4, dtype)
+    dy = _rt(torch.randn(N, P, Ct, device="cuda", generator=g), dtype)
+    gamma = 1 + 0.2 * torch.randn(Ct, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(Ct, device="cuda", generator=g)
+
+    def act(t):
+        st = torch.stack([t.sum(1), (t * t).sum(1)], dim=-1).contiguous()   # [N, C, 2] like a conv epilogue writes
+        return Act(t.contiguous().to(dtype).reshape(-1), N, 1, P, t.shape[2], stats=st)
+
+    a0 = act(x[..., :C0])
+    a1 = act(x[..., C0:]) if C1 else None
+    dx0, dx1, dgam, dbet = groupnorm_silu_backward(a0, Act(dy.to(dtype).reshape(-1), N, 1, P, Ct), gamma, beta, silu=silu, x1=a1)
+    torch.cuda.synchronize()
+    xr = x.double().permute(0, 2, 1).clone().requires_grad_(True)
+    gr, br = gamma.double().clone().requires_grad_(True), beta.double().clone().requires_grad_(True)
+    y = F.group_norm(xr, 32, gr, br, eps=1e-5)
+    if silu:
+        y = F.silu(y)
+    y.backward(dy.double().permute(0, 2, 1))
+    want = xr.grad.permute(0, 2, 1)
+    tol = 5e-3 if dtype == torch.bfloat16 else 2e-5
+    assert rel_l2(dx0.t.float().reshape(N, P, C0), want[..., :C0]) < tol
+    if C1:
+        assert rel_l2(dx1.t.float().reshape(N, P, C1), want[..., C0:]) < tol
+    ptol = 2e-3 if dtype == torch.bfloat16 else 2e-5
+    assert rel_l2(dgam, gr.grad) < ptol and rel_l2(dbet, br.grad) < ptol
+
+
+@pytest.mark.parametrize("N,L,cin,cout,k", [(2, 200, 128, 192, 5), (3, 508, 256, 256, 5), (2, 100, 64, 128, 1)])
+def test_conv1d_input_grad_matches_autograd(N, L, cin, cout, k):
+    """dX of a stride-1 'same' conv1d = the forward tcgen05 implicit GEMM over dY with tap-flipped, transposed weights
+    (tqdne_b200.backward.conv1d_input_grad), with and without accumulation into an existing gradient."""
+    from tqdne_b200.backward import conv1d_input_grad
+
+    dtype = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(L + k)
+    w = _rt(torch.randn(cout, cin, k, device="cuda", generator=g) / math.sqrt(cin * k), dtype)
+    dy = _rt(torch.randn(N, cout, L, device="cuda", generator=g), dtype)
+    prev = _rt(torch.randn(N, cin, L, device="cuda", generator=g), dtype)
+    plan = _plan(dtype)
+    dx = conv1d_input_grad(plan, w, _act(dy, dtype))
+    dx_acc = conv1d_input_grad(plan, w, _act(dy, dtype), accumulate_into=_act(prev, dtype))
+    plan.run()
+    torch.cuda.synchronize()
+    x = torch.zeros(N, cin, L, device="cuda", dtype=torch.float64, requires_grad=True)
+    F.conv1d(x, w.double(), padding=k // 2).backward(dy.double())
+    assert rel_l2(_to_nchw(dx, 1), x.grad) < 4e-3
+    assert rel_l2(_to_nchw(dx_acc, 1), x.grad + prev) < 4e-3

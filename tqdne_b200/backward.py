@@ -1,0 +1,82 @@
+"""Backward kernels of the training-step row -- groundwork, not yet a training step.
+
+What autograd computes for the layers of the 1D EDM UNet (`LightningEDM.step`, tqdne/edm.py:115-134, config 5 of
+BASELINE.json) expressed on the engine's kernels, channels-last bf16 activations / gradients, fp32 parameter gradients:
+
+  * `conv1d_input_grad`  -- dX of a stride-1 "same" convolution IS a convolution of dY with the tap-flipped,
+    in/out-transposed weights: the forward tcgen05 implicit GEMM (`tq_plan_add_conv`) runs it unchanged, including the
+    epilogue add that accumulates the gradient of a tensor with two consumers;
+  * `conv1d_weight_grad` -- `tq_conv1d_wgrad` (tcgen05, K = positions, MN-major operands, taps by descriptor row offset);
+  * `groupnorm_silu_backward` -- `tq_gn_silu_backward` (two streaming passes: group reductions, then dX / dgamma / dbeta).
+
+The optimiser, the loss, attention / resampling backward and the graph walker that strings these together are the
+remaining work of that row.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .engine import Act, Plan, current_stream_ptr, pack_conv, require_cuda
+
+
+def conv1d_input_grad(plan: Plan, weight: torch.Tensor, dy: Act, *, accumulate_into: Act | None = None) -> Act:
+    """Append dX = conv(dY, flip(W)^T) to `plan`.  weight: [cout, cin, k] (the forward layer's), dy: [N, 1, L, cout_pad].
+    `accumulate_into`: a gradient already written by another consumer of X; it is added in the epilogue."""
+    w = weight.detach()
+    assert w.dim() == 3 and w.shape[2] % 2 == 1, "stride-1 'same' 1-D convolutions only"
+    wt = w.permute(1, 0, 2).flip(-1).contiguous()           # [cin, cout, k]
+    pc = pack_conv(wt, None, [w.shape[0]], plan.act_dtype)
+    return plan.conv(pc, [dy], dims=1, residual=accumulate_into)
+
+
+def conv1d_weight_grad(x: torch.Tensor, dy: torch.Tensor, taps: int, dw: torch.Tensor | None = None,
+                       db: torch.Tensor | None = None):
+    """x: [N, L, cin] bf16, dy: [N, L, cout] bf16 (channels-last, channel counts multiples of 64) ->
+    dw [cout, taps, cin] fp32 (+= if given), db [cout] fp32 (+= if given).  Reference layout: dw.permute(0, 2, 1)."""
+    require_cuda(x, "x")
+    N, L, cin = x.shape
+    cout = dy.shape[2]
+    assert dy.shape[:2] == (N, L) and x.dtype == dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+    if dw is None:
+        dw = torch.zeros(cout, taps, cin, device=x.device, dtype=torch.float32)
+    if db is None:
+        db = torch.zeros(cout, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().tq_conv1d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), N, L, cin, cout, taps,
+                                          current_stream_ptr()), "conv1d_wgrad")
+    return dw, db
+
+
+def groupnorm_silu_backward(x0: Act, dy: Act, gamma: torch.Tensor, beta: torch.Tensor, *, silu: bool = True, x1: Act | None = None,
+                            eps: float = 1e-5, dgamma: torch.Tensor | None = None, dbeta: torch.Tensor | None = None):
+    """dX (one tensor per source), dgamma, dbeta of y = [SiLU](GroupNorm32(cat[x0, x1])).  x0 / x1 carry the forward
+    per-(sample, channel) statistics (`Act.stats`, written by the producing conv's epilogue)."""
+    from .engine import tq_dtype
+
+    assert x0.stats is not None and (x1 is None or x1.stats is not None), "forward statistics missing"
+    N, P = x0.N, x0.H * x0.W
+    C0, C1 = x0.C, (x1.C if x1 is not None else 0)
+    Ct = C0 + C1
+    assert dy.C == Ct and dy.N == N and dy.H * dy.W == P
+    dev = x0.t.device
+    dx0 = torch.empty_like(x0.t)
+    dx1 = torch.empty_like(x1.t) if x1 is not None else None
+    dgamma = torch.zeros(Ct, device=dev, dtype=torch.float32) if dgamma is None else dgamma
+    dbeta = torch.zeros(Ct, device=dev, dtype=torch.float32) if dbeta is None else dbeta
+    ws = torch.empty(N * Ct * 2, device=dev, dtype=torch.float32)
+    g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+    d = _lib.TqGnBwdDesc()
+    d.dtype = tq_dtype(x0.t.dtype)
+    d.N, d.P, d.C0, d.C1 = N, P, C0, C1
+    d.x0, d.x1, d.dy = x0.t.data_ptr(), (x1.t.data_ptr() if x1 is not None else None), dy.t.data_ptr()
+    d.gamma, d.beta, d.eps, d.silu = g32.data_ptr(), b32.data_ptr(), eps, 1 if silu else 0
+    d.stats0, d.stats1 = x0.stats.data_ptr(), (x1.stats.data_ptr() if x1 is not None else None)
+    d.ws, d.dx0, d.dx1 = ws.data_ptr(), dx0.data_ptr(), (dx1.data_ptr() if dx1 is not None else None)
+    d.dgamma, d.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
+    _lib.check(_lib.lib().tq_gn_silu_backward(C.byref(d), current_stream_ptr()), "gn_silu_backward")
+    out0 = Act(dx0, N, x0.H, x0.W, C0)
+    out1 = Act(dx1, N, x1.H, x1.W, C1) if x1 is not None else None
+    return out0, out1, dgamma, dbeta

@@ -1,0 +1,277 @@
+// tq_norm_bwd.cu -- backward of GroupNorm(32 groups) [+ SiLU] over a virtual channel concat, channels-last.
+// Training-step row.  Reference: autograd through GroupNorm32 / nn.SiLU (tqdne/nn.py:11-13,90-105,
+// tqdne/unet.py:85-88,100-103) inside LightningEDM.step (tqdne/edm.py:115-134).
+//
+//   forward   xh = (x - mu_g) rstd_g,  v = xh gamma_c + beta_c,  y = v sigmoid(v)   (or y = v without SiLU)
+//   backward  dv = dy * s (1 + v (1 - s)), s = sigmoid(v)
+//             dbeta_c  = sum_{n,p} dv            dgamma_c = sum_{n,p} dv xh
+//             dx = rstd_g ( gamma_c dv - M1_{n,g} - xh M2_{n,g} ),
+//                  M1 = mean over the group of gamma_c dv,  M2 = mean over the group of gamma_c dv xh
+//
+// HBM-bound, two streaming passes over (x, dy): pass 1 leaves A[n][c] = sum_p dv and B[n][c] = sum_p dv xh in a
+// scratch buffer laid out like the forward statistics; pass 2 forms M1 / M2 from them and writes dx (10 B per element in
+// bf16).  mu / rstd come from the per-(sample, channel) sums the FORWARD conv epilogue left behind (tq_conv_desc.stats).
+#include <cuda_bf16.h>
+
+#include "tq_common.h"
+
+namespace tq {
+namespace {
+
+struct GnBwdParams {
+    const void* x0; const void* x1; const void* dy;
+    void* dx0; void* dx1;
+    int N, P, C0, C1;
+    const float* gamma; const float* beta;
+    float eps; int silu;
+    const float* st0; const float* st1;   // forward sums [N][C0][2], [N][C1][2]
+    float* ws;                            // [N][C0 + C1][2]: A, B
+    float* dgamma; float* dbeta;          // [C0 + C1], accumulated into
+    int chunks;
+};
+
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+            v[2 * k] = __low2float(b2);
+            v[2 * k + 1] = __high2float(b2);
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+            w[k] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ float sigmoid_f(float v) {
+    if constexpr (sizeof(T) == 4) return 1.f / (1.f + expf(-v));
+    else {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+        return fmaf(0.5f, t, 0.5f);
+    }
+}
+
+// group mean / rstd of sample n from the forward per-channel sums; 8 threads per group (256 threads, 32 groups)
+__device__ __forceinline__ void group_stats(const GnBwdParams& p, int n, int cpg, float* gstat) {
+    const float* s0 = p.st0 + (long long)n * p.C0 * 2;
+    const float* s1 = p.st1 ? p.st1 + (long long)n * p.C1 * 2 : nullptr;
+    const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    float s = 0.f, ss = 0.f;
+    for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
+        const float2 q = __ldcg(reinterpret_cast<const float2*>(c < p.C0 ? s0 + 2 * c : s1 + 2 * (c - p.C0)));
+        s += q.x;
+        ss += q.y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (sub == 0) {
+        const float inv = 1.f / ((float)cpg * (float)p.P);
+        const float mean = s * inv;
+        float var = ss * inv - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        gstat[2 * g] = mean;
+        gstat[2 * g + 1] = 1.f / sqrtf(var + p.eps);
+    }
+}
+
+// the thread's 8-channel vector of the concatenated tensor: pointers into the right source
+template <typename T>
+struct VecSrc {
+    const T* x; T* dx; int C; int c_local;
+};
+template <typename T>
+__device__ __forceinline__ VecSrc<T> pick_src(const GnBwdParams& p, int n, int c0) {
+    VecSrc<T> s;
+    if (c0 < p.C0) {
+        s.C = p.C0; s.c_local = c0;
+        s.x = static_cast<const T*>(p.x0) + (long long)n * p.P * p.C0 + c0;
+        s.dx = p.dx0 ? static_cast<T*>(p.dx0) + (long long)n * p.P * p.C0 + c0 : nullptr;
+    } else {
+        s.C = p.C1; s.c_local = c0 - p.C0;
+        s.x = static_cast<const T*>(p.x1) + (long long)n * p.P * p.C1 + s.c_local;
+        s.dx = p.dx1 ? static_cast<T*>(p.dx1) + (long long)n * p.P * p.C1 + s.c_local : nullptr;
+    }
+    return s;
+}
+
+template <typename T, int PASS>
+__global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
+    __shared__ float gstat[64];   // mean, rstd per group
+    __shared__ float gm[64];      // pass 2: M1, M2 per group
+    __shared__ float red[256 * 17];
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int Ct = p.C0 + p.C1, cpg = Ct / 32;
+    const int cv = Ct >> 3, lanes = 256 / cv;
+    const int vi = threadIdx.x % cv, pl = threadIdx.x / cv;
+    const bool on = pl < lanes;
+    const int c0 = vi * 8;
+    group_stats(p, n, cpg, gstat);
+    if constexpr (PASS == 2) {
+        // M1_g = sum_{c in g} gamma_c A_c / m, M2_g = sum_{c in g} gamma_c B_c / m
+        const float* ws = p.ws + (long long)n * Ct * 2;
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+        float m1 = 0.f, m2 = 0.f;
+        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
+            const float2 q = __ldcg(reinterpret_cast<const float2*>(ws + 2 * c));
+            const float gmm = __ldg(p.gamma + c);
+            m1 = fmaf(gmm, q.x, m1);
+            m2 = fmaf(gmm, q.y, m2);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+        }
+        if (sub == 0) {
+            const float inv = 1.f / ((float)cpg * (float)p.P);
+            gm[2 * g] = m1 * inv;
+            gm[2 * g + 1] = m2 * inv;
+        }
+    }
+    __syncthreads();
+    float ga[8], be[8], mu[8], rs[8], M1[8] = {}, M2[8] = {};
+    if (on) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c0 + j) / cpg;
+            ga[j] = __ldg(p.gamma + c0 + j);
+            be[j] = __ldg(p.beta + c0 + j);
+            mu[j] = gstat[2 * g];
+            rs[j] = gstat[2 * g + 1];
+            if constexpr (PASS == 2) {
+                M1[j] = gm[2 * g];
+                M2[j] = gm[2 * g + 1];
+            }
+        }
+    }
+    const int per = (p.P + p.chunks - 1) / p.chunks;
+    const int p0 = chunk * per, p1 = min(p.P, p0 + per);
+    float A[8] = {}, B[8] = {};
+    if (on) {
+        const VecSrc<T> s = pick_src<T>(p, n, c0);
+        const T* dyb = static_cast<const T*>(p.dy) + (long long)n * p.P * Ct + c0;
+        for (int pix = p0 + pl; pix < p1; pix += lanes) {
+            float xv[8], dv[8];
+            Vec8<T>::load(s.x + (long long)pix * s.C, xv);
+            Vec8<T>::load(dyb + (long long)pix * Ct, dv);
+            float out[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (xv[j] - mu[j]) * rs[j];
+                float d = dv[j];
+                if (p.silu) {
+                    const float v = fmaf(xh, ga[j], be[j]);
+                    const float sg = sigmoid_f<T>(v);
+                    d *= sg * fmaf(v, 1.f - sg, 1.f);
+                }
+                if constexpr (PASS == 1) {
+                    A[j] += d;
+                    B[j] = fmaf(d, xh, B[j]);
+                } else {
+                    out[j] = rs[j] * (fmaf(ga[j], d, -M1[j]) - xh * M2[j]);
+                }
+            }
+            if constexpr (PASS == 2) Vec8<T>::store(s.dx + (long long)pix * s.C, out);
+        }
+    }
+    if constexpr (PASS == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[threadIdx.x * 17 + j] = A[j];
+            red[threadIdx.x * 17 + 8 + j] = B[j];
+        }
+        __syncthreads();
+        float* ws = p.ws + (long long)n * Ct * 2;
+        for (int o = threadIdx.x; o < cv * 16; o += 256) {
+            const int vi2 = o >> 4, j = o & 15;
+            float a = 0.f;
+            for (int l = 0; l < lanes; ++l) a += red[(l * cv + vi2) * 17 + j];
+            atomicAdd(ws + 2 * (vi2 * 8 + (j & 7)) + (j >> 3), a);
+        }
+    }
+}
+
+// dgamma_c += sum_n B[n][c], dbeta_c += sum_n A[n][c]
+__global__ void __launch_bounds__(256) gn_bwd_param_kernel(const float* __restrict__ ws, int N, int Ct, float* dgamma, float* dbeta) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= Ct) return;
+    float a = 0.f, b = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const float2 q = __ldg(reinterpret_cast<const float2*>(ws + ((long long)n * Ct + c) * 2));
+        a += q.x;
+        b += q.y;
+    }
+    if (dbeta) dbeta[c] += a;
+    if (dgamma) dgamma[c] += b;
+}
+
+}  // namespace
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream) {
+    TQ_CHECK(d != nullptr, "gn_silu_backward: null descriptor");
+    TQ_CHECK(d->dtype == TQ_BF16 || d->dtype == TQ_F32, "gn_silu_backward: bad dtype");
+    const int Ct = d->C0 + d->C1;
+    TQ_CHECK(d->C0 > 0 && d->C0 % 8 == 0 && d->C1 >= 0 && d->C1 % 8 == 0 && Ct % 32 == 0 && Ct <= 2048,
+             "gn_silu_backward: channel counts must be multiples of 8, their sum a multiple of 32 and <= 2048");
+    TQ_CHECK(d->x0 && d->dy && d->gamma && d->beta && d->stats0 && d->ws && d->dx0, "gn_silu_backward: null pointer");
+    TQ_CHECK(d->C1 == 0 || (d->x1 && d->stats1 && d->dx1), "gn_silu_backward: second source incomplete");
+    TQ_CHECK(d->N > 0 && d->P > 0, "gn_silu_backward: empty tensor");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GnBwdParams p;
+    p.x0 = d->x0; p.x1 = d->x1; p.dy = d->dy; p.dx0 = d->dx0; p.dx1 = d->dx1;
+    p.N = d->N; p.P = d->P; p.C0 = d->C0; p.C1 = d->C1; p.gamma = d->gamma; p.beta = d->beta; p.eps = d->eps;
+    p.silu = d->silu; p.st0 = d->stats0; p.st1 = d->C1 > 0 ? d->stats1 : nullptr; p.ws = d->ws;
+    p.dgamma = d->dgamma; p.dbeta = d->dbeta;
+    const int slots = device_sm_count() * 4;
+    const int max_chunks = (d->P + 31) / 32;
+    int chunks = slots / d->N;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    p.chunks = chunks;
+    TQ_CUDA(cudaMemsetAsync(d->ws, 0, (size_t)d->N * Ct * 2 * sizeof(float), st));
+    const dim3 grid(chunks, d->N);
+    if (d->dtype == TQ_F32) {
+        gn_bwd_kernel<float, 1><<<grid, 256, 0, st>>>(p);
+        gn_bwd_kernel<float, 2><<<grid, 256, 0, st>>>(p);
+    } else {
+        gn_bwd_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(p);
+        gn_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(p);
+    }
+    TQ_CUDA(cudaGetLastError());
+    if (d->dgamma || d->dbeta) {
+        gn_bwd_param_kernel<<<(Ct + 255) / 256, 256, 0, st>>>(d->ws, d->N, Ct, d->dgamma, d->dbeta);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    count_launch(2);
+    return 0;
+}
