@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 5
+#define TQ_ABI_VERSION 6
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -170,6 +170,9 @@ int tq_plan_add_spatial_mean(tq_plan* p, const float* x, int32_t N, int32_t P, i
  * cin and cout must be multiples of 64, taps odd and <= 7.                                          */
 int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* db, int32_t N, int64_t L, int32_t cin,
                     int32_t cout, int32_t taps, void* stream);
+/* out[n][c] += sum_p dy[n][p][c] (dy bf16 [N,P,C], out fp32 [N,C]): gradient of the per-sample embedding
+ * term a ResBlock adds after its first convolution (tqdne/unet.py:129-141).                          */
+int tq_sample_channel_sums(const void* dy, float* out, int32_t N, int64_t P, int32_t C, void* stream);
 
 /* ---- GroupNorm(32) [+ SiLU] backward (training-step row) --------------------- *
  * Replaces: autograd through GroupNorm32 + nn.SiLU (tqdne/nn.py:11-13,90-105, tqdne/unet.py:85-88,100-103).

@@ -651,3 +651,64 @@ def test_conv1d_input_grad_matches_autograd(N, L, cin, cout, k):
     F.conv1d(x, w.double(), padding=k // 2).backward(dy.double())
     assert rel_l2(_to_nchw(dx, 1), x.grad) < 4e-3
     assert rel_l2(_to_nchw(dx_acc, 1), x.grad + prev) < 4e-3
+
+
+@pytest.mark.parametrize("N,L,C", [(3, 508, 128), (2, 1016, 256)])
+def test_resblock1d_forward_backward_matches_autograd(N, L, C):
+    """One 1D UNet ResBlock (tqdne/unet.py:42-143, identity skip, k = 5, embedding add) forward through the plan kernels
+    and backward through tqdne_b200.backward -- input gradient, both convolutions' weight / bias gradients, both
+    GroupNorm affine gradients and the embedding gradient -- against autograd on the fp32 reference block (bf16 mode)."""
+    from tqdne_b200 import backward as bw
+    from tqdne_b200.engine import Act, pack_conv
+
+    dt = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(C + L)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    w0 = _rt(rn(C, 64, 1) / 8, dt)          # stem 1x1 conv: produces x WITH epilogue statistics
+    u = _rt(rn(N, 64, L), dt)
+    w1, b1 = _rt(rn(C, C, 5) / math.sqrt(5 * C), dt), 0.1 * rn(C)
+    w2, b2 = _rt(rn(C, C, 5) / math.sqrt(5 * C), dt), 0.1 * rn(C)
+    g1, be1, g2, be2 = 1 + 0.1 * rn(C), 0.1 * rn(C), 1 + 0.1 * rn(C), 0.1 * rn(C)
+    e = 0.5 * rn(N, C)
+    dout = _rt(rn(N, C, L), dt)
+
+    # ---- forward on the engine
+    plan = _plan(dt)
+    x = plan.conv(pack_conv(w0, None, [64], dt), [_act(u, dt)], dims=1, stats=True)
+    h0 = plan.groupnorm([x], g1, be1, silu=True)
+    h1 = plan.conv(pack_conv(w1, b1, [C], dt), [h0], emb=e.contiguous(), emb_ld=C, dims=1, stats=True)
+    h2 = plan.groupnorm([h1], g2, be2, silu=True)
+    out = plan.conv(pack_conv(w2, b2, [C], dt), [h2], residual=x, dims=1)
+    plan.run()
+    # ---- backward on the engine
+    d_out = _act(dout, dt)
+    p1 = _plan(dt)
+    dh2 = bw.conv1d_input_grad(p1, w2, d_out)
+    p1.run()
+    as3 = lambda a: a.t.reshape(a.N, a.W, a.C)  # noqa: E731
+    dw2, db2 = bw.conv1d_weight_grad(as3(h2), as3(d_out), 5)
+    dh1, _, dg2, dbe2 = bw.groupnorm_silu_backward(h1, dh2, g2, be2)
+    de = bw.sample_channel_sums(dh1)
+    p2 = _plan(dt)
+    dh0 = bw.conv1d_input_grad(p2, w1, dh1)
+    p2.run()
+    dw1, db1 = bw.conv1d_weight_grad(as3(h0), as3(dh1), 5)
+    dx_main, _, dg1, dbe1 = bw.groupnorm_silu_backward(x, dh0, g1, be1)
+    torch.cuda.synchronize()
+    dx = _to_nchw(dx_main, 1) + dout                      # identity skip: the two gradient paths of x add
+
+    # ---- fp32 reference block under autograd, fed with the engine's (rounded) block input
+    xr = _to_nchw(x, 1).double().requires_grad_(True)
+    P = [t.double().clone().requires_grad_(True) for t in (w1, b1, w2, b2, g1, be1, g2, be2, e)]
+    rw1, rb1, rw2, rb2, rg1, rbe1, rg2, rbe2, re_ = P
+    hh = F.conv1d(F.silu(F.group_norm(xr, 32, rg1, rbe1, eps=1e-5)), rw1, rb1, padding=2) + re_[..., None]
+    ref = xr + F.conv1d(F.silu(F.group_norm(hh, 32, rg2, rbe2, eps=1e-5)), rw2, rb2, padding=2)
+    ref.backward(dout.double())
+    assert rel_l2(_to_nchw(out, 1), ref.detach()) < 5e-3
+    tol = 2e-2   # gradients pass through two bf16 activations-gradient tensors and two recomputed SiLUs
+    assert rel_l2(dx, xr.grad) < tol
+    assert rel_l2(dw2.permute(0, 2, 1), rw2.grad) < tol and rel_l2(db2, rb2.grad) < tol
+    assert rel_l2(dw1.permute(0, 2, 1), rw1.grad) < tol and rel_l2(db1, rb1.grad) < tol
+    assert rel_l2(dg2, rg2.grad) < tol and rel_l2(dbe2, rbe2.grad) < tol
+    assert rel_l2(dg1, rg1.grad) < tol and rel_l2(dbe1, rbe1.grad) < tol
+    assert rel_l2(de, re_.grad) < tol

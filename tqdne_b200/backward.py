@@ -80,3 +80,13 @@ def groupnorm_silu_backward(x0: Act, dy: Act, gamma: torch.Tensor, beta: torch.T
     out0 = Act(dx0, N, x0.H, x0.W, C0)
     out1 = Act(dx1, N, x1.H, x1.W, C1) if x1 is not None else None
     return out0, out1, dgamma, dbeta
+
+
+def sample_channel_sums(dy: Act, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[N, C] fp32 sums of dy over the positions of each sample (+= into `out`): gradient of the embedding term."""
+    if out is None:
+        out = torch.zeros(dy.N, dy.C, device=dy.t.device, dtype=torch.float32)
+    assert dy.t.dtype == torch.bfloat16
+    _lib.check(_lib.lib().tq_sample_channel_sums(dy.t.data_ptr(), out.data_ptr(), dy.N, dy.H * dy.W, dy.C, current_stream_ptr()),
+               "sample_channel_sums")
+    return out

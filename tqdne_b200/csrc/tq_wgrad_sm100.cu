@@ -190,6 +190,25 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __r
     if (rl == 0 && c < cout) atomicAdd(db + c, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 
+// out[n][c] += sum over the P positions of sample n of dy[n][p][c]: the gradient of a per-sample, per-channel additive
+// term (the timestep / conditioning embedding added after a ResBlock's first convolution, tqdne/unet.py:129-141)
+__global__ void __launch_bounds__(256) sample_channel_sum_kernel(const __nv_bfloat16* __restrict__ dy, int P, int C,
+                                                                 float* __restrict__ out) {
+    const int n = blockIdx.y;
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int rl = threadIdx.x >> 6;
+    float a = 0.f;
+    if (c < C) {
+        const __nv_bfloat16* b = dy + (long long)n * P * C + c;
+        for (int r = rl; r < P; r += 4) a += __bfloat162float(b[(long long)r * C]);
+    }
+    __shared__ float red[4][64];
+    red[rl][threadIdx.x & 63] = a;
+    __syncthreads();
+    if (rl == 0 && c < C)
+        out[(long long)n * C + c] += red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 wg_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (fn) return fn;
@@ -261,5 +280,14 @@ extern "C" int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* 
         TQ_CUDA(cudaGetLastError());
         count_launch();
     }
+    return 0;
+}
+
+extern "C" int tq_sample_channel_sums(const void* dy, float* out, int32_t N, int64_t P, int32_t C, void* stream) {
+    TQ_CHECK(dy && out && N > 0 && P > 0 && C > 0 && P < (1ll << 31), "sample_channel_sums: bad arguments");
+    sample_channel_sum_kernel<<<dim3((C + 63) / 64, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy), (int)P, C, out);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
