@@ -158,10 +158,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad1d_kernel(const __grid_con
                     tmem_ld_32x32(t_row + t * 64 + c, r);
                     tmem_ld_wait();
                     if (co < p.cout) {
+                        // cin is a multiple of 64: the 32 columns are in range and 16 B aligned -> 8 vector reductions
                         float* dst = p.dw + ((long long)co * p.taps + t) * p.cin + ci_t * 64 + c;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (ci_t * 64 + c + j < p.cin) atomicAdd(dst + j, __uint_as_float(r[j]));
+                        for (int j = 0; j < 32; j += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                                         "f"(__uint_as_float(r[j + 3]))
+                                         : "memory");
                     }
                 }
             }
@@ -257,7 +261,7 @@ extern "C" int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* 
     p.co_tiles = (cout + 127) / 128;
     p.ci_tiles = cin / 64;
     const int tiles = p.co_tiles * p.ci_tiles;
-    int kchunks = (2 * device_sm_count() + tiles - 1) / tiles;  // ~2 waves of CTAs: the K chunks even out the tail
+    int kchunks = device_sm_count() / tiles;  // one wave of CTAs: every extra K chunk adds a full tile of fp32 reductions
     if (kchunks > p.total_steps) kchunks = p.total_steps;
     if (kchunks < 1) kchunks = 1;
     p.steps_per_cta = (p.total_steps + kchunks - 1) / kchunks;
