@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 6
+#define TQ_ABI_VERSION 7
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -190,6 +190,14 @@ typedef struct {
     float* dgamma; float* dbeta;
 } tq_gn_bwd_desc;
 int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream);
+
+/* ---- attention core backward (training-step row) -------------------------------- *
+ * Replaces: autograd through QKVAttention.forward (tqdne/blocks.py:156-190).  Same layouts as tq_attn_desc:
+ * qkv [N,T,3*heads*d] (forward input), out [N,T,heads*d] (forward output), dout = gradient of out, all bf16;
+ * writes dqkv [N,T,3*heads*d] bf16.  ws: 2*N*heads*T floats of scratch (row log-sum-exp and D_i).
+ * tcgen05 kernels; head dim 64, 32 < T <= 512 (the 1D UNet's attention blocks).                          */
+int tq_attention_backward(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws, int32_t N,
+                          int32_t T, int32_t heads, int32_t d, void* stream);
 
 /* ---- sampler element-wise steps ------------------------------------------------------------------ *
  * Replaces: LightningEDM.forward pre/post scaling (tqdne/edm.py:105-113) and the Heun/Euler

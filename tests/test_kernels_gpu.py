@@ -712,3 +712,35 @@ def test_resblock1d_forward_backward_matches_autograd(N, L, C):
     assert rel_l2(dg2, rg2.grad) < tol and rel_l2(dbe2, rbe2.grad) < tol
     assert rel_l2(dg1, rg1.grad) < tol and rel_l2(dbe1, rbe1.grad) < tol
     assert rel_l2(de, re_.grad) < tol
+
+
+@pytest.mark.parametrize("N,T,heads", [(2, 508, 4), (3, 128, 2), (1, 300, 4), (2, 512, 1), (1, 77, 3)])
+def test_attention_backward_matches_autograd(N, T, heads):
+    """tq_attention_backward (two tcgen05 kernels: dQ + row statistics, then dK / dV with everything transposed) against
+    autograd through the reference formula (tqdne/blocks.py:156-190) on the same bf16-rounded tensors; ragged T
+    exercises the key / query masks of both kernels."""
+    from tqdne_b200.backward import attention_backward
+    from tqdne_b200.engine import Act
+
+    d, dt = 64, torch.bfloat16
+    C = heads * d
+    g = torch.Generator(device="cuda").manual_seed(T + heads)
+    qkv = _rt(torch.randn(N, T, 3 * C, device="cuda", generator=g), dt)
+    dout = _rt(torch.randn(N, T, C, device="cuda", generator=g), dt)
+    plan = _plan(dt)
+    qa = Act(qkv.to(dt).reshape(-1), N, 1, T, 3 * C)
+    out = plan.attention(qa, heads)
+    plan.run()
+    dqkv = attention_backward(qa, out, Act(dout.to(dt).reshape(-1), N, 1, T, C), heads)
+    torch.cuda.synchronize()
+    x = qkv.double().permute(0, 2, 1).clone().requires_grad_(True)   # [N, 3C, T] like the reference
+    q, k, v = x.chunk(3, dim=1)
+    s = 1 / math.sqrt(math.sqrt(d))
+    w = torch.einsum("bct,bcs->bts", (q * s).reshape(N * heads, d, T), (k * s).reshape(N * heads, d, T))
+    a = torch.einsum("bts,bcs->bct", torch.softmax(w, dim=-1), v.reshape(N * heads, d, T)).reshape(N, C, T)
+    a.backward(dout.double().permute(0, 2, 1))
+    want = x.grad.permute(0, 2, 1)                                    # [N, T, 3C]
+    got = dqkv.t.float().reshape(N, T, 3 * C)
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        err = rel_l2(got[..., sl], want[..., sl])
+        assert err < 1e-2, (name, err)

@@ -90,3 +90,16 @@ def sample_channel_sums(dy: Act, out: torch.Tensor | None = None) -> torch.Tenso
     _lib.check(_lib.lib().tq_sample_channel_sums(dy.t.data_ptr(), out.data_ptr(), dy.N, dy.H * dy.W, dy.C, current_stream_ptr()),
                "sample_channel_sums")
     return out
+
+
+def attention_backward(qkv: Act, out: Act, dout: Act, heads: int) -> Act:
+    """d(qkv) [N, T, 3C] of the attention core (QKVAttention.forward, blocks.py:156-190) from the forward's input / output
+    and the gradient of its output; bf16, head dim 64, 32 < T <= 512."""
+    N, T, C3 = qkv.N, qkv.H * qkv.W, qkv.C
+    Cc = C3 // 3
+    assert out.C == Cc and dout.C == Cc and qkv.t.dtype == torch.bfloat16
+    dqkv = torch.empty_like(qkv.t)
+    ws = torch.empty(2 * N * heads * T, device=qkv.t.device, dtype=torch.float32)
+    _lib.check(_lib.lib().tq_attention_backward(qkv.t.data_ptr(), out.t.data_ptr(), dout.t.data_ptr(), dqkv.data_ptr(),
+                                                ws.data_ptr(), N, T, heads, Cc // heads, current_stream_ptr()), "attention_backward")
+    return Act(dqkv, N, qkv.H, qkv.W, C3)
