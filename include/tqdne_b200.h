@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 7
+#define TQ_ABI_VERSION 8
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -167,12 +167,13 @@ int tq_plan_add_spatial_mean(tq_plan* p, const float* x, int32_t N, int32_t P, i
  *   dy : [N, L, cout] bf16 channels-last (gradient of the layer output)
  *   dw : [cout, taps, cin] fp32, db : [cout] fp32 or NULL -- ACCUMULATED INTO (zero them first):
  *        dw[co][t][ci] += sum_{n,l} dy[n][l][co] * x[n][l + t - taps/2][ci],  db[co] += sum_{n,l} dy[n][l][co]
- * cin and cout must be multiples of 64, taps odd and <= 7.                                          */
+ * cin and cout must be multiples of 64, taps odd and <= 7.  A layer whose input is a channel concat calls this once
+ * per source: dw_ld = input channels of the whole layer (0 = cin), ci_off = this source's first channel.   */
 int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* db, int32_t N, int64_t L, int32_t cin,
-                    int32_t cout, int32_t taps, void* stream);
-/* out[n][c] += sum_p dy[n][p][c] (dy bf16 [N,P,C], out fp32 [N,C]): gradient of the per-sample embedding
+                    int32_t cout, int32_t taps, int32_t dw_ld, int32_t ci_off, void* stream);
+/* out[n*out_ld + c] += sum_p dy[n][p][c] (dy bf16 [N,P,C], out fp32 rows of length out_ld, 0 = C): gradient of the per-sample embedding
  * term a ResBlock adds after its first convolution (tqdne/unet.py:129-141).                          */
-int tq_sample_channel_sums(const void* dy, float* out, int32_t N, int64_t P, int32_t C, void* stream);
+int tq_sample_channel_sums(const void* dy, float* out, int32_t out_ld, int32_t N, int64_t P, int32_t C, void* stream);
 
 /* ---- GroupNorm(32) [+ SiLU] backward (training-step row) --------------------- *
  * Replaces: autograd through GroupNorm32 + nn.SiLU (tqdne/nn.py:11-13,90-105, tqdne/unet.py:85-88,100-103).
@@ -188,6 +189,7 @@ typedef struct {
     float* ws;
     void* dx0; void* dx1;
     float* dgamma; float* dbeta;
+    const void* dx_add0; const void* dx_add1;   /* optional: gradient of x0 / x1 from their other consumer, added to dx */
 } tq_gn_bwd_desc;
 int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream);
 
@@ -198,6 +200,28 @@ int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream);
  * tcgen05 kernels; head dim 64, 32 < T <= 512 (the 1D UNet's attention blocks).                          */
 int tq_attention_backward(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws, int32_t N,
                           int32_t T, int32_t heads, int32_t d, void* stream);
+
+/* ---- small kernels of the training step ------------------------------------------ *
+ * tq_rows_op: rows of a channels-last bf16 tensor [N, L, C]; L_dst = rows of dst per sample.
+ *   mode 0 zero_stuff (dst[2j] = src[j], dst[2j+1] = 0: dY of a stride-2 conv on the stride-1 grid, blocks.py:93-101),
+ *   mode 1 nearest x2 upsample (blocks.py:59-65), mode 2 pair_sum (its gradient), mode 3 dst = src * aux (dropout mask),
+ *   mode 4 dst = src + aux (two gradient paths of one tensor).
+ * tq_linear_backward: v = act_in(x) W^T + b in fp32 (time / cond MLPs, emb_layers; unet.py:210-227,92):
+ *   dW += dy^T act_in(x), db += sum dy, dx = act_in'(x) * (dy W); act_in 0 none / 1 SiLU; dx, dW, db may be NULL.
+ * tq_edm_noise / tq_edm_loss: LightningEDM.step (edm.py:115-134): xn = y + sigma*noise, network input bf16(c_in xn)
+ *   with padded channels; loss = mean(w (c_out F + c_skip xn - y)^2) and dF (bf16, padded) = its gradient wrt F.
+ * tq_dropout_mask: 0 / 1/(1-p) scale tensor (nn.Dropout, unet.py:100-108).
+ * tq_adam_ema_step: torch.optim.Adam defaults (edm.py:240-251) + EMA lerp (ema.py:24-28) over flat fp32 arrays.    */
+int tq_rows_op(const void* src, const void* aux, void* dst, int32_t mode, int64_t N, int64_t L_dst, int32_t C, void* stream);
+int tq_linear_backward(const float* dy, const float* x, const float* W, int32_t act_in, float* dx, float* dW, float* db, int32_t M,
+                       int32_t K, int32_t Nout, void* stream);
+int tq_edm_noise(const float* y, const float* noise, const float* sigma, float* xn, void* xin, int64_t N, int64_t P, int32_t C,
+                 int32_t Cpad, float sigma_data, void* stream);
+int tq_edm_loss(const float* F, int32_t Cf, const float* xn, const float* y, const float* sigma, void* dF, float* loss, int64_t N,
+                int64_t P, int32_t C, int32_t Cpad, float sigma_data, void* stream);
+int tq_dropout_mask(void* mask, int64_t n, uint64_t seed, float p, void* stream);
+int tq_adam_ema_step(float* param, const float* grad, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2,
+                     float eps, int64_t step, float ema_decay, float grad_scale, void* stream);
 
 /* ---- sampler element-wise steps ------------------------------------------------------------------ *
  * Replaces: LightningEDM.forward pre/post scaling (tqdne/edm.py:105-113) and the Heun/Euler

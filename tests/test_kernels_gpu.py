@@ -577,7 +577,7 @@ def test_conv1d_wgrad_matches_autograd(N, L, cin, cout, taps):
     dw = torch.zeros(cout, taps, cin, device="cuda")
     db = torch.zeros(cout, device="cuda")
     _lib.check(_lib.lib().tq_conv1d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), N, L, cin, cout, taps,
-                                          current_stream_ptr()), "conv1d_wgrad")
+                                          0, 0, current_stream_ptr()), "conv1d_wgrad")
     torch.cuda.synchronize()
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 7  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 8  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -92,7 +92,8 @@ class TqGnBwdDesc(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("N", C.c_int32), ("P", C.c_int32), ("C0", C.c_int32), ("C1", C.c_int32),
                 ("x0", C.c_void_p), ("x1", C.c_void_p), ("dy", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("eps", C.c_float), ("silu", C.c_int32), ("stats0", C.c_void_p), ("stats1", C.c_void_p), ("ws", C.c_void_p),
-                ("dx0", C.c_void_p), ("dx1", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+                ("dx0", C.c_void_p), ("dx1", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("dx_add0", C.c_void_p), ("dx_add1", C.c_void_p)]
 
 
 # name -> (restype, argtypes): every symbol include/tqdne_b200.h declares
@@ -118,8 +119,14 @@ SIGNATURES = {
     "tq_plan_add_spatial_mean": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     "tq_gn_silu_backward": (C.c_int, [C.POINTER(TqGnBwdDesc), _VP]),
     "tq_attention_backward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
-    "tq_sample_channel_sums": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _VP]),
-    "tq_conv1d_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _I32, _VP]),
+    "tq_sample_channel_sums": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _I32, _VP]),
+    "tq_conv1d_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "tq_rows_op": (C.c_int, [_VP, _VP, _VP, _I32, _I64, _I64, _I32, _VP]),
+    "tq_linear_backward": (C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
+    "tq_edm_noise": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _I32, _I32, _F, _VP]),
+    "tq_edm_loss": (C.c_int, [_VP, _I32, _VP, _VP, _VP, _VP, _VP, _I64, _I64, _I32, _I32, _F, _VP]),
+    "tq_dropout_mask": (C.c_int, [_VP, _I64, C.c_uint64, _F, _VP]),
+    "tq_adam_ema_step": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _I64, _F, _F, _VP]),
     "tq_edm_precondition": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _I32, _F, _VP]),
     "tq_edm_euler": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _F, _F, _F, _F, _F, _I32, _VP]),
     "tq_edm_heun": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _I32, _I64, _I32, _I32, _F, _F, _F, _F, _F, _I32, _VP]),

@@ -34,7 +34,7 @@ def conv1d_input_grad(plan: Plan, weight: torch.Tensor, dy: Act, *, accumulate_i
 
 
 def conv1d_weight_grad(x: torch.Tensor, dy: torch.Tensor, taps: int, dw: torch.Tensor | None = None,
-                       db: torch.Tensor | None = None):
+                       db: torch.Tensor | None = None, *, dw_ld: int = 0, ci_off: int = 0, bias: bool = True):
     """x: [N, L, cin] bf16, dy: [N, L, cout] bf16 (channels-last, channel counts multiples of 64) ->
     dw [cout, taps, cin] fp32 (+= if given), db [cout] fp32 (+= if given).  Reference layout: dw.permute(0, 2, 1)."""
     require_cuda(x, "x")
@@ -43,15 +43,16 @@ def conv1d_weight_grad(x: torch.Tensor, dy: torch.Tensor, taps: int, dw: torch.T
     assert dy.shape[:2] == (N, L) and x.dtype == dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
     if dw is None:
         dw = torch.zeros(cout, taps, cin, device=x.device, dtype=torch.float32)
-    if db is None:
+    if db is None and bias:
         db = torch.zeros(cout, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().tq_conv1d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), N, L, cin, cout, taps,
-                                          current_stream_ptr()), "conv1d_wgrad")
+    _lib.check(_lib.lib().tq_conv1d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr() if bias else None, N, L, cin,
+                                          cout, taps, dw_ld, ci_off, current_stream_ptr()), "conv1d_wgrad")
     return dw, db
 
 
 def groupnorm_silu_backward(x0: Act, dy: Act, gamma: torch.Tensor, beta: torch.Tensor, *, silu: bool = True, x1: Act | None = None,
-                            eps: float = 1e-5, dgamma: torch.Tensor | None = None, dbeta: torch.Tensor | None = None):
+                            eps: float = 1e-5, dgamma: torch.Tensor | None = None, dbeta: torch.Tensor | None = None,
+                            add0: Act | None = None, add1: Act | None = None):
     """dX (one tensor per source), dgamma, dbeta of y = [SiLU](GroupNorm32(cat[x0, x1])).  x0 / x1 carry the forward
     per-(sample, channel) statistics (`Act.stats`, written by the producing conv's epilogue)."""
     from .engine import tq_dtype
@@ -76,18 +77,20 @@ def groupnorm_silu_backward(x0: Act, dy: Act, gamma: torch.Tensor, beta: torch.T
     d.stats0, d.stats1 = x0.stats.data_ptr(), (x1.stats.data_ptr() if x1 is not None else None)
     d.ws, d.dx0, d.dx1 = ws.data_ptr(), dx0.data_ptr(), (dx1.data_ptr() if dx1 is not None else None)
     d.dgamma, d.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
+    d.dx_add0 = add0.t.data_ptr() if add0 is not None else None
+    d.dx_add1 = add1.t.data_ptr() if add1 is not None else None
     _lib.check(_lib.lib().tq_gn_silu_backward(C.byref(d), current_stream_ptr()), "gn_silu_backward")
     out0 = Act(dx0, N, x0.H, x0.W, C0)
     out1 = Act(dx1, N, x1.H, x1.W, C1) if x1 is not None else None
     return out0, out1, dgamma, dbeta
 
 
-def sample_channel_sums(dy: Act, out: torch.Tensor | None = None) -> torch.Tensor:
+def sample_channel_sums(dy: Act, out: torch.Tensor | None = None, out_ld: int = 0) -> torch.Tensor:
     """[N, C] fp32 sums of dy over the positions of each sample (+= into `out`): gradient of the embedding term."""
     if out is None:
         out = torch.zeros(dy.N, dy.C, device=dy.t.device, dtype=torch.float32)
     assert dy.t.dtype == torch.bfloat16
-    _lib.check(_lib.lib().tq_sample_channel_sums(dy.t.data_ptr(), out.data_ptr(), dy.N, dy.H * dy.W, dy.C, current_stream_ptr()),
+    _lib.check(_lib.lib().tq_sample_channel_sums(dy.t.data_ptr(), out.data_ptr(), out_ld, dy.N, dy.H * dy.W, dy.C, current_stream_ptr()),
                "sample_channel_sums")
     return out
 

@@ -21,6 +21,7 @@ namespace {
 struct GnBwdParams {
     const void* x0; const void* x1; const void* dy;
     void* dx0; void* dx1;
+    const void* add0; const void* add1;   // optional second gradient path of x0 / x1, added to dx
     int N, P, C0, C1;
     const float* gamma; const float* beta;
     float eps; int silu;
@@ -103,7 +104,7 @@ __device__ __forceinline__ void group_stats(const GnBwdParams& p, int n, int cpg
 // the thread's 8-channel vector of the concatenated tensor: pointers into the right source
 template <typename T>
 struct VecSrc {
-    const T* x; T* dx; int C; int c_local;
+    const T* x; T* dx; const T* add; int C; int c_local;
 };
 template <typename T>
 __device__ __forceinline__ VecSrc<T> pick_src(const GnBwdParams& p, int n, int c0) {
@@ -112,10 +113,12 @@ __device__ __forceinline__ VecSrc<T> pick_src(const GnBwdParams& p, int n, int c
         s.C = p.C0; s.c_local = c0;
         s.x = static_cast<const T*>(p.x0) + (long long)n * p.P * p.C0 + c0;
         s.dx = p.dx0 ? static_cast<T*>(p.dx0) + (long long)n * p.P * p.C0 + c0 : nullptr;
+        s.add = p.add0 ? static_cast<const T*>(p.add0) + (long long)n * p.P * p.C0 + c0 : nullptr;
     } else {
         s.C = p.C1; s.c_local = c0 - p.C0;
         s.x = static_cast<const T*>(p.x1) + (long long)n * p.P * p.C1 + s.c_local;
         s.dx = p.dx1 ? static_cast<T*>(p.dx1) + (long long)n * p.P * p.C1 + s.c_local : nullptr;
+        s.add = p.add1 ? static_cast<const T*>(p.add1) + (long long)n * p.P * p.C1 + s.c_local : nullptr;
     }
     return s;
 }
@@ -197,7 +200,15 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
                     out[j] = rs[j] * (fmaf(ga[j], d, -M1[j]) - xh * M2[j]);
                 }
             }
-            if constexpr (PASS == 2) Vec8<T>::store(s.dx + (long long)pix * s.C, out);
+            if constexpr (PASS == 2) {
+                if (s.add) {
+                    float ad[8];
+                    Vec8<T>::load(s.add + (long long)pix * s.C, ad);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) out[j] += ad[j];
+                }
+                Vec8<T>::store(s.dx + (long long)pix * s.C, out);
+            }
         }
     }
     if constexpr (PASS == 1) {
@@ -247,7 +258,7 @@ extern "C" int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream) {
     TQ_CHECK(d->N > 0 && d->P > 0, "gn_silu_backward: empty tensor");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GnBwdParams p;
-    p.x0 = d->x0; p.x1 = d->x1; p.dy = d->dy; p.dx0 = d->dx0; p.dx1 = d->dx1;
+    p.x0 = d->x0; p.x1 = d->x1; p.dy = d->dy; p.dx0 = d->dx0; p.dx1 = d->dx1; p.add0 = d->dx_add0; p.add1 = d->dx_add1;
     p.N = d->N; p.P = d->P; p.C0 = d->C0; p.C1 = d->C1; p.gamma = d->gamma; p.beta = d->beta; p.eps = d->eps;
     p.silu = d->silu; p.st0 = d->stats0; p.st1 = d->C1 > 0 ? d->stats1 : nullptr; p.ws = d->ws;
     p.dgamma = d->dgamma; p.dbeta = d->dbeta;

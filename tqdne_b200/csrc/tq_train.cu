@@ -1,0 +1,267 @@
+// tq_train.cu -- the small kernels of the training step: resampling helpers of the strided /
+// upsampled convolution gradients, dense-layer backward of the embedding MLPs, EDM noising + loss, dropout, Adam + EMA.
+// Reference: LightningEDM.step / configure_optimizers (tqdne/edm.py:115-134,240-251), EMA (tqdne/ema.py:24-28),
+// Downsample / Upsample (tqdne/blocks.py:29-108), ResBlock dropout (tqdne/unet.py:100-108).  All HBM- or latency-bound.
+#include <cuda_bf16.h>
+
+#include "tq_common.h"
+
+namespace tq {
+namespace {
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        v[2 * k] = __low2float(b2);
+        v[2 * k + 1] = __high2float(b2);
+    }
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        w[k] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// rows of a channels-last bf16 tensor [N][L][C], 8 channels per thread; index space = destination vectors
+//   mode 0  zero_stuff   dst[n][2j] = src[n][j], dst[n][2j+1] = 0           (gradient of "take the even positions")
+//   mode 1  upsample     dst[n][l]  = src[n][l / 2]                         (F.interpolate(scale_factor=2, "nearest"))
+//   mode 2  pair_sum     dst[n][j]  = src[n][2j] + src[n][2j+1]             (its gradient)
+//   mode 3  mul          dst[n][l]  = src[n][l] * aux[n][l]                 (dropout mask, forward and backward)
+//   mode 4  add          dst[n][l]  = src[n][l] + aux[n][l]                 (two gradient paths of one tensor)
+__global__ void __launch_bounds__(256) rows_op_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ aux,
+                                                      __nv_bfloat16* __restrict__ dst, int mode, long long N, long long Ld, int C) {
+    const int cv = C >> 3;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N * Ld * cv) return;
+    const int vi = (int)(i % cv);
+    const long long r = i / cv, n = r / Ld, l = r % Ld;
+    float v[8] = {};
+    if (mode == 0) {
+        if ((l & 1) == 0) ld8(src + ((n * (Ld / 2) + l / 2) * C + vi * 8), v);
+    } else if (mode == 1) {
+        ld8(src + ((n * (Ld / 2) + l / 2) * C + vi * 8), v);
+    } else if (mode == 2) {
+        float a[8], b[8];
+        ld8(src + ((n * (2 * Ld) + 2 * l) * C + vi * 8), a);
+        ld8(src + ((n * (2 * Ld) + 2 * l + 1) * C + vi * 8), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = a[j] + b[j];
+    } else {
+        float a[8], b[8];
+        ld8(src + (r * C + vi * 8), a);
+        ld8(aux + (r * C + vi * 8), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = mode == 3 ? a[j] * b[j] : a[j] + b[j];
+    }
+    st8(dst + (r * C + vi * 8), v);
+}
+
+__device__ __forceinline__ float silu_d(float x) {
+    const float s = 1.f / (1.f + expf(-x));
+    return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float silu_v(float x) { return x / (1.f + expf(-x)); }
+
+// dense layer v = act(x) W^T + b, fp32 (time / conditioning MLPs, emb_layers): dW[j][k] += sum_m dy[m][j] act(x[m][k])
+__global__ void __launch_bounds__(256) linear_bwd_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x, int act_in,
+                                                            float* __restrict__ dW, float* __restrict__ db, int M, int K, int Nout) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)Nout * K) return;
+    const int j = (int)(i / K), k = (int)(i % K);
+    float a = 0.f, bsum = 0.f;
+    for (int m = 0; m < M; ++m) {
+        const float d = __ldg(dy + (long long)m * Nout + j);
+        float xv = __ldg(x + (long long)m * K + k);
+        if (act_in) xv = silu_v(xv);
+        a = fmaf(d, xv, a);
+        bsum += d;
+    }
+    dW[i] += a;
+    if (db && k == 0) db[j] += bsum;
+}
+// dx[m][k] = act'(x[m][k]) * sum_j dy[m][j] W[j][k]
+__global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ W, int act_in, float* __restrict__ dx, int M,
+                                                            int K, int Nout) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)M * K) return;
+    const int m = (int)(i / K), k = (int)(i % K);
+    float a = 0.f;
+    for (int j = 0; j < Nout; ++j) a = fmaf(__ldg(dy + (long long)m * Nout + j), __ldg(W + (long long)j * K + k), a);
+    if (act_in) a *= silu_d(x[i]);
+    dx[i] = a;
+}
+
+// EDM noising (edm.py:125-128): xn = y + sigma_n * noise; network input = bf16(c_in(sigma_n) * xn), channels padded
+__global__ void __launch_bounds__(256) edm_noise_kernel(const float* __restrict__ y, const float* __restrict__ noise,
+                                                        const float* __restrict__ sigma, float* __restrict__ xn,
+                                                        __nv_bfloat16* __restrict__ xin, long long P, int C, int Cpad, long long total,
+                                                        float sigma_data) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // over [N][P][Cpad]
+    if (i >= total) return;
+    const int c = (int)(i % Cpad);
+    const long long r = i / Cpad, n = r / P;
+    float v = 0.f;
+    if (c < C) {
+        const float s = sigma[n];
+        const float x = y[r * C + c] + s * noise[r * C + c];
+        xn[r * C + c] = x;
+        v = x * rsqrtf(s * s + sigma_data * sigma_data);
+    }
+    xin[i] = __float2bfloat16_rn(v);
+}
+// EDM loss (edm.py:105-113,129-134): pred = c_out F + c_skip xn; loss = mean(w (pred - y)^2), w = (s^2 + sd^2) / (s sd)^2;
+// dF = 2 w (pred - y) c_out / count, written as bf16 with the channels padded (the output conv's dY)
+__global__ void __launch_bounds__(256) edm_loss_kernel(const float* __restrict__ F, int Cf, const float* __restrict__ xn,
+                                                       const float* __restrict__ y, const float* __restrict__ sigma,
+                                                       __nv_bfloat16* __restrict__ dF, float* __restrict__ loss, long long P, int C,
+                                                       int Cpad, long long total, float sigma_data, float inv_count) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // over [N][P][Cpad]
+    float contrib = 0.f;
+    if (i < total) {
+        const int c = (int)(i % Cpad);
+        const long long r = i / Cpad, n = r / P;
+        float g = 0.f;
+        if (c < C) {
+            const float s = sigma[n], sd = sigma_data;
+            const float den = s * s + sd * sd;
+            const float c_out = s * sd * rsqrtf(den), c_skip = sd * sd / den, w = den / (s * sd * s * sd);
+            const float diff = c_out * F[r * Cf + c] + c_skip * xn[r * C + c] - y[r * C + c];
+            contrib = w * diff * diff * inv_count;
+            g = 2.f * w * diff * c_out * inv_count;
+        }
+        dF[i] = __float2bfloat16_rn(g);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = contrib;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k];
+        atomicAdd(loss, t);
+    }
+}
+
+// dropout scale tensor: 0 with probability p, else 1 / (1 - p); counter-based hash of (seed, element index)
+__global__ void __launch_bounds__(256) dropout_mask_kernel(__nv_bfloat16* __restrict__ mask, long long n, unsigned long long seed,
+                                                           float p) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);   // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(z >> 40) * (1.f / 16777216.f);
+    mask[i] = __float2bfloat16_rn(u < p ? 0.f : 1.f / (1.f - p));
+}
+
+// Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) + EMA lerp (ema.py:24-28), one pass over flat fp32 arrays
+__global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                                                       float* __restrict__ v, float* __restrict__ ema, long long n, float lr, float b1,
+                                                       float b2, float eps, float bc1, float bc2, float ema_w, float grad_scale) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float g = grad[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    // torch: param -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+    const float pnew = param[i] - (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+    param[i] = pnew;
+    if (ema) ema[i] += ema_w * (pnew - ema[i]);
+}
+
+inline unsigned grid_for(long long n) { return (unsigned)((n + 255) / 256); }
+
+}  // namespace
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" {
+
+int tq_rows_op(const void* src, const void* aux, void* dst, int32_t mode, int64_t N, int64_t L_dst, int32_t C, void* stream) {
+    TQ_CHECK(src && dst && mode >= 0 && mode <= 4 && N > 0 && L_dst > 0 && C > 0 && C % 8 == 0, "rows_op: bad arguments");
+    TQ_CHECK(mode < 3 || aux, "rows_op: mul / add need aux");
+    TQ_CHECK(mode >= 2 || L_dst % 2 == 0, "rows_op: destination length must be even");
+    rows_op_kernel<<<grid_for(N * L_dst * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src), static_cast<const __nv_bfloat16*>(aux), static_cast<__nv_bfloat16*>(dst), mode, N,
+        L_dst, C);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int tq_linear_backward(const float* dy, const float* x, const float* W, int32_t act_in, float* dx, float* dW, float* db, int32_t M,
+                       int32_t K, int32_t Nout, void* stream) {
+    TQ_CHECK(dy && x && W && M > 0 && K > 0 && Nout > 0, "linear_backward: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dW) {
+        linear_bwd_dw_kernel<<<grid_for((long long)Nout * K), 256, 0, st>>>(dy, x, act_in, dW, db, M, K, Nout);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    if (dx) {
+        linear_bwd_dx_kernel<<<grid_for((long long)M * K), 256, 0, st>>>(dy, x, W, act_in, dx, M, K, Nout);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    return 0;
+}
+
+int tq_edm_noise(const float* y, const float* noise, const float* sigma, float* xn, void* xin, int64_t N, int64_t P, int32_t C,
+                 int32_t Cpad, float sigma_data, void* stream) {
+    TQ_CHECK(y && noise && sigma && xn && xin && N > 0 && P > 0 && C > 0 && Cpad >= C, "edm_noise: bad arguments");
+    const long long total = N * P * Cpad;
+    edm_noise_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, noise, sigma, xn,
+                                                                                     static_cast<__nv_bfloat16*>(xin), P, C, Cpad,
+                                                                                     total, sigma_data);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int tq_edm_loss(const float* F, int32_t Cf, const float* xn, const float* y, const float* sigma, void* dF, float* loss, int64_t N,
+                int64_t P, int32_t C, int32_t Cpad, float sigma_data, void* stream) {
+    TQ_CHECK(F && xn && y && sigma && dF && loss && N > 0 && P > 0 && C > 0 && Cpad >= C && Cf >= C, "edm_loss: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    const long long total = N * P * Cpad;
+    edm_loss_kernel<<<grid_for(total), 256, 0, st>>>(F, Cf, xn, y, sigma, static_cast<__nv_bfloat16*>(dF), loss, P, C, Cpad, total,
+                                                    sigma_data, 1.f / (float)(N * P * C));
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int tq_dropout_mask(void* mask, int64_t n, uint64_t seed, float p, void* stream) {
+    TQ_CHECK(mask && n > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
+    dropout_mask_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(mask), n, seed, p);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int tq_adam_ema_step(float* param, const float* grad, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2,
+                     float eps, int64_t step, float ema_decay, float grad_scale, void* stream) {
+    TQ_CHECK(param && grad && m && v && n > 0 && step >= 1, "adam_ema_step: bad arguments");
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    adam_ema_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, m, v, ema, n, lr, beta1, beta2, eps, bc1,
+                                                                                 bc2, 1.f - ema_decay, grad_scale);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // extern "C"

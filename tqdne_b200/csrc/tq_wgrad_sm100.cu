@@ -37,6 +37,7 @@ struct WgradParams {
     float* dw;         // [Cout][taps][Cin]
     float* db;         // [Cout] or nullptr
     int N, L, cin, cout, taps, pad;
+    int dw_ld, ci_off;  // dW row length (input channels of the WHOLE layer) and this source's first channel in it
     int b_rows;        // rows of the X halo box
     int b_stage;       // bytes of the X halo buffer rounded up to 1024
     int steps_per_sample, total_steps, steps_per_cta, kchunks, co_tiles, ci_tiles;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad1d_kernel(const __grid_con
                     tmem_ld_wait();
                     if (co < p.cout) {
                         // cin is a multiple of 64: the 32 columns are in range and 16 B aligned -> 8 vector reductions
-                        float* dst = p.dw + ((long long)co * p.taps + t) * p.cin + ci_t * 64 + c;
+                        float* dst = p.dw + ((long long)co * p.taps + t) * p.dw_ld + p.ci_off + ci_t * 64 + c;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __r
 // out[n][c] += sum over the P positions of sample n of dy[n][p][c]: the gradient of a per-sample, per-channel additive
 // term (the timestep / conditioning embedding added after a ResBlock's first convolution, tqdne/unet.py:129-141)
 __global__ void __launch_bounds__(256) sample_channel_sum_kernel(const __nv_bfloat16* __restrict__ dy, int P, int C,
-                                                                 float* __restrict__ out) {
+                                                                 float* __restrict__ out, int out_ld) {
     const int n = blockIdx.y;
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
     const int rl = threadIdx.x >> 6;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) sample_channel_sum_kernel(const __nv_bflo
     red[rl][threadIdx.x & 63] = a;
     __syncthreads();
     if (rl == 0 && c < C)
-        out[(long long)n * C + c] += red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+        out[(long long)n * out_ld + c] += red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 wg_encode_fn() {
@@ -245,7 +246,9 @@ int encode_nlc(CUtensorMap* m, const void* ptr, int N, int L, int Cc, int box_ro
 using namespace tq;
 
 extern "C" int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* db, int32_t N, int64_t L, int32_t cin,
-                               int32_t cout, int32_t taps, void* stream) {
+                               int32_t cout, int32_t taps, int32_t dw_ld, int32_t ci_off, void* stream) {
+    if (dw_ld <= 0) dw_ld = cin;
+    TQ_CHECK(ci_off >= 0 && ci_off % 4 == 0 && ci_off + cin <= dw_ld && dw_ld % 4 == 0, "conv1d_wgrad: bad dw_ld / ci_off");
     TQ_CHECK(x && dy && dw && N > 0 && L > 0, "conv1d_wgrad: bad arguments");
     TQ_CHECK(taps >= 1 && taps <= MAX_TAPS && (taps & 1), "conv1d_wgrad: odd kernel sizes up to %d", MAX_TAPS);
     TQ_CHECK(cin % 64 == 0 && cout % 64 == 0, "conv1d_wgrad: channel counts must be multiples of 64 (pad the stem / head)");
@@ -253,7 +256,7 @@ extern "C" int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* 
     TQ_CHECK(L < (1ll << 30), "conv1d_wgrad: sequence too long");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     WgradParams p;
-    p.dw = dw; p.db = db; p.N = N; p.L = (int)L; p.cin = cin; p.cout = cout; p.taps = taps; p.pad = taps / 2;
+    p.dw = dw; p.db = db; p.N = N; p.L = (int)L; p.cin = cin; p.cout = cout; p.taps = taps; p.pad = taps / 2; p.dw_ld = dw_ld; p.ci_off = ci_off;
     p.b_rows = (KSTEP + taps - 1 + 7) / 8 * 8;
     p.b_stage = (p.b_rows * 128 + 1023) / 1024 * 1024;
     p.steps_per_sample = (int)((L + KSTEP - 1) / KSTEP);
@@ -287,10 +290,11 @@ extern "C" int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* 
     return 0;
 }
 
-extern "C" int tq_sample_channel_sums(const void* dy, float* out, int32_t N, int64_t P, int32_t C, void* stream) {
+extern "C" int tq_sample_channel_sums(const void* dy, float* out, int32_t out_ld, int32_t N, int64_t P, int32_t C, void* stream) {
+    if (out_ld <= 0) out_ld = C;
     TQ_CHECK(dy && out && N > 0 && P > 0 && C > 0 && P < (1ll << 31), "sample_channel_sums: bad arguments");
     sample_channel_sum_kernel<<<dim3((C + 63) / 64, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dy), (int)P, C, out);
+        static_cast<const __nv_bfloat16*>(dy), (int)P, C, out, out_ld);
     TQ_CUDA(cudaGetLastError());
     count_launch();
     return 0;
