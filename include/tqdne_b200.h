@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 8
+#define TQ_ABI_VERSION 9
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -190,6 +190,7 @@ typedef struct {
     void* dx0; void* dx1;
     float* dgamma; float* dbeta;
     const void* dx_add0; const void* dx_add1;   /* optional: gradient of x0 / x1 from their other consumer, added to dx */
+    float* dx_sum; int32_t dx_sum_ld;            /* optional: dx_sum[n*ld + c] += sum_p dx0[n][p][c] (embedding gradient) */
 } tq_gn_bwd_desc;
 int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream);
 

@@ -77,6 +77,7 @@ def groupnorm_silu_backward(x0: Act, dy: Act, gamma: torch.Tensor, beta: torch.T
     d.stats0, d.stats1 = x0.stats.data_ptr(), (x1.stats.data_ptr() if x1 is not None else None)
     d.ws, d.dx0, d.dx1 = ws.data_ptr(), dx0.data_ptr(), (dx1.data_ptr() if dx1 is not None else None)
     d.dgamma, d.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
+    d.dx_sum, d.dx_sum_ld = None, 0
     d.dx_add0 = add0.t.data_ptr() if add0 is not None else None
     d.dx_add1 = add1.t.data_ptr() if add1 is not None else None
     _lib.check(_lib.lib().tq_gn_silu_backward(C.byref(d), current_stream_ptr()), "gn_silu_backward")

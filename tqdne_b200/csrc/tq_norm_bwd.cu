@@ -28,6 +28,7 @@ struct GnBwdParams {
     const float* st0; const float* st1;   // forward sums [N][C0][2], [N][C1][2]
     float* ws;                            // [N][C0 + C1][2]: A, B
     float* dgamma; float* dbeta;          // [C0 + C1], accumulated into
+    float* dx_sum; int dx_sum_ld;         // optional: dx_sum[n * ld + c] += sum over positions of dx0 (embedding gradient)
     int chunks;
 };
 
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
     }
     const int per = (p.P + p.chunks - 1) / p.chunks;
     const int p0 = chunk * per, p1 = min(p.P, p0 + per);
-    float A[8] = {}, B[8] = {};
+    float A[8] = {}, B[8] = {}, S[8] = {};
     if (on) {
         const VecSrc<T> s = pick_src<T>(p, n, c0);
         const T* dyb = static_cast<const T*>(p.dy) + (long long)n * p.P * Ct + c0;
@@ -207,6 +208,8 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) out[j] += ad[j];
                 }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) S[j] += out[j];
                 Vec8<T>::store(s.dx + (long long)pix * s.C, out);
             }
         }
@@ -223,23 +226,25 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
             const int vi2 = o >> 4, j = o & 15;
             float a = 0.f;
             for (int l = 0; l < lanes; ++l) a += red[(l * cv + vi2) * 17 + j];
-            atomicAdd(ws + 2 * (vi2 * 8 + (j & 7)) + (j >> 3), a);
+            const int c = vi2 * 8 + (j & 7);
+            atomicAdd(ws + 2 * c + (j >> 3), a);
+            float* par = (j >> 3) ? p.dgamma : p.dbeta;   // dbeta_c = sum_n A, dgamma_c = sum_n B
+            if (par) atomicAdd(par + c, a);
+        }
+    } else if (p.dx_sum != nullptr) {
+        // per-sample channel sums of dx0 (first source only): same smem tree as pass 1
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 17 + j] = (on && c0 < p.C0) ? S[j] : 0.f;
+        __syncthreads();
+        for (int o = threadIdx.x; o < cv * 8; o += 256) {
+            const int vi2 = o >> 3, j = o & 7;
+            const int c = vi2 * 8 + j;
+            if (c >= p.C0) continue;
+            float a = 0.f;
+            for (int l = 0; l < lanes; ++l) a += red[(l * cv + vi2) * 17 + j];
+            atomicAdd(p.dx_sum + (long long)n * p.dx_sum_ld + c, a);
         }
     }
-}
-
-// dgamma_c += sum_n B[n][c], dbeta_c += sum_n A[n][c]
-__global__ void __launch_bounds__(256) gn_bwd_param_kernel(const float* __restrict__ ws, int N, int Ct, float* dgamma, float* dbeta) {
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c >= Ct) return;
-    float a = 0.f, b = 0.f;
-    for (int n = 0; n < N; ++n) {
-        const float2 q = __ldg(reinterpret_cast<const float2*>(ws + ((long long)n * Ct + c) * 2));
-        a += q.x;
-        b += q.y;
-    }
-    if (dbeta) dbeta[c] += a;
-    if (dgamma) dgamma[c] += b;
 }
 
 }  // namespace
@@ -261,7 +266,7 @@ extern "C" int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream) {
     p.x0 = d->x0; p.x1 = d->x1; p.dy = d->dy; p.dx0 = d->dx0; p.dx1 = d->dx1; p.add0 = d->dx_add0; p.add1 = d->dx_add1;
     p.N = d->N; p.P = d->P; p.C0 = d->C0; p.C1 = d->C1; p.gamma = d->gamma; p.beta = d->beta; p.eps = d->eps;
     p.silu = d->silu; p.st0 = d->stats0; p.st1 = d->C1 > 0 ? d->stats1 : nullptr; p.ws = d->ws;
-    p.dgamma = d->dgamma; p.dbeta = d->dbeta;
+    p.dgamma = d->dgamma; p.dbeta = d->dbeta; p.dx_sum = d->dx_sum; p.dx_sum_ld = d->dx_sum_ld > 0 ? d->dx_sum_ld : d->C0;
     const int slots = device_sm_count() * 4;
     const int max_chunks = (d->P + 31) / 32;
     int chunks = slots / d->N;
@@ -278,11 +283,6 @@ extern "C" int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream) {
         gn_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(p);
     }
     TQ_CUDA(cudaGetLastError());
-    if (d->dgamma || d->dbeta) {
-        gn_bwd_param_kernel<<<(Ct + 255) / 256, 256, 0, st>>>(d->ws, d->N, Ct, d->dgamma, d->dbeta);
-        TQ_CUDA(cudaGetLastError());
-        count_launch();
-    }
     count_launch(2);
     return 0;
 }

@@ -86,17 +86,24 @@ __global__ void __launch_bounds__(256) linear_bwd_dw_kernel(const float* __restr
     dW[i] += a;
     if (db && k == 0) db[j] += bsum;
 }
-// dx[m][k] = act'(x[m][k]) * sum_j dy[m][j] W[j][k]
-__global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                            const float* __restrict__ W, int act_in, float* __restrict__ dx, int M,
-                                                            int K, int Nout) {
+// dx[m][k] = act'(x[m][k]) * sum_j dy[m][j] W[j][k]: the j range is split over blocks (the emb_layers GEMM has ~4000 rows
+// against M*K = 16 K outputs) and accumulated with fp32 atomics into the zeroed dx; a second pass applies act'
+constexpr int LIN_JB = 64;
+__global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+                                                            float* __restrict__ dx, int M, int K, int Nout) {
+    const int m = blockIdx.y, j0 = blockIdx.x * LIN_JB, j1 = min(Nout, j0 + LIN_JB);
+    __shared__ float dys[LIN_JB];
+    for (int j = threadIdx.x; j < j1 - j0; j += 256) dys[j] = dy[(long long)m * Nout + j0 + j];
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += 256) {
+        float a = 0.f;
+        for (int j = j0; j < j1; ++j) a = fmaf(dys[j - j0], __ldg(W + (long long)j * K + k), a);
+        atomicAdd(dx + (long long)m * K + k, a);
+    }
+}
+__global__ void __launch_bounds__(256) silu_grad_scale_kernel(float* __restrict__ dx, const float* __restrict__ x, long long n) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= (long long)M * K) return;
-    const int m = (int)(i / K), k = (int)(i % K);
-    float a = 0.f;
-    for (int j = 0; j < Nout; ++j) a = fmaf(__ldg(dy + (long long)m * Nout + j), __ldg(W + (long long)j * K + k), a);
-    if (act_in) a *= silu_d(x[i]);
-    dx[i] = a;
+    if (i < n) dx[i] *= silu_d(x[i]);
 }
 
 // EDM noising (edm.py:125-128): xn = y + sigma_n * noise; network input = bf16(c_in(sigma_n) * xn), channels padded
@@ -213,9 +220,12 @@ int tq_linear_backward(const float* dy, const float* x, const float* W, int32_t 
         count_launch();
     }
     if (dx) {
-        linear_bwd_dx_kernel<<<grid_for((long long)M * K), 256, 0, st>>>(dy, x, W, act_in, dx, M, K, Nout);
+        TQ_CUDA(cudaMemsetAsync(dx, 0, (size_t)M * K * sizeof(float), st));
+        linear_bwd_dx_kernel<<<dim3((Nout + LIN_JB - 1) / LIN_JB, M), 256, 0, st>>>(dy, W, dx, M, K, Nout);
         TQ_CUDA(cudaGetLastError());
-        count_launch();
+        if (act_in) silu_grad_scale_kernel<<<grid_for((long long)M * K), 256, 0, st>>>(dx, x, (long long)M * K);
+        TQ_CUDA(cudaGetLastError());
+        count_launch(act_in ? 2 : 1);
     }
     return 0;
 }

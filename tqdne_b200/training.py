@@ -180,6 +180,7 @@ class TrainStep1D:
         mc = model.model_channels
         E = 4 * mc
         self.nodes: list = []
+        self.emb_of_act: dict = {}   # id(conv1 output) -> column offset of its ResBlock in e_all / de_all
         self.cin = model.in_channels
         self.cin_pad = _pad64(self.cin)
         # ---- step inputs
@@ -231,7 +232,8 @@ class TrainStep1D:
             self.nodes.append(("gn", gn1, srcs, h0, True))
             eo = self.emb_off[id(blk)]
             h1 = self._conv(conv1, [h0], [h0.C], emb=self.e_all[:, eo:], emb_ld=R, stats=True)
-            self.nodes.append(("conv", conv1, [h0], h1, dict(emb_off=eo)))
+            self.nodes.append(("conv", conv1, [h0], h1, {}))
+            self.emb_of_act[id(h1)] = eo
             h2 = self._gn(gn2, [h1], True)
             self.nodes.append(("gn", gn2, [h1], h2, True))
             if self.p_drop > 0:
@@ -326,11 +328,6 @@ class TrainStep1D:
                 O, I, k = mod.weight.shape
                 Op, Ip = _pad64(O), _pad64(I)
                 gw, gb = st.view(st.G, mod.weight), st.view(st.G, mod.bias)
-                if "emb_off" in extra:
-                    eo = extra["emb_off"]
-                    dst = self.de_all[:, eo:]
-                    self._direct(ops, lambda dy=dy, dst=dst: _lib.check(lib.tq_sample_channel_sums(
-                        dy.t.data_ptr(), dst.data_ptr(), R, N, dy.W, dy.C, self._st()), "sample_channel_sums"))
                 dy_eff, x_eff = dy, list(srcs)
                 if extra.get("stride") == 2:
                     dy_eff = self._new(N, srcs[0].W, dy.C)
@@ -387,6 +384,9 @@ class TrainStep1D:
                 d.dgamma, d.dbeta = st.view(st.G, mod.weight).data_ptr(), st.view(st.G, mod.bias).data_ptr()
                 d.dx_add0 = a0.t.data_ptr() if a0 is not None else None
                 d.dx_add1 = a1.t.data_ptr() if a1 is not None else None
+                if id(x0) in self.emb_of_act:   # x0 = conv1(h0) + e: de[n][c] = sum over positions of d(x0), fused here
+                    d.dx_sum = self.de_all[:, self.emb_of_act[id(x0)]:].data_ptr()
+                    d.dx_sum_ld = R
                 self._keep += [ws, d]
                 self._direct(ops, lambda d=d: _lib.check(lib.tq_gn_silu_backward(C.byref(d), self._st()), "gn_silu_backward"))
                 grad[id(x0)] = dx0
