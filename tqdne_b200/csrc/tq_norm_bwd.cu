@@ -34,6 +34,17 @@ struct GnBwdParams {
 
 template <typename T> struct Vec8;
 template <> struct Vec8<__nv_bfloat16> {
+    using Raw = uint4;
+    static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+    static __device__ __forceinline__ void cvt(const Raw& u, float (&v)[8]) {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+            v[2 * k] = __low2float(b2);
+            v[2 * k + 1] = __high2float(b2);
+        }
+    }
     static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -55,6 +66,13 @@ template <> struct Vec8<__nv_bfloat16> {
     }
 };
 template <> struct Vec8<float> {
+    struct Raw { float4 a, b; };
+    static __device__ __forceinline__ Raw ldraw(const float* p) {
+        return Raw{__ldg(reinterpret_cast<const float4*>(p)), __ldg(reinterpret_cast<const float4*>(p) + 1)};
+    }
+    static __device__ __forceinline__ void cvt(const Raw& r, float (&v)[8]) {
+        v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+    }
     static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(p));
         const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -180,10 +198,8 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
     if (on) {
         const VecSrc<T> s = pick_src<T>(p, n, c0);
         const T* dyb = static_cast<const T*>(p.dy) + (long long)n * p.P * Ct + c0;
-        for (int pix = p0 + pl; pix < p1; pix += lanes) {
-            float xv[8], dv[8];
-            Vec8<T>::load(s.x + (long long)pix * s.C, xv);
-            Vec8<T>::load(dyb + (long long)pix * Ct, dv);
+        // one position: everything from (x, dy[, add]) already converted to fp32
+        auto body = [&](const float (&xv)[8], const float (&dv)[8], const float (&ad)[8], int pix) {
             float out[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -198,20 +214,39 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
                     A[j] += d;
                     B[j] = fmaf(d, xh, B[j]);
                 } else {
-                    out[j] = rs[j] * (fmaf(ga[j], d, -M1[j]) - xh * M2[j]);
+                    out[j] = rs[j] * (fmaf(ga[j], d, -M1[j]) - xh * M2[j]) + ad[j];
+                    S[j] += out[j];
                 }
             }
-            if constexpr (PASS == 2) {
-                if (s.add) {
-                    float ad[8];
-                    Vec8<T>::load(s.add + (long long)pix * s.C, ad);
+            if constexpr (PASS == 2) Vec8<T>::store(s.dx + (long long)pix * s.C, out);
+        };
+        constexpr int UN = sizeof(T) == 2 ? 4 : 2;   // positions in flight per thread, kept RAW (16 B) until consumed
+        using Raw = typename Vec8<T>::Raw;
+        const bool has_add = PASS == 2 && s.add != nullptr;
+        int pix = p0 + pl;
+        for (; pix + (UN - 1) * lanes < p1; pix += UN * lanes) {
+            Raw rx[UN], rd[UN], ra[UN];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) out[j] += ad[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) S[j] += out[j];
-                Vec8<T>::store(s.dx + (long long)pix * s.C, out);
+            for (int u = 0; u < UN; ++u) {
+                rx[u] = Vec8<T>::ldraw(s.x + (long long)(pix + u * lanes) * s.C);
+                rd[u] = Vec8<T>::ldraw(dyb + (long long)(pix + u * lanes) * Ct);
+                if (has_add) ra[u] = Vec8<T>::ldraw(s.add + (long long)(pix + u * lanes) * s.C);
             }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                float xv[8], dv[8], ad[8] = {};
+                Vec8<T>::cvt(rx[u], xv);
+                Vec8<T>::cvt(rd[u], dv);
+                if (has_add) Vec8<T>::cvt(ra[u], ad);
+                body(xv, dv, ad, pix + u * lanes);
+            }
+        }
+        for (; pix < p1; pix += lanes) {
+            float xv[8], dv[8], ad[8] = {};
+            Vec8<T>::load(s.x + (long long)pix * s.C, xv);
+            Vec8<T>::load(dyb + (long long)pix * Ct, dv);
+            if (has_add) Vec8<T>::load(s.add + (long long)pix * s.C, ad);
+            body(xv, dv, ad, pix);
         }
     }
     if constexpr (PASS == 1) {
