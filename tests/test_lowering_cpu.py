@@ -103,3 +103,33 @@ def test_pack_conv_layout():
     pc2 = pack_conv(w[:, :2], None, [2], torch.float32, shortcut=(ws, torch.tensor([0.5, 0.5]), [2, 1]))
     assert pc2.ktot == 9 * 64 + 128 and pc2.extra_kb == {(0, 0): 9, (1, 0): 10} and float(pc2.bias[0]) == 0.5
     assert float(pc2.weights[0, 9 * 64 + 64]) == 1.0 and float(pc2.weights[0, 9 * 64 + 2]) == 0.0
+
+
+def test_training_parameter_store_layout_round_trip():
+    """tqdne_b200.training._Store (host logic, no kernels): every trainable parameter of the 1D UNet gets an engine-layout
+    view (conv weights [cout_pad, taps, cin_pad]); module -> store -> module is the identity, the emb_layers rows are
+    adjacent (one dense layer), padded stem / head channels are zero."""
+    import torch
+
+    import tqdne_b200 as tq
+    from tests.helpers import seeded, unet_cfg
+    from tqdne_b200.training import _Store
+
+    net = seeded(tq.UNetModel(**unet_cfg("1d")), 3)
+    st = _Store(net, "cpu")
+    st.load_from_module()
+    trainable = [p for p in net.parameters() if p.requires_grad]
+    assert len(st.order) == len(trainable) and st.n >= sum(p.numel() for p in trainable)
+    for p in trainable:
+        assert torch.equal(st.to_module_layout(st.P, p), p.detach())
+    stem = net.input_blocks[0][0]
+    v = st.view(st.P, stem.weight)
+    assert v.shape == (64, 5, 64) and float(v[:, :, 6:].abs().max()) == 0.0 and torch.equal(v[:, 2, :6], stem.weight[:, :, 2])
+    head = net.out[2]
+    assert st.view(st.P, head.weight).shape == (64, 5, 64) and float(st.view(st.P, head.weight)[6:].abs().max()) == 0.0
+    res = [m for m in net.modules() if type(m).__name__ == "ResBlock"]
+    rows = sum(r.emb_layers[1].weight.shape[0] for r in res)
+    wall = st.P[st.emb_w_off:st.emb_w_off + rows * 256].view(rows, 256)
+    assert st.emb_rows == rows and torch.equal(wall[:64], res[0].emb_layers[1].weight.detach())
+    assert torch.equal(wall[-res[-1].emb_layers[1].weight.shape[0]:], res[-1].emb_layers[1].weight.detach())
+    assert torch.equal(st.EMA, st.P)

@@ -112,3 +112,28 @@ def test_adam_ema_update_matches_torch_and_loss_decreases():
     step.sync_module()
     w = edm.unet.out[2].weight.detach()
     assert rel_l2(w, step.store.to_module_layout(step.store.P, edm.unet.out[2].weight)) < 1e-6
+
+
+def test_lightning_module_training_step_entry_point():
+    """LightningEDM.training_step(batch, batch_idx) (reference: edm.py:115-139) runs the engine's step for the 1D config and
+    refuses the configurations it is not built for."""
+    import tqdne_b200 as tq
+    from tests.helpers import CFG, arch
+
+    edm, _ = _edm(seed=33)
+    edm.optimizer_params = {"learning_rate": 1e-3, "max_steps": 10, "eta_min": 0.0}
+    g = torch.Generator(device="cuda").manual_seed(9)
+    batch = {"signal": torch.randn(2, 6, 512, device="cuda", generator=g), "cond": torch.randn(2, 5, device="cuda", generator=g)}
+    l0 = float(edm.training_step(batch, 0))
+    w0 = edm.unet.out[2].weight.detach().clone()
+    for i in range(3):
+        edm.training_step(batch, i + 1)
+    assert np.isfinite(l0)
+    edm.sync_trained_weights()
+    assert float((edm.unet.out[2].weight.detach() - w0).abs().max()) > 0       # the module sees the trained weights
+    out = edm.sample((2, 6, 512), cond=batch["cond"])                        # and the sampling path still runs on them
+    assert out.shape == (2, 6, 512) and bool(torch.isfinite(out).all())
+    enc_cfg, dec_cfg = arch().get_2d_autoencoder_configs(CFG)
+    latent = tq.LightningEDM(unet_cfg("latent2d"), {}, autoencoder=tq.LightningAutoencoder(enc_cfg, dec_cfg, {})).cuda()
+    with pytest.raises(NotImplementedError):
+        latent.training_step({"signal": torch.zeros(1, 3, 128, 128, device="cuda")}, 0)

@@ -345,8 +345,42 @@ class LightningEDM(LightningModule):
         cond = batch["cond"] if "cond" in batch else None
         return self.sample(batch["signal"].shape, cond_sample, cond)
 
-    # training is outside this engine; fail loudly instead of silently doing nothing
-    def step(self, batch, batch_idx):  # pragma: no cover
-        raise NotImplementedError("tqdne_b200 accelerates sampling; train with the reference tqdne package")
+    # ---- training: the 1D UNet (BASELINE.json configs[4]); everything else fails loudly
+    def _train_step(self, batch):
+        from .training import TrainStep1D
 
-    training_step = validation_step = step
+        if self.autoencoder is not None or self.unet.dims != 1 or "cond_signal" in batch:
+            raise NotImplementedError("tqdne_b200: the training step is built for the 1D EDM UNet without an autoencoder / "
+                                      "cond_signal (train_1d_edm config); train the other models with the reference package")
+        x = batch["signal"]
+        key = (x.shape[0], x.shape[-1])
+        ts = self.__dict__.get("_tq_train")
+        if ts is None or ts[0] != key:
+            op = self.optimizer_params or {}
+            ts = (key, TrainStep1D(self, x.shape[0], x.shape[-1], lr=op.get("learning_rate", 1e-4),
+                                   max_steps=op.get("max_steps", 100000), eta_min=op.get("eta_min", 0.0)))
+            self.__dict__["_tq_train"] = ts
+        return ts[1]
+
+    def step(self, batch, batch_idx=0):
+        """Loss of one batch (reference: edm.py:115-134); the gradients are left in the step's flat buffer."""
+        return self._train_step(batch).forward_backward(batch["signal"], batch.get("cond"))
+
+    def training_step(self, batch, batch_idx=0):
+        """Loss, gradients, gradient all-reduce over the initialised process group, Adam (cosine schedule) and EMA
+        update in one call (reference: training_step + configure_optimizers + the EMA callback, edm.py:136-139,240-251,
+        ema.py:24-28).  `sync_trained_weights()` writes the master (or EMA) parameters back into the module."""
+        import torch.distributed as dist
+
+        ts = self._train_step(batch)
+        loss = ts.forward_backward(batch["signal"], batch.get("cond"))
+        ts.optimizer_step(dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1)
+        return loss
+
+    def sync_trained_weights(self, ema: bool = False):
+        ts = self.__dict__.get("_tq_train")
+        if ts is not None:
+            ts[1].sync_module(ema=ema)
+
+    def validation_step(self, batch, batch_idx=0):  # pragma: no cover
+        raise NotImplementedError("tqdne_b200: validation-time sampling is `evaluate(batch)`; there is no validation loss path")
