@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 9
+#define TQ_ABI_VERSION 10
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -221,6 +221,12 @@ int tq_edm_noise(const float* y, const float* noise, const float* sigma, float* 
 int tq_edm_loss(const float* F, int32_t Cf, const float* xn, const float* y, const float* sigma, void* dF, float* loss, int64_t N,
                 int64_t P, int32_t C, int32_t Cpad, float sigma_data, void* stream);
 int tq_dropout_mask(void* mask, int64_t n, uint64_t seed, float p, void* stream);
+/* dst = src * the same scale, generated on the fly (forward and backward call it with the same seed): bf16, n % 8 == 0 */
+int tq_dropout_apply(const void* src, void* dst, int64_t n, uint64_t seed, float p, void* stream);
+/* bf16 operand copies of one convolution from its fp32 master [Op][k][Ip]: fwd [Op][k*Ip] (plain cast) and / or
+ * bwd [Cs][k*Op] = master[co][k-1-t][ci_off+ci] (input-gradient operand: taps flipped, in / out transposed).      */
+int tq_repack_conv_weights(const float* master, void* fwd, void* bwd, int32_t Op, int32_t k, int32_t Ip, int32_t ci_off,
+                           int32_t Cs, void* stream);
 int tq_adam_ema_step(float* param, const float* grad, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2,
                      float eps, int64_t step, float ema_decay, float grad_scale, void* stream);
 

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 9  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 10  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -126,6 +126,8 @@ SIGNATURES = {
     "tq_edm_noise": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _I32, _I32, _F, _VP]),
     "tq_edm_loss": (C.c_int, [_VP, _I32, _VP, _VP, _VP, _VP, _VP, _I64, _I64, _I32, _I32, _F, _VP]),
     "tq_dropout_mask": (C.c_int, [_VP, _I64, C.c_uint64, _F, _VP]),
+    "tq_repack_conv_weights": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "tq_dropout_apply": (C.c_int, [_VP, _VP, _I64, C.c_uint64, _F, _VP]),
     "tq_adam_ema_step": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _I64, _F, _F, _VP]),
     "tq_edm_precondition": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _I32, _F, _VP]),
     "tq_edm_euler": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _F, _F, _F, _F, _F, _I32, _VP]),

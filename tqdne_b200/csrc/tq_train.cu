@@ -159,17 +159,57 @@ __global__ void __launch_bounds__(256) edm_loss_kernel(const float* __restrict__
     }
 }
 
-// dropout scale tensor: 0 with probability p, else 1 / (1 - p); counter-based hash of (seed, element index)
+// dropout: element i is dropped when hash(seed, i) < p (counter-based splitmix64: the backward pass regenerates the same
+// decisions from the same seed, no mask tensor is stored); kept elements are scaled by 1 / (1 - p)   (nn.Dropout)
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, long long i, float p, float keep_scale) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.f / 16777216.f) < p ? 0.f : keep_scale;
+}
 __global__ void __launch_bounds__(256) dropout_mask_kernel(__nv_bfloat16* __restrict__ mask, long long n, unsigned long long seed,
                                                            float p) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);   // splitmix64
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    const float u = (float)(z >> 40) * (1.f / 16777216.f);
-    mask[i] = __float2bfloat16_rn(u < p ? 0.f : 1.f / (1.f - p));
+    mask[i] = __float2bfloat16_rn(dropout_scale(seed, i, p, 1.f / (1.f - p)));
+}
+// dst = src * dropout_scale: 8 elements per thread
+__global__ void __launch_bounds__(256) dropout_apply_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            long long nvec, unsigned long long seed, float p) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= nvec) return;
+    float v[8];
+    ld8(src + i * 8, v);
+    const float ks = 1.f / (1.f - p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= dropout_scale(seed, i * 8 + j, p, ks);
+    st8(dst + i * 8, v);
+}
+
+// bf16 operand copies of one convolution from its fp32 master [Op][k][Ip] (engine layout):
+//   fwd[co][t][ci]      = master[co][t][ci]                       (the forward igemm's [cout_pad, k * cin_pad] matrix)
+//   bwd[ci][t][co]      = master[co][k - 1 - t][ci_off + ci]      (input gradient: taps flipped, in / out transposed)
+__global__ void __launch_bounds__(256) repack_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, long long n) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(w[i]);
+}
+__global__ void __launch_bounds__(256) repack_bwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Op, int k,
+                                                         int Ip, int ci_off, int Cs) {
+    // 32 x 32 (co, ci) tile transpose through shared memory per tap: coalesced on both sides
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z;
+    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows per pass
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        tile[r][tx] = (co < Op && ci < Cs) ? w[((long long)co * k + (k - 1 - t)) * Ip + ci_off + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        if (ci < Cs && co < Op) dst[((long long)ci * k + t) * Op + co] = __float2bfloat16_rn(tile[tx][r]);
+    }
 }
 
 // Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) + EMA lerp (ema.py:24-28), one pass over flat fp32 arrays
@@ -260,6 +300,34 @@ int tq_dropout_mask(void* mask, int64_t n, uint64_t seed, float p, void* stream)
     dropout_mask_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(mask), n, seed, p);
     TQ_CUDA(cudaGetLastError());
     count_launch();
+    return 0;
+}
+
+int tq_dropout_apply(const void* src, void* dst, int64_t n, uint64_t seed, float p, void* stream) {
+    TQ_CHECK(src && dst && n > 0 && n % 8 == 0 && p >= 0.f && p < 1.f, "dropout_apply: bad arguments");
+    dropout_apply_kernel<<<grid_for(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n / 8, seed, p);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int tq_repack_conv_weights(const float* master, void* fwd, void* bwd, int32_t Op, int32_t k, int32_t Ip, int32_t ci_off,
+                           int32_t Cs, void* stream) {
+    TQ_CHECK(master && Op > 0 && k > 0 && Ip > 0 && ci_off >= 0 && (bwd == nullptr || ci_off + Cs <= Ip), "repack_conv_weights: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (fwd) {
+        const long long n = (long long)Op * k * Ip;
+        repack_fwd_kernel<<<grid_for(n), 256, 0, st>>>(master, static_cast<__nv_bfloat16*>(fwd), n);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    if (bwd) {
+        repack_bwd_kernel<<<dim3((Cs + 31) / 32, (Op + 31) / 32, k), 256, 0, st>>>(master, static_cast<__nv_bfloat16*>(bwd), Op, k, Ip,
+                                                                                    ci_off, Cs);
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+    }
     return 0;
 }
 

@@ -130,9 +130,10 @@ class TrainStep1D:
         self.p_drop = float(first_res.out_layers[2].p) if dropout is None else float(dropout)
         self.sigma_data = float(edm.edm.sigma_data)
         self.step_count = 0
+        self.pass_count = 0
         self.store = _Store(model, dev)
         self.store.load_from_module()
-        self.repack: list = []     # (destination bf16 tensor, thunk producing the fp32 source view)
+        self.repack: list = []     # (fp32 master view [Op, k, Ip], forward bf16 copy | None, input-gradient bf16 copy | None, ci_off, Cs)
         self.fwd: list = []
         self.bwd: list = []
         self.masks: list = []
@@ -156,6 +157,10 @@ class TrainStep1D:
     def _st(self):
         return current_stream_ptr()
 
+    def _seed(self, site: int) -> int:
+        """Dropout seed of (forward/backward pass number, dropout site): fresh decisions every step, same in both passes."""
+        return ((self.pass_count << 16) + site + 1) * 0x9E3779B1 & 0xFFFFFFFFFFFF
+
     def _new(self, N, L, Cc, dtype=BF16) -> Act:
         return Act(torch.empty(N * L * Cc, device=self.dev, dtype=dtype), N, 1, L, Cc)
 
@@ -165,7 +170,7 @@ class TrainStep1D:
         pc = pack_conv(mod.weight, mod.bias, real_in, BF16)
         wv, bv = st.view(st.P, mod.weight), st.view(st.P, mod.bias)
         pc.bias = bv
-        self.repack.append((pc.weights, lambda wv=wv: wv.reshape(wv.shape[0], -1)))
+        self.repack.append((wv, pc.weights, None, 0, 0))
         out = self._plan(self.fwd).conv(pc, srcs, dims=1, **kw)
         self._keep.append(pc)
         return out
@@ -237,11 +242,12 @@ class TrainStep1D:
             h2 = self._gn(gn2, [h1], True)
             self.nodes.append(("gn", gn2, [h1], h2, True))
             if self.p_drop > 0:
-                mask, h2d = self._new(N, h2.W, h2.C), self._new(N, h2.W, h2.C)
-                self.masks.append(mask)
-                self._direct(self.fwd, lambda a=h2, m=mask, o=h2d: _lib.check(self.lib.tq_rows_op(
-                    a.t.data_ptr(), m.t.data_ptr(), o.t.data_ptr(), 3, N, a.W, a.C, self._st()), "dropout"))
-                self.nodes.append(("mul", None, [h2], h2d, mask))
+                h2d = self._new(N, h2.W, h2.C)
+                di = len(self.masks)
+                self.masks.append(di)     # dropout site index: its seed is (step, site)
+                self._direct(self.fwd, lambda a=h2, o=h2d, di=di: _lib.check(self.lib.tq_dropout_apply(
+                    a.t.data_ptr(), o.t.data_ptr(), a.t.numel(), self._seed(di), self.p_drop, self._st()), "dropout"))
+                self.nodes.append(("mul", None, [h2], h2d, di))
                 h2 = h2d
             skip = blk.skip_connection
             if isinstance(skip, nn.Identity):
@@ -352,8 +358,8 @@ class TrainStep1D:
                     Cs = xs.C
                     wt = mod.weight.detach()[:, coff:coff + Cs, :].permute(1, 0, 2).flip(-1)   # [Cs, O, k]
                     pcb = pack_conv(wt, None, [O], BF16)
-                    self.repack.append((pcb.weights, lambda wv=wv, coff=coff, Cs=Cs: wv[:, :, coff:coff + Cs].flip(1).permute(2, 1, 0)
-                                        .reshape(Cs, -1)))
+                    assert tuple(pcb.weights.shape) == (Cs, k * Op), (pcb.weights.shape, Cs, k, Op)
+                    self.repack.append((wv, None, pcb.weights, coff, Cs))
                     self._keep.append(pcb)
                     pending = grad.get(id(xs)) if not extra.get("upsample") else None
                     dx = self._plan(ops).conv(pcb, [dy_eff], dims=1, residual=pending)
@@ -405,7 +411,8 @@ class TrainStep1D:
             elif kind == "mul":
                 dy = grad[id(out)]
                 dx = self._new(N, dy.W, dy.C)
-                rows_op(dy, dx, 3, aux=extra)
+                self._direct(ops, lambda dy=dy, dx=dx, di=extra: _lib.check(lib.tq_dropout_apply(
+                    dy.t.data_ptr(), dx.t.data_ptr(), dy.t.numel(), self._seed(di), self.p_drop, self._st()), "dropout backward"))
                 grad[id(srcs[0])] = dx
         # ---- embedding MLPs (all ResBlocks have deposited their de into de_all by now)
         f32 = dict(device=self.dev, dtype=torch.float32)
@@ -434,9 +441,13 @@ class TrainStep1D:
     # ------------------------------------------------------------------------------------------ running
     @torch.no_grad()
     def refresh_weights(self):
-        """bf16 operand copies (forward and transposed / flipped) from the fp32 master buffer: pure re-layout + cast."""
-        for dst, src in self.repack:
-            dst.copy_(src())
+        """bf16 operand copies (forward, and tap-flipped / transposed for the input gradient) from the fp32 masters."""
+        st = self._st()
+        for wv, fwd, bwd, coff, Cs in self.repack:
+            Op, k, Ip = wv.shape
+            _lib.check(self.lib.tq_repack_conv_weights(wv.data_ptr(), fwd.data_ptr() if fwd is not None else None,
+                                                       bwd.data_ptr() if bwd is not None else None, Op, k, Ip, coff, Cs, st),
+                       "repack_conv_weights")
 
     def lr(self) -> float:
         """CosineAnnealingLR stepped every optimiser step (edm.py:242-251)."""
@@ -464,10 +475,8 @@ class TrainStep1D:
             self.cond.copy_(cond.to(torch.float32))
         self.store.G.zero_()
         self.de_all.zero_()
+        self.pass_count += 1
         st = self._st()
-        for i, m in enumerate(self.masks):
-            _lib.check(self.lib.tq_dropout_mask(m.t.data_ptr(), m.t.numel(), (self.step_count << 20) + 7919 * (i + 1), self.p_drop, st),
-                       "dropout_mask")
         for f in self.fwd:
             f()
         _lib.check(self.lib.tq_edm_loss(self.out.t.data_ptr(), self.out.C, self.xn.data_ptr(), self.y.data_ptr(), self.sigma.data_ptr(),
