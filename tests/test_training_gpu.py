@@ -34,15 +34,17 @@ def _reference_loss_and_grads(sd, x, cond, sigma, noise):
     return loss.detach(), {k[len("unet."):]: v.grad for k, v in P.items() if v.requires_grad and v.grad is not None}
 
 
-def test_training_step_loss_and_gradients_match_autograd():
+@pytest.mark.parametrize("N,L", [(2, 512), (1, 4064)], ids=["2x512", "1x4064"])
+def test_training_step_loss_and_gradients_match_autograd(N, L):
+    """(1, 4064) is the reference signal length: 508 attention tokens (ragged against the 128-row tiles of both attention
+    backward kernels), 4064 / 2032 / 1016 / 508 positions per level."""
     from tqdne_b200.training import TrainStep1D
 
-    N, L = 2, 512
     edm, sd = _edm()
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randn(N, 6, L, device="cuda", generator=g)
     cond = torch.randn(N, 5, device="cuda", generator=g)
-    sigma = torch.tensor([0.4, 2.5], device="cuda")
+    sigma = torch.tensor([0.4, 2.5], device="cuda")[:N]
     noise = torch.randn(N, 6, L, device="cuda", generator=g)
     step = TrainStep1D(edm, N, L, dropout=0.0)
     loss = step.forward_backward(x, cond, sigma=sigma, noise=noise)

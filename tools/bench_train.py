@@ -29,7 +29,63 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--length", type=int, default=4064)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--impl", default="engine", choices=["engine", "reference"],
+                help="reference: the reference training step (autograd + torch.optim.Adam + EMA lerp) on the host CPUs")
+ap.add_argument("--cpu-batch", type=int, default=2)
 args = ap.parse_args()
+
+if args.impl == "reference":
+    # LightningEDM.step (edm.py:115-134) + Adam + EMA on the CPU: the unmodified reference module when /root/reference is
+    # present (build container), else the oracle port (GPU box); a bounded sample of the batch-64 workload
+    if int(os.environ.get("RANK", 0)) != 0:
+        sys.exit(0)
+    from oracle import reference_loader, torch_ref
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = MovingAverageEnvelopeConfig()
+    ucfg = tq.get_1d_unet_config(cfg, 6, 6)
+    shell = tq.LightningEDM(ucfg, {}, num_sampling_steps=18)
+    sd = seeded_state_dict(shapes_of(shell), 0)
+    B, L = args.cpu_batch, args.length
+    x, cond = torch.randn(B, 6, L), torch.randn(B, 5)
+    if reference_loader.available():
+        ref = reference_loader.load()
+        mod = ref.edm.LightningEDM(ucfg, {"learning_rate": 1e-4, "max_steps": 100000, "eta_min": 0.0}, num_sampling_steps=18)
+        mod.load_state_dict(sd)
+        mod.train()
+        params = [p for p in mod.parameters() if p.requires_grad]
+        loss_fn = lambda: mod.step({"signal": x, "cond": cond}, 0)  # noqa: E731
+        kind = "reference"
+    else:
+        P = {k: v.clone().requires_grad_(not k.endswith("time_embed.W")) for k, v in sd.items()}
+        params = [v for v in P.values() if v.requires_grad]
+
+        def loss_fn():
+            sigma = (torch.randn(B) * 1.2 - 1.2).exp()
+            pred = torch_ref.denoise(P, ucfg, x + torch.randn_like(x) * sigma[:, None, None], sigma, cond)
+            return ((pred - x) ** 2 * ((sigma**2 + 0.25) / (sigma * 0.5) ** 2)[:, None, None]).mean()
+        kind = "port"
+    opt = torch.optim.Adam(params, lr=1e-4)
+    ema = [p.detach().clone() for p in params]
+
+    def ref_step():
+        opt.zero_grad()
+        loss = loss_fn()
+        loss.backward()
+        opt.step()
+        torch._foreach_lerp_(ema, [p.detach() for p in params], 1e-3)
+        return float(loss)
+
+    ref_step()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 5)):
+        loss = ref_step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps // 5)
+    print(json.dumps({"impl": "reference", "metric": "training samples/sec (1D EDM UNet, fwd + bwd + Adam + EMA)", "value": B / dt,
+                      "unit": "samples/s", "ms_per_step": dt * 1e3, "dtype": "f32",
+                      "cpu_baseline": {"value": B / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": kind,
+                                       "sample": f"{B} x [6, {L}] per step"}, "loss": loss}), flush=True)
+    sys.exit(0)
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)

@@ -1,16 +1,17 @@
-"""Backward kernels of the training-step row -- groundwork, not yet a training step.
+"""Stand-alone front-ends of the training-step kernels.
 
 What autograd computes for the layers of the 1D EDM UNet (`LightningEDM.step`, tqdne/edm.py:115-134, config 5 of
-BASELINE.json) expressed on the engine's kernels, channels-last bf16 activations / gradients, fp32 parameter gradients:
+BASELINE.json) expressed on the engine's kernels, channels-last bf16 activations / gradients, fp32 parameter gradients.
+`tqdne_b200/training.py` strings the same kernels into the static tape of a whole step (with preallocated buffers); the
+functions here allocate per call and exist for kernel-level parity tests and benchmarks:
 
   * `conv1d_input_grad`  -- dX of a stride-1 "same" convolution IS a convolution of dY with the tap-flipped,
     in/out-transposed weights: the forward tcgen05 implicit GEMM (`tq_plan_add_conv`) runs it unchanged, including the
     epilogue add that accumulates the gradient of a tensor with two consumers;
   * `conv1d_weight_grad` -- `tq_conv1d_wgrad` (tcgen05, K = positions, MN-major operands, taps by descriptor row offset);
-  * `groupnorm_silu_backward` -- `tq_gn_silu_backward` (two streaming passes: group reductions, then dX / dgamma / dbeta).
-
-The optimiser, the loss, attention / resampling backward and the graph walker that strings these together are the
-remaining work of that row.
+  * `groupnorm_silu_backward` -- `tq_gn_silu_backward` (two streaming passes: group reductions, then dX / dgamma / dbeta);
+  * `attention_backward` -- `tq_attention_backward` (two tcgen05 kernels: dQ + row statistics, transposed dK / dV);
+  * `sample_channel_sums` -- the gradient of the per-sample embedding term.
 """
 
 from __future__ import annotations
