@@ -744,3 +744,76 @@ def test_attention_backward_matches_autograd(N, T, heads):
     for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
         err = rel_l2(got[..., sl], want[..., sl])
         assert err < 1e-2, (name, err)
+
+
+def test_training_helper_kernels_match_torch():
+    """tq_rows_op (zero-stuff / nearest upsample / pair-sum / mul / add), tq_linear_backward, tq_edm_noise + tq_edm_loss,
+    tq_dropout_apply and tq_repack_conv_weights against their torch definitions."""
+    from tqdne_b200 import _lib
+    from tqdne_b200.engine import current_stream_ptr
+
+    lib, st = _lib.lib(), current_stream_ptr()
+    g = torch.Generator(device="cuda").manual_seed(77)
+    bf = torch.bfloat16
+    N, L, C = 3, 50, 64
+    src = torch.randn(N, L, C, device="cuda", generator=g).to(bf)
+    aux = torch.randn(N, L, C, device="cuda", generator=g).to(bf)
+    dst2 = torch.empty(N, 2 * L, C, device="cuda", dtype=bf)
+    _lib.check(lib.tq_rows_op(src.data_ptr(), None, dst2.data_ptr(), 0, N, 2 * L, C, st), "zero_stuff")
+    want = torch.zeros_like(dst2)
+    want[:, 0::2] = src
+    assert torch.equal(dst2, want)
+    _lib.check(lib.tq_rows_op(src.data_ptr(), None, dst2.data_ptr(), 1, N, 2 * L, C, st), "upsample")
+    assert torch.equal(dst2, src.repeat_interleave(2, dim=1))
+    half = torch.empty(N, L // 2, C, device="cuda", dtype=bf)
+    _lib.check(lib.tq_rows_op(src.data_ptr(), None, half.data_ptr(), 2, N, L // 2, C, st), "pair_sum")
+    assert torch.equal(half, (src[:, 0::2].float() + src[:, 1::2].float()).to(bf))
+    out = torch.empty_like(src)
+    _lib.check(lib.tq_rows_op(src.data_ptr(), aux.data_ptr(), out.data_ptr(), 3, N, L, C, st), "mul")
+    assert torch.equal(out, (src.float() * aux.float()).to(bf))
+    _lib.check(lib.tq_rows_op(src.data_ptr(), aux.data_ptr(), out.data_ptr(), 4, N, L, C, st), "add")
+    assert torch.equal(out, (src.float() + aux.float()).to(bf))
+    # dropout: same decisions for the same seed, kept fraction ~ 1 - p, kept values scaled by 1 / (1 - p)
+    big = torch.ones(1 << 16, device="cuda", dtype=bf)
+    d1, d2, d3 = torch.empty_like(big), torch.empty_like(big), torch.empty_like(big)
+    for d, seed in ((d1, 11), (d2, 11), (d3, 12)):
+        _lib.check(lib.tq_dropout_apply(big.data_ptr(), d.data_ptr(), big.numel(), seed, 0.1, st), "dropout_apply")
+    assert torch.equal(d1, d2) and not torch.equal(d1, d3)
+    kept = (d1 != 0).float().mean().item()
+    assert abs(kept - 0.9) < 0.01 and torch.allclose(d1[d1 != 0].float(), torch.tensor(1 / 0.9, device="cuda"), rtol=1e-2)
+    # dense layer backward
+    M, K, No = 5, 48, 37
+    x, W, dy = (torch.randn(s, device="cuda", generator=g) for s in ((M, K), (No, K), (M, No)))
+    for act in (0, 1):
+        xr, Wr = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
+        br = torch.zeros(No, device="cuda", requires_grad=True)
+        (F.linear(F.silu(xr) if act else xr, Wr, br)).backward(dy)
+        dx, dW, db = torch.empty(M, K, device="cuda"), torch.zeros(No, K, device="cuda"), torch.zeros(No, device="cuda")
+        _lib.check(lib.tq_linear_backward(dy.data_ptr(), x.data_ptr(), W.data_ptr(), act, dx.data_ptr(), dW.data_ptr(), db.data_ptr(),
+                                          M, K, No, st), "linear_backward")
+        assert rel_l2(dx, xr.grad) < 1e-5 and rel_l2(dW, Wr.grad) < 1e-5 and rel_l2(db, br.grad) < 1e-5
+    # EDM noising + loss against LightningEDM.step's formulas (edm.py:105-134)
+    Nn, P, Cc, Cp = 3, 40, 6, 64
+    y, nz = torch.randn(Nn, P, Cc, device="cuda", generator=g), torch.randn(Nn, P, Cc, device="cuda", generator=g)
+    sig = torch.tensor([0.3, 1.0, 4.0], device="cuda")
+    xn, xin = torch.empty_like(y), torch.empty(Nn, P, Cp, device="cuda", dtype=bf)
+    _lib.check(lib.tq_edm_noise(y.data_ptr(), nz.data_ptr(), sig.data_ptr(), xn.data_ptr(), xin.data_ptr(), Nn, P, Cc, Cp, 0.5, st), "noise")
+    s3 = sig[:, None, None]
+    assert rel_l2(xn, y + s3 * nz) < 1e-6
+    assert rel_l2(xin[..., :Cc].float(), (xn / (s3**2 + 0.25).sqrt()).to(bf).float()) < 1e-6 and float(xin[..., Cc:].abs().max()) == 0
+    Fo = torch.randn(Nn, P, Cc, device="cuda", generator=g).requires_grad_(True)
+    c_out, c_skip, w = s3 * 0.5 / (s3**2 + 0.25).sqrt(), 0.25 / (s3**2 + 0.25), (s3**2 + 0.25) / (s3 * 0.5) ** 2
+    ref = (w * (c_out * Fo + c_skip * xn - y) ** 2).mean()
+    ref.backward()
+    dF, loss = torch.empty(Nn, P, Cp, device="cuda", dtype=bf), torch.zeros(1, device="cuda")
+    _lib.check(lib.tq_edm_loss(Fo.detach().data_ptr(), Cc, xn.data_ptr(), y.data_ptr(), sig.data_ptr(), dF.data_ptr(), loss.data_ptr(),
+                               Nn, P, Cc, Cp, 0.5, st), "loss")
+    assert abs(float(loss) - float(ref.detach())) < 1e-5 * abs(float(ref.detach()))
+    assert rel_l2(dF[..., :Cc].float(), Fo.grad) < 4e-3 and float(dF[..., Cc:].abs().max()) == 0
+    # operand copies of a convolution's fp32 master [Op, k, Ip]
+    Op, k, Ip, off, Cs = 128, 5, 192, 64, 128
+    m = torch.randn(Op, k, Ip, device="cuda", generator=g)
+    fwd, bwd = torch.empty(Op, k * Ip, device="cuda", dtype=bf), torch.empty(Cs, k * Op, device="cuda", dtype=bf)
+    _lib.check(lib.tq_repack_conv_weights(m.data_ptr(), fwd.data_ptr(), bwd.data_ptr(), Op, k, Ip, off, Cs, st), "repack")
+    assert torch.equal(fwd, m.reshape(Op, -1).to(bf))
+    assert torch.equal(bwd, m[:, :, off:off + Cs].flip(1).permute(2, 1, 0).reshape(Cs, -1).to(bf))
