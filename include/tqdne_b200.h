@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 10
+#define TQ_ABI_VERSION 11
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -125,6 +125,9 @@ typedef struct {
     void*   y;
     float*  ws;
     const float* stats0; const float* stats1;
+    /* training only (bf16): y = dropout(act(GroupNorm(x))), nn.Dropout of ResBlock.out_layers (tqdne/unet.py:100-108).
+     * The decision of element i is hash(*drop_seed + site, i) < drop_p; NULL / 0 = no dropout (every sampling plan).   */
+    const uint64_t* drop_seed; float drop_p; int32_t drop_site;
 } tq_gn_desc;
 int tq_plan_add_groupnorm(tq_plan* p, const tq_gn_desc* d);
 
@@ -191,6 +194,7 @@ typedef struct {
     float* dgamma; float* dbeta;
     const void* dx_add0; const void* dx_add1;   /* optional: gradient of x0 / x1 from their other consumer, added to dx */
     float* dx_sum; int32_t dx_sum_ld;            /* optional: dx_sum[n*ld + c] += sum_p dx0[n][p][c] (embedding gradient) */
+    const uint64_t* drop_seed; float drop_p; int32_t drop_site;   /* the forward's fused dropout (tq_gn_desc), or NULL */
 } tq_gn_bwd_desc;
 int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream);
 

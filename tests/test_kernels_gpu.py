@@ -817,3 +817,46 @@ def test_training_helper_kernels_match_torch():
     _lib.check(lib.tq_repack_conv_weights(m.data_ptr(), fwd.data_ptr(), bwd.data_ptr(), Op, k, Ip, off, Cs, st), "repack")
     assert torch.equal(fwd, m.reshape(Op, -1).to(bf))
     assert torch.equal(bwd, m[:, :, off:off + Cs].flip(1).permute(2, 1, 0).reshape(Cs, -1).to(bf))
+
+
+def test_groupnorm_fused_dropout_forward_and_backward_agree():
+    """Training-mode GroupNorm+SiLU with nn.Dropout fused behind the activation (tq_gn_desc.drop_*): the forward's dropped
+    elements are recovered from its output, and the backward kernel -- which regenerates the decisions from (seed, element
+    index) -- must match autograd through silu(group_norm(x)) * mask with exactly that mask."""
+    from tqdne_b200.backward import groupnorm_silu_backward
+    from tqdne_b200.engine import Act
+
+    dt, N, P, C, p = torch.bfloat16, 3, 300, 128, 0.25
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = _rt(torch.randn(N, P, C, device="cuda", generator=g) + 0.3, dt)
+    dy = _rt(torch.randn(N, P, C, device="cuda", generator=g), dt)
+    gamma, beta = 1 + 0.1 * torch.randn(C, device="cuda", generator=g), 0.1 * torch.randn(C, device="cuda", generator=g)
+    st = torch.stack([x.sum(1), (x * x).sum(1)], dim=-1).contiguous()
+    xa = Act(x.to(dt).reshape(-1), N, 1, P, C, stats=st)
+    seed = torch.tensor([123456789], device="cuda", dtype=torch.int64)
+    plan = _plan(dt)
+    y = plan.groupnorm([xa], gamma, beta, silu=True, drop_seed=seed, drop_p=p, drop_site=3)
+    y0 = plan.groupnorm([xa], gamma, beta, silu=True)
+    plan.run()
+    torch.cuda.synchronize()
+    yv, y0v = y.t.float().reshape(N, P, C), y0.t.float().reshape(N, P, C)
+    dropped = (yv == 0) & (y0v != 0)
+    frac = dropped.float().mean().item()
+    assert abs(frac - p) < 0.01, frac
+    keep = 1 / (1 - p)
+    assert rel_l2(yv[~dropped], y0v[~dropped] * keep) < 5e-3          # kept elements: scaled by 1 / (1 - p)
+    dx, _, dgam, dbet = groupnorm_silu_backward(xa, Act(dy.to(dt).reshape(-1), N, 1, P, C), gamma, beta, drop_seed=seed,
+                                                drop_p=p, drop_site=3)
+    torch.cuda.synchronize()
+    mask = (~dropped).double().permute(0, 2, 1) * keep
+    xr = x.double().permute(0, 2, 1).clone().requires_grad_(True)
+    gr, br = gamma.double().clone().requires_grad_(True), beta.double().clone().requires_grad_(True)
+    (F.silu(F.group_norm(xr, 32, gr, br, eps=1e-5)) * mask).backward(dy.double().permute(0, 2, 1))
+    assert rel_l2(dx.t.float().reshape(N, P, C), xr.grad.permute(0, 2, 1)) < 5e-3
+    assert rel_l2(dgam, gr.grad) < 2e-3 and rel_l2(dbet, br.grad) < 2e-3
+    # another site or seed draws other decisions
+    plan2 = _plan(dt)
+    y2 = plan2.groupnorm([xa], gamma, beta, silu=True, drop_seed=seed, drop_p=p, drop_site=4)
+    plan2.run()
+    torch.cuda.synchronize()
+    assert not torch.equal(y2.t, y.t)

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 10  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 11  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -66,6 +66,7 @@ class TqGnDesc(C.Structure):
         ("y", C.c_void_p),
         ("ws", C.c_void_p),
         ("stats0", C.c_void_p), ("stats1", C.c_void_p),
+        ("drop_seed", C.c_void_p), ("drop_p", C.c_float), ("drop_site", C.c_int32),
     ]
 
 
@@ -93,7 +94,8 @@ class TqGnBwdDesc(C.Structure):
                 ("x0", C.c_void_p), ("x1", C.c_void_p), ("dy", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("eps", C.c_float), ("silu", C.c_int32), ("stats0", C.c_void_p), ("stats1", C.c_void_p), ("ws", C.c_void_p),
                 ("dx0", C.c_void_p), ("dx1", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
-                ("dx_add0", C.c_void_p), ("dx_add1", C.c_void_p), ("dx_sum", C.c_void_p), ("dx_sum_ld", C.c_int32)]
+                ("dx_add0", C.c_void_p), ("dx_add1", C.c_void_p), ("dx_sum", C.c_void_p), ("dx_sum_ld", C.c_int32),
+                ("drop_seed", C.c_void_p), ("drop_p", C.c_float), ("drop_site", C.c_int32)]
 
 
 # name -> (restype, argtypes): every symbol include/tqdne_b200.h declares

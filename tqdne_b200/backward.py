@@ -53,7 +53,8 @@ def conv1d_weight_grad(x: torch.Tensor, dy: torch.Tensor, taps: int, dw: torch.T
 
 def groupnorm_silu_backward(x0: Act, dy: Act, gamma: torch.Tensor, beta: torch.Tensor, *, silu: bool = True, x1: Act | None = None,
                             eps: float = 1e-5, dgamma: torch.Tensor | None = None, dbeta: torch.Tensor | None = None,
-                            add0: Act | None = None, add1: Act | None = None):
+                            add0: Act | None = None, add1: Act | None = None, drop_seed: torch.Tensor | None = None,
+                            drop_p: float = 0.0, drop_site: int = 0):
     """dX (one tensor per source), dgamma, dbeta of y = [SiLU](GroupNorm32(cat[x0, x1])).  x0 / x1 carry the forward
     per-(sample, channel) statistics (`Act.stats`, written by the producing conv's epilogue)."""
     from .engine import tq_dtype
@@ -79,6 +80,8 @@ def groupnorm_silu_backward(x0: Act, dy: Act, gamma: torch.Tensor, beta: torch.T
     d.ws, d.dx0, d.dx1 = ws.data_ptr(), dx0.data_ptr(), (dx1.data_ptr() if dx1 is not None else None)
     d.dgamma, d.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
     d.dx_sum, d.dx_sum_ld = None, 0
+    if drop_seed is not None and drop_p > 0:
+        d.drop_seed, d.drop_p, d.drop_site = drop_seed.data_ptr(), drop_p, drop_site
     d.dx_add0 = add0.t.data_ptr() if add0 is not None else None
     d.dx_add1 = add1.t.data_ptr() if add1 is not None else None
     _lib.check(_lib.lib().tq_gn_silu_backward(C.byref(d), current_stream_ptr()), "gn_silu_backward")

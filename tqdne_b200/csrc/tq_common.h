@@ -52,6 +52,20 @@ int pdl_mode();
 void pdl_set_current(bool on);
 
 #ifdef __CUDACC__
+// dropout (nn.Dropout, tqdne/unet.py:100-108): element i is dropped when hash(seed, i) < p -- a counter-based splitmix64,
+// so the backward pass regenerates the forward's decisions from (seed, element index) and no mask tensor is stored
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, long long i, float p, float keep_scale) {
+    // 32-bit counter hash (two multiply / xor-shift rounds): ~8 integer instructions per element -- the 64-bit splitmix
+    // version made the GroupNorm backward passes, which evaluate it twice per element, measurably slower
+    unsigned int x = (unsigned int)i * 0x9E3779B1u + (unsigned int)seed;
+    x ^= (unsigned int)(seed >> 32) + (unsigned int)((unsigned long long)i >> 32);
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return (float)(x >> 8) * (1.f / 16777216.f) < p ? 0.f : keep_scale;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

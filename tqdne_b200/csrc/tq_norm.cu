@@ -31,6 +31,9 @@ struct GnParams {
     const float* st0;  // [N][C0][2]  (== ws when the statistics pass ran)
     const float* st1;  // [N][C1][2]
     int chunks;
+    const unsigned long long* drop_seed;  // training only: dropout after the activation (nullptr = none)
+    float drop_p;
+    int drop_site;
 };
 
 template <typename T>
@@ -186,8 +189,13 @@ __device__ __forceinline__ SrcView<T> make_view(const T* x, int C, int cbase, in
 
 // `silu` in {0, 1}; for bf16 + SiLU the caller passes a / 2 and b / 2 (exact), so that h = x a' + b' = v / 2 and
 // SiLU(v) = v sigmoid(v) = h (1 + tanh(h)) = fma(h, tanh(h), h): FMA, MUFU, FMA per element instead of five operations
-template <typename T>
-__device__ __forceinline__ void emit8(const Raw8<T>& r, const float (&a)[8], const float (&b)[8], int silu, T* dst) {
+struct Drop {
+    unsigned long long seed;
+    float p, keep;
+};
+template <typename T, bool DROP>
+__device__ __forceinline__ void emit8(const Raw8<T>& r, const float (&a)[8], const float (&b)[8], int silu, T* dst, const Drop& dr,
+                                      long long idx0) {
     float v[8];
     r.get(v);
     if constexpr (sizeof(T) == 2) {
@@ -210,17 +218,24 @@ __device__ __forceinline__ void emit8(const Raw8<T>& r, const float (&a)[8], con
             if (silu) v[j] = silu_f<T>(v[j]);
         }
     }
+    if constexpr (DROP) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= dropout_scale(dr.seed, idx0 + j, dr.p, dr.keep);
+    }
     store8(dst, v);
 }
 
-template <typename T>
+template <typename T, bool DROP>
 __device__ __forceinline__ void stream_source(SrcView<T>& s, const float (&a)[8], const float (&b)[8], int silu, int Ct,
-                                              Raw8<T> (&pre)[GN_UNROLL], bool have_pre) {
+                                              Raw8<T> (&pre)[GN_UNROLL], bool have_pre, const Drop& dr, long long nbase) {
+    // element index of (position pix, this thread's first channel) in the [N][P][Ct] output: the dropout counter
+    auto eidx = [&](int pix) { return (nbase + pix) * Ct + s.cvec0; };
     if (!s.on) return;
     const int step = GN_UNROLL * s.lanes;
     if (have_pre) {
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) emit8<T>(pre[u], a, b, silu, s.yb + (long long)(s.pix + u * s.lanes) * Ct);
+        for (int u = 0; u < GN_UNROLL; ++u)
+            emit8<T, DROP>(pre[u], a, b, silu, s.yb + (long long)(s.pix + u * s.lanes) * Ct, dr, eidx(s.pix + u * s.lanes));
         s.pix += step;
     }
     for (; s.pix + (GN_UNROLL - 1) * s.lanes < s.p1; s.pix += step) {
@@ -228,12 +243,13 @@ __device__ __forceinline__ void stream_source(SrcView<T>& s, const float (&a)[8]
 #pragma unroll
         for (int u = 0; u < GN_UNROLL; ++u) r[u].load(s.xb + (long long)(s.pix + u * s.lanes) * s.C);
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) emit8<T>(r[u], a, b, silu, s.yb + (long long)(s.pix + u * s.lanes) * Ct);
+        for (int u = 0; u < GN_UNROLL; ++u)
+            emit8<T, DROP>(r[u], a, b, silu, s.yb + (long long)(s.pix + u * s.lanes) * Ct, dr, eidx(s.pix + u * s.lanes));
     }
     for (; s.pix < s.p1; s.pix += s.lanes) {
         Raw8<T> r;
         r.load(s.xb + (long long)s.pix * s.C);
-        emit8<T>(r, a, b, silu, s.yb + (long long)s.pix * Ct);
+        emit8<T, DROP>(r, a, b, silu, s.yb + (long long)s.pix * Ct, dr, eidx(s.pix));
     }
 }
 
@@ -250,7 +266,7 @@ __device__ __forceinline__ void affine8(const float* gstat, int cpg, int c0, con
     }
 }
 
-template <typename T>
+template <typename T, bool DROP>
 __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(const GnParams p) {
     __shared__ float gstat[64];  // [32][2] group mean, rstd
     const int n = blockIdx.y, chunk = blockIdx.x;
@@ -310,7 +326,14 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(c
             for (int j = 0; j < 8; ++j) { a[j] *= 0.5f; b[j] *= 0.5f; }
         }
     }
-    stream_source<T>(v0, a, b, p.silu, Ct, pre, have_pre);
+    Drop dr{0ull, 0.f, 1.f};
+    if constexpr (DROP) {
+        dr.seed = *p.drop_seed + 0x632BE59BD9B4E019ull * (unsigned long long)(p.drop_site + 1);
+        dr.p = p.drop_p;
+        dr.keep = 1.f / (1.f - p.drop_p);
+    }
+    const long long nbase = (long long)n * p.P;
+    stream_source<T, DROP>(v0, a, b, p.silu, Ct, pre, have_pre, dr, nbase);
     if (p.C1 > 0) {
         SrcView<T> v1 = make_view<T>(static_cast<const T*>(p.x1), p.C1, p.C0, Ct, p.P, n, chunk, p.chunks, y);
         if (v1.on) {
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(c
                 for (int j = 0; j < 8; ++j) { a[j] *= 0.5f; b[j] *= 0.5f; }
             }
         }
-        stream_source<T>(v1, a, b, p.silu, Ct, pre, false);
+        stream_source<T, DROP>(v1, a, b, p.silu, Ct, pre, false, dr, nbase);
     }
 }
 
@@ -382,9 +405,13 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
     Op ap;
     ap.name = f32 ? "gn_apply<f32>" : "gn_apply<bf16>";
     ap.small = (double)d.N * d.P * Ct * (f32 ? 8 : 4) < 40e6;  // < 40 MB moved: latency-bound
-    ap.launch = [p, grid, f32, smem](cudaStream_t s) -> int {
-        if (f32) TQ_CUDA(launch_pdl(gn_apply_kernel<float>, grid, dim3(256), smem, s, *p));
-        else TQ_CUDA(launch_pdl(gn_apply_kernel<__nv_bfloat16>, grid, dim3(256), smem, s, *p));
+    const bool drop = d.drop_seed != nullptr && d.drop_p > 0.f;
+    TQ_CHECK(!drop || (!f32 && d.drop_p < 1.f), "groupnorm: fused dropout is built for bf16 and p < 1");
+    p->drop_seed = reinterpret_cast<const unsigned long long*>(d.drop_seed); p->drop_p = d.drop_p; p->drop_site = d.drop_site;
+    ap.launch = [p, grid, f32, smem, drop](cudaStream_t s) -> int {
+        if (f32) TQ_CUDA(launch_pdl(gn_apply_kernel<float, false>, grid, dim3(256), smem, s, *p));
+        else if (drop) TQ_CUDA(launch_pdl(gn_apply_kernel<__nv_bfloat16, true>, grid, dim3(256), smem, s, *p));
+        else TQ_CUDA(launch_pdl(gn_apply_kernel<__nv_bfloat16, false>, grid, dim3(256), smem, s, *p));
         TQ_CUDA(cudaGetLastError());
         count_launch();
         return 0;

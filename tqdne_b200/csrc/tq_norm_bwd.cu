@@ -28,6 +28,7 @@ struct GnBwdParams {
     const float* st0; const float* st1;   // forward sums [N][C0][2], [N][C1][2]
     float* ws;                            // [N][C0 + C1][2]: A, B
     float* dgamma; float* dbeta;          // [C0 + C1], accumulated into
+    const unsigned long long* drop_seed; float drop_p; int drop_site;   // the forward's fused dropout (nullptr = none)
     float* dx_sum; int dx_sum_ld;         // optional: dx_sum[n * ld + c] += sum over positions of dx0 (embedding gradient)
     int chunks;
 };
@@ -199,12 +200,17 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
         const VecSrc<T> s = pick_src<T>(p, n, c0);
         const T* dyb = static_cast<const T*>(p.dy) + (long long)n * p.P * Ct + c0;
         // one position: everything from (x, dy[, add]) already converted to fp32
+        const bool drop = p.drop_seed != nullptr;
+        const unsigned long long dseed = drop ? *p.drop_seed + 0x632BE59BD9B4E019ull * (unsigned long long)(p.drop_site + 1) : 0ull;
+        const float dkeep = drop ? 1.f / (1.f - p.drop_p) : 1.f;
         auto body = [&](const float (&xv)[8], const float (&dv)[8], const float (&ad)[8], int pix) {
             float out[8];
+            const long long idx0 = ((long long)n * p.P + pix) * Ct + c0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float xh = (xv[j] - mu[j]) * rs[j];
                 float d = dv[j];
+                if (drop) d *= dropout_scale(dseed, idx0 + j, p.drop_p, dkeep);   // y = dropout(act(v)): dy first meets the mask
                 if (p.silu) {
                     const float v = fmaf(xh, ga[j], be[j]);
                     const float sg = sigmoid_f<T>(v);
@@ -301,6 +307,8 @@ extern "C" int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream) {
     p.x0 = d->x0; p.x1 = d->x1; p.dy = d->dy; p.dx0 = d->dx0; p.dx1 = d->dx1; p.add0 = d->dx_add0; p.add1 = d->dx_add1;
     p.N = d->N; p.P = d->P; p.C0 = d->C0; p.C1 = d->C1; p.gamma = d->gamma; p.beta = d->beta; p.eps = d->eps;
     p.silu = d->silu; p.st0 = d->stats0; p.st1 = d->C1 > 0 ? d->stats1 : nullptr; p.ws = d->ws;
+    p.drop_seed = reinterpret_cast<const unsigned long long*>(d->drop_seed); p.drop_p = d->drop_p; p.drop_site = d->drop_site;
+    if (!(d->drop_p > 0.f)) p.drop_seed = nullptr;
     p.dgamma = d->dgamma; p.dbeta = d->dbeta; p.dx_sum = d->dx_sum; p.dx_sum_ld = d->dx_sum_ld > 0 ? d->dx_sum_ld : d->C0;
     const int slots = device_sm_count() * 4;
     const int max_chunks = (d->P + 31) / 32;

@@ -161,13 +161,6 @@ __global__ void __launch_bounds__(256) edm_loss_kernel(const float* __restrict__
 
 // dropout: element i is dropped when hash(seed, i) < p (counter-based splitmix64: the backward pass regenerates the same
 // decisions from the same seed, no mask tensor is stored); kept elements are scaled by 1 / (1 - p)   (nn.Dropout)
-__device__ __forceinline__ float dropout_scale(unsigned long long seed, long long i, float p, float keep_scale) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (float)(z >> 40) * (1.f / 16777216.f) < p ? 0.f : keep_scale;
-}
 __global__ void __launch_bounds__(256) dropout_mask_kernel(__nv_bfloat16* __restrict__ mask, long long n, unsigned long long seed,
                                                            float p) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;

@@ -369,7 +369,8 @@ class Plan:
             self.keep.append(residual.t)
         return out
 
-    def groupnorm(self, srcs: list[Act], gamma: torch.Tensor, beta: torch.Tensor, silu: bool) -> Act:
+    def groupnorm(self, srcs: list[Act], gamma: torch.Tensor, beta: torch.Tensor, silu: bool, *, drop_seed: torch.Tensor | None = None,
+                  drop_p: float = 0.0, drop_site: int = 0) -> Act:
         a0 = srcs[0]
         a1 = srcs[1] if len(srcs) > 1 else None
         Ct = a0.C + (a1.C if a1 else 0)
@@ -385,6 +386,9 @@ class Plan:
         d.eps = GN_EPS
         d.silu = 1 if silu else 0
         d.y = out.t.data_ptr()
+        if drop_seed is not None and drop_p > 0:      # training only: dropout fused behind the activation
+            d.drop_seed, d.drop_p, d.drop_site = drop_seed.data_ptr(), drop_p, drop_site
+            self.keep.append(drop_seed)
         fused = a0.stats is not None and (a1 is None or a1.stats is not None)
         if fused:
             d.stats0 = a0.stats.data_ptr()

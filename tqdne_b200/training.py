@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 from torch import nn
@@ -131,6 +132,8 @@ class TrainStep1D:
         self.sigma_data = float(edm.edm.sigma_data)
         self.step_count = 0
         self.pass_count = 0
+        # dropout inside the GroupNorm kernels of both passes (default) or as separate multiply passes (A/B switch)
+        self.fused_dropout = os.environ.get("TQ_TRAIN_FUSED_DROPOUT", "1") != "0"
         self.store = _Store(model, dev)
         self.store.load_from_module()
         self.repack: list = []     # (fp32 master view [Op, k, Ip], forward bf16 copy | None, input-gradient bf16 copy | None, ci_off, Cs)
@@ -157,8 +160,7 @@ class TrainStep1D:
     def _st(self):
         return current_stream_ptr()
 
-    def _seed(self, site: int) -> int:
-        """Dropout seed of (forward/backward pass number, dropout site): fresh decisions every step, same in both passes."""
+    def _host_seed(self, site: int) -> int:
         return ((self.pass_count << 16) + site + 1) * 0x9E3779B1 & 0xFFFFFFFFFFFF
 
     def _new(self, N, L, Cc, dtype=BF16) -> Act:
@@ -175,9 +177,10 @@ class TrainStep1D:
         self._keep.append(pc)
         return out
 
-    def _gn(self, gn: nn.GroupNorm, srcs: list[Act], silu: bool) -> Act:
+    def _gn(self, gn: nn.GroupNorm, srcs: list[Act], silu: bool, drop_site: int | None = None) -> Act:
         st = self.store
-        return self._plan(self.fwd).groupnorm(srcs, st.view(st.P, gn.weight), st.view(st.P, gn.bias), silu=silu)
+        kw = dict(drop_seed=self.drop_seed, drop_p=self.p_drop, drop_site=drop_site) if drop_site is not None else {}
+        return self._plan(self.fwd).groupnorm(srcs, st.view(st.P, gn.weight), st.view(st.P, gn.bias), silu=silu, **kw)
 
     def _build(self):
         model, st, N, L, dev = self.model, self.store, self.N, self.L, self.dev
@@ -185,6 +188,8 @@ class TrainStep1D:
         mc = model.model_channels
         E = 4 * mc
         self.nodes: list = []
+        self.drop_of_act: dict = {}  # id(GroupNorm output) -> dropout site fused into it (or None)
+        self.drop_seed = torch.zeros(1, device=dev, dtype=torch.int64)
         self.emb_of_act: dict = {}   # id(conv1 output) -> column offset of its ResBlock in e_all / de_all
         self.cin = model.in_channels
         self.cin_pad = _pad64(self.cin)
@@ -239,15 +244,19 @@ class TrainStep1D:
             h1 = self._conv(conv1, [h0], [h0.C], emb=self.e_all[:, eo:], emb_ld=R, stats=True)
             self.nodes.append(("conv", conv1, [h0], h1, {}))
             self.emb_of_act[id(h1)] = eo
-            h2 = self._gn(gn2, [h1], True)
+            site = None
+            if self.p_drop > 0:       # nn.Dropout behind the activation
+                site = len(self.masks)
+                self.masks.append(site)
+            h2 = self._gn(gn2, [h1], True, drop_site=site if self.fused_dropout else None)
             self.nodes.append(("gn", gn2, [h1], h2, True))
-            if self.p_drop > 0:
+            if site is not None and self.fused_dropout:
+                self.drop_of_act[id(h2)] = site
+            elif site is not None:
                 h2d = self._new(N, h2.W, h2.C)
-                di = len(self.masks)
-                self.masks.append(di)     # dropout site index: its seed is (step, site)
-                self._direct(self.fwd, lambda a=h2, o=h2d, di=di: _lib.check(self.lib.tq_dropout_apply(
-                    a.t.data_ptr(), o.t.data_ptr(), a.t.numel(), self._seed(di), self.p_drop, self._st()), "dropout"))
-                self.nodes.append(("mul", None, [h2], h2d, di))
+                self._direct(self.fwd, lambda a=h2, o=h2d, site=site: _lib.check(self.lib.tq_dropout_apply(
+                    a.t.data_ptr(), o.t.data_ptr(), a.t.numel(), self._host_seed(site), self.p_drop, self._st()), "dropout"))
+                self.nodes.append(("mul", None, [h2], h2d, site))
                 h2 = h2d
             skip = blk.skip_connection
             if isinstance(skip, nn.Identity):
@@ -390,6 +399,9 @@ class TrainStep1D:
                 d.dgamma, d.dbeta = st.view(st.G, mod.weight).data_ptr(), st.view(st.G, mod.bias).data_ptr()
                 d.dx_add0 = a0.t.data_ptr() if a0 is not None else None
                 d.dx_add1 = a1.t.data_ptr() if a1 is not None else None
+                site = self.drop_of_act.get(id(out))
+                if site is not None:
+                    d.drop_seed, d.drop_p, d.drop_site = self.drop_seed.data_ptr(), self.p_drop, site
                 if id(x0) in self.emb_of_act:   # x0 = conv1(h0) + e: de[n][c] = sum over positions of d(x0), fused here
                     d.dx_sum = self.de_all[:, self.emb_of_act[id(x0)]:].data_ptr()
                     d.dx_sum_ld = R
@@ -411,8 +423,8 @@ class TrainStep1D:
             elif kind == "mul":
                 dy = grad[id(out)]
                 dx = self._new(N, dy.W, dy.C)
-                self._direct(ops, lambda dy=dy, dx=dx, di=extra: _lib.check(lib.tq_dropout_apply(
-                    dy.t.data_ptr(), dx.t.data_ptr(), dy.t.numel(), self._seed(di), self.p_drop, self._st()), "dropout backward"))
+                self._direct(ops, lambda dy=dy, dx=dx, site=extra: _lib.check(lib.tq_dropout_apply(
+                    dy.t.data_ptr(), dx.t.data_ptr(), dy.t.numel(), self._host_seed(site), self.p_drop, self._st()), "dropout backward"))
                 grad[id(srcs[0])] = dx
         # ---- embedding MLPs (all ResBlocks have deposited their de into de_all by now)
         f32 = dict(device=self.dev, dtype=torch.float32)
@@ -476,6 +488,7 @@ class TrainStep1D:
         self.store.G.zero_()
         self.de_all.zero_()
         self.pass_count += 1
+        self.drop_seed.fill_((self.pass_count * 0x9E3779B1) & 0x7FFFFFFFFFFF)   # fresh dropout decisions every pass
         st = self._st()
         for f in self.fwd:
             f()
