@@ -75,7 +75,7 @@ def cond_grid(n: int):
 # clocks
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -90,7 +90,12 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc = None
 
-    def stop(self) -> dict:
+    def stop(self, t_begin: float | None = None, t_end: float | None = None) -> dict:
+        """Median SM clock / throttle reasons of the samples taken inside [t_begin, t_end] (time.time() stamps of the
+        timed region).  The process is started BEFORE the warm-up: nvidia-smi's start-up (NVML initialisation) must not
+        fall into the timed region -- it stalled one run's first timed steps by ~10 %."""
+        import datetime
+
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,19 +104,27 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
             out = ""
-        sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []   # (inside the timed window, sm, max sm, power, active reasons)
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                vals = (float(f[1]), float(f[2]), float(f[3]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+            inside = True
+            if t_begin is not None:
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    inside = t_begin - 0.05 <= ts <= t_end + 0.05
+                except ValueError:
+                    inside = True
+            rows.append((inside, *vals, [nm for nm, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
+        use = [r for r in rows if r[0]] or rows   # an unparsable / shifted clock must not leave the line without clocks
+        sm, mx, pw = [r[1] for r in use], [r[2] for r in use], [r[3] for r in use]
+        reasons = {nm for r in use for nm in r[4]}
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
@@ -332,16 +345,18 @@ def run_engine(args) -> None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1]), out
 
-    for _ in range(max(3, args.warmup)):
-        w = step_resident()
-    assert tuple(w.shape) == (hi - lo, 3, cfg.t) and bool(torch.isfinite(w).all()), "non-finite waveforms"
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(max(3, args.warmup)):
+        w = step_resident()
+    assert tuple(w.shape) == (hi - lo, 3, cfg.t) and bool(torch.isfinite(w).all()), "non-finite waveforms"
     _lib.launch_count_reset()
+    t_begin = time.time()
     ev_ms, wall_ms, _ = timed(step_resident, args.steps)
+    t_end = time.time()
     launches = _lib.launch_count()
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_begin, t_end) if rank == 0 else None
     step_e2e()  # warm the pinned-copy path
     e2e_ev_ms, e2e_wall_ms, _ = timed(step_e2e, args.steps)
     e2e_ms = max(e2e_ev_ms, e2e_wall_ms)  # the D2H at the end is host-synchronous: wall clock bounds it
