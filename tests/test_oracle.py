@@ -5,7 +5,7 @@ import torch
 
 from oracle import griffinlim_ref, torch_ref
 from oracle.weights import seeded_state_dict, shapes_of
-from tests.conftest import rel_l2
+from tests.conftest import GOLDEN, rel_l2
 from tests.helpers import CFG, arch, golden, unet_cfg
 
 TOL = 2e-5  # fp32 CPU restatement vs fp32 CPU reference: same ops, possibly different summation order
@@ -202,3 +202,31 @@ def test_classifier_embedding_and_frechet_distance_restatement():
     ref = float(g["fid"])
     assert abs(torch_ref.frechet_distance(a, b) - ref) < 1e-9 * abs(ref)
     assert abs(float(frechet_distance(a, b)) - ref) < 1e-9 * abs(ref)   # the product's host-side reduction
+
+
+def _train_golden():
+    z = np.load(GOLDEN / "train_step_1d.npz", allow_pickle=False)
+    return z
+
+
+def test_training_step_oracle_matches_reference_autograd():
+    """Autograd through the oracle's denoiser + the EDM loss against the UNMODIFIED reference's LightningEDM.step under
+    autograd (oracle/make_golden_train.py): loss, the L2 norm of all 310 parameter gradients, nine whole gradient tensors.
+    This pins the checker the GPU training parity tests use."""
+    import tqdne_b200 as tq
+
+    z = _train_golden()
+    shell = tq.LightningEDM(unet_cfg("1d"), {}, num_sampling_steps=18)
+    sd = _sd(shell, int(z["seed"]))
+    P = {k: v.clone().requires_grad_(not k.endswith("time_embed.W")) for k, v in sd.items()}
+    x, cond, sigma, noise = (torch.from_numpy(z[k]) for k in ("x", "cond", "sigma", "noise"))
+    pred = torch_ref.denoise(P, unet_cfg("1d"), x + noise * sigma[:, None, None], sigma, cond)
+    loss = ((pred - x) ** 2 * ((sigma**2 + 0.25) / (sigma * 0.5) ** 2)[:, None, None]).mean()
+    loss.backward()
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-5 * float(z["loss"])
+    names = [str(n) for n in z["grad_names"]]
+    norms = torch.tensor([float(P[n].grad.norm()) for n in names], dtype=torch.float64)
+    assert rel_l2(norms, torch.from_numpy(z["grad_norms"])) < 1e-4
+    for k in z.files:
+        if k.startswith("grad:"):
+            assert rel_l2(P[k[5:]].grad, torch.from_numpy(z[k])) < 1e-4, k

@@ -139,3 +139,25 @@ def test_lightning_module_training_step_entry_point():
     latent = tq.LightningEDM(unet_cfg("latent2d"), {}, autoencoder=tq.LightningAutoencoder(enc_cfg, dec_cfg, {})).cuda()
     with pytest.raises(NotImplementedError):
         latent.training_step({"signal": torch.zeros(1, 3, 128, 128, device="cuda")}, 0)
+
+
+def test_training_step_matches_reference_golden():
+    """The engine's step against the UNMODIFIED reference's LightningEDM.step under autograd (tests/golden/
+    train_step_1d.npz, oracle/make_golden_train.py): same weights, batch, sigma and noise."""
+    from tests.conftest import GOLDEN
+    from tqdne_b200.training import TrainStep1D
+
+    z = np.load(GOLDEN / "train_step_1d.npz")
+    edm, _ = _edm(seed=int(z["seed"]))
+    x, cond, sigma, noise = (torch.from_numpy(z[k]).cuda() for k in ("x", "cond", "sigma", "noise"))
+    step = TrainStep1D(edm, x.shape[0], x.shape[2], dropout=0.0)
+    loss = float(step.forward_backward(x, cond, sigma=sigma, noise=noise))
+    assert abs(loss - float(z["loss"])) < 1e-2 * float(z["loss"]), (loss, float(z["loss"]))
+    got = step.grads_by_name()
+    names = [str(n) for n in z["grad_names"]]
+    assert set(names) == {"unet." + k for k in got}
+    norms = torch.tensor([float(got[n[len("unet."):]].norm()) for n in names], dtype=torch.float64)
+    assert rel_l2(norms, torch.from_numpy(z["grad_norms"])) < 2e-2
+    for k in z.files:
+        if k.startswith("grad:"):
+            assert rel_l2(got[k[len("grad:unet."):]].cpu(), torch.from_numpy(z[k])) < 5e-2, k
