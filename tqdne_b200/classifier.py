@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from .blocks import Encoder
-from .engine import Plan, current_stream_ptr, nchw_to_nhwc, require_cuda  # noqa: F401
+from .engine import Plan, nchw_to_nhwc, require_cuda
 from .lightning_shim import LightningModule
 
 
