@@ -119,3 +119,38 @@ def test_reference_checkpoint_loads_without_the_reference_package(monkeypatch):
     ema = tq.LightningEDM.load_from_checkpoint(path, use_ema=True)
     k = "unet.time_mlp.0.weight"
     assert torch.equal(ema.state_dict()[k], raw["ema_state"][k]) and not torch.equal(ema.state_dict()[k], sd[k])
+
+
+def test_bench_clock_sampler_filters_to_the_timed_window():
+    """bench.ClockSampler (host logic): samples outside the timed window are ignored, throttle reasons are collected, and an
+    unparsable timestamp falls back to all samples instead of leaving the JSON line without clocks."""
+    import datetime
+    import time
+
+    import bench
+
+    now = time.time()
+    fmt = lambda t: datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]  # noqa: E731
+
+    class FakeProc:
+        def __init__(self, text):
+            self.text = text
+
+        def terminate(self):
+            pass
+
+        def communicate(self, timeout=None):
+            return self.text, ""
+
+    rows = [f"{fmt(now - 30)}, 345, 1965, 120.0, 0x0, Not Active, Not Active, Not Active, Not Active",
+            f"{fmt(now - 1.0)}, 1700, 1965, 950.0, 0x4, Not Active, Not Active, Not Active, Active",
+            f"{fmt(now - 0.6)}, 1690, 1965, 970.0, 0x4, Not Active, Not Active, Not Active, Active",
+            f"{fmt(now - 0.2)}, 1710, 1965, 960.0, 0x4, Not Active, Not Active, Not Active, Active"]
+    c = bench.ClockSampler(0)
+    c.proc = FakeProc("\n".join(rows))
+    got = c.stop(now - 2, now)
+    assert got["sm_mhz"] == 1700.0 and got["samples"] == 3 and got["reasons"] == ["sw_power_cap"] and got["power_w_max"] == 970.0
+    c.proc = FakeProc("\n".join(r.replace("/", "-") for r in rows))      # timestamp format nvidia-smi does not use
+    assert c.stop(now - 2, now)["samples"] == 4
+    c.proc = FakeProc("")
+    assert c.stop(now - 2, now)["reasons"] == ["no samples"]
