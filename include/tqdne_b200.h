@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 11
+#define TQ_ABI_VERSION 12
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -174,6 +174,11 @@ int tq_plan_add_spatial_mean(tq_plan* p, const float* x, int32_t N, int32_t P, i
  * per source: dw_ld = input channels of the whole layer (0 = cin), ci_off = this source's first channel.   */
 int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* db, int32_t N, int64_t L, int32_t cin,
                     int32_t cout, int32_t taps, int32_t dw_ld, int32_t ci_off, void* stream);
+/* 2-D counterpart (groundwork for training the 2-D UNets / autoencoder; nn.Conv2d, stride 1, padding "same"):
+ *   x [N,H,W,cin], dy [N,H,W,cout] bf16 channels-last; dw [cout, kh*kw, cin] fp32 ACCUMULATED INTO:
+ *   dw[co][ky*kw+kx][ci] += sum_{n,y,x} dy[n][y][x][co] * x[n][y+ky-kh/2][x+kx-kw/2][ci]; the bias gradient is not computed. */
+int tq_conv2d_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t H, int32_t W, int32_t cin, int32_t cout,
+                    int32_t kh, int32_t kw, void* stream);
 /* out[n*out_ld + c] += sum_p dy[n][p][c] (dy bf16 [N,P,C], out fp32 rows of length out_ld, 0 = C): gradient of the per-sample embedding
  * term a ResBlock adds after its first convolution (tqdne/unet.py:129-141).                          */
 int tq_sample_channel_sums(const void* dy, float* out, int32_t out_ld, int32_t N, int64_t P, int32_t C, void* stream);

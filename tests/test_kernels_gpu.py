@@ -860,3 +860,21 @@ def test_groupnorm_fused_dropout_forward_and_backward_agree():
     plan2.run()
     torch.cuda.synchronize()
     assert not torch.equal(y2.t, y.t)
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k", [(4, 32, 32, 128, 128, 3), (3, 4, 4, 512, 256, 3), (2, 16, 16, 256, 128, 3),
+                                              (1, 128, 128, 64, 64, 3), (5, 8, 8, 192, 64, 1), (2, 24, 40, 64, 128, 3)])
+def test_conv2d_wgrad_matches_autograd(N, H, W, cin, cout, k):
+    """tq_conv2d_wgrad (tcgen05, K = boxes of 64 positions, one shifted TMA box per tap, tap groups over the grid) against
+    autograd's weight gradient of F.conv2d(padding='same'); 4 x 4 images pack several samples into a K-step (3 samples
+    leave the box ragged), 24 x 40 is ragged in both image dimensions."""
+    from tqdne_b200.backward import conv2d_weight_grad
+
+    g = torch.Generator(device="cuda").manual_seed(H + W + k)
+    x = torch.randn(N, H, W, cin, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(N, H, W, cout, device="cuda", generator=g).to(torch.bfloat16)
+    dw = conv2d_weight_grad(x, dy, k, k)
+    torch.cuda.synchronize()
+    w = torch.zeros(cout, cin, k, k, device="cuda", dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double().permute(0, 3, 1, 2), w, padding=k // 2).backward(dy.double().permute(0, 3, 1, 2))
+    assert rel_l2(dw.view(cout, k, k, cin).permute(0, 3, 1, 2), w.grad) < 2e-5

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 11  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 12  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -123,6 +123,7 @@ SIGNATURES = {
     "tq_attention_backward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     "tq_sample_channel_sums": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _I32, _VP]),
     "tq_conv1d_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "tq_conv2d_wgrad": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "tq_rows_op": (C.c_int, [_VP, _VP, _VP, _I32, _I64, _I64, _I32, _VP]),
     "tq_linear_backward": (C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
     "tq_edm_noise": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _I32, _I32, _F, _VP]),

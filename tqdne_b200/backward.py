@@ -111,3 +111,17 @@ def attention_backward(qkv: Act, out: Act, dout: Act, heads: int) -> Act:
     _lib.check(_lib.lib().tq_attention_backward(qkv.t.data_ptr(), out.t.data_ptr(), dout.t.data_ptr(), dqkv.data_ptr(),
                                                 ws.data_ptr(), N, T, heads, Cc // heads, current_stream_ptr()), "attention_backward")
     return Act(dqkv, N, qkv.H, qkv.W, C3)
+
+
+def conv2d_weight_grad(x: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, dw: torch.Tensor | None = None) -> torch.Tensor:
+    """x: [N, H, W, cin] bf16, dy: [N, H, W, cout] bf16 (channels-last, channel counts multiples of 64) ->
+    dw [cout, kh*kw, cin] fp32 (+= if given).  Reference layout: dw.view(cout, kh, kw, cin).permute(0, 3, 1, 2)."""
+    require_cuda(x, "x")
+    N, H, W, cin = x.shape
+    cout = dy.shape[3]
+    assert dy.shape[:3] == (N, H, W) and x.dtype == dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+    if dw is None:
+        dw = torch.zeros(cout, kh * kw, cin, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().tq_conv2d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, cin, cout, kh, kw, current_stream_ptr()),
+               "conv2d_wgrad")
+    return dw
