@@ -61,3 +61,20 @@ for cin, cout, L in [(256, 256, 1016), (256, 256, 508), (512, 256, 1016), (128, 
     print(f"conv1d {cin:4d}->{cout:4d} k5 L={L:5d} N={N}: fwd {t_f * 1e6:7.1f} us {flops / t_f / 1e12:7.1f} TF/s | dgrad {t_d * 1e6:7.1f} us "
           f"{flops / t_d / 1e12:7.1f} TF/s | wgrad(+bias) {t_w * 1e6:7.1f} us {flops / t_w / 1e12:7.1f} TF/s | GN+SiLU fwd "
           f"{t_g * 1e6:6.1f} us {4 * el / t_g / 1e9:6.0f} GB/s | bwd {t_gb * 1e6:6.1f} us {10 * el / t_gb / 1e9:6.0f} GB/s", flush=True)
+
+# ---- 2-D weight gradient on the latent UNet's top shapes (batch 256), against the forward igemm of the same layer
+for cin, cout, H in [(128, 128, 32), (256, 256, 16), (512, 512, 8), (512, 512, 4)]:
+    Nb = 256
+    x = torch.randn(Nb, H, H, cin, device=dev).to(dt)
+    dy = torch.randn(Nb, H, H, cout, device=dev).to(dt)
+    w = (torch.randn(cout, cin, 3, 3, device=dev) / math.sqrt(cin * 9)).to(dt).float()
+    flops = 2.0 * Nb * H * H * cin * cout * 9
+    with torch.cuda.stream(s):
+        pf = Plan(dev, dt)
+        pf.conv(pack_conv(w, None, [cin], dt), [Act(x.reshape(-1), Nb, H, H, cin)], dims=2, stats=True)
+        dw = torch.zeros(cout, 9, cin, device=dev)
+        pf.run()
+    t_f = timed(pf.run)
+    t_w = timed(lambda: bw.conv2d_weight_grad(x, dy, 3, 3, dw))
+    print(f"conv2d {cin:4d}->{cout:4d} 3x3 @{H}x{H} N={Nb}: fwd {t_f * 1e6:7.1f} us {flops / t_f / 1e12:7.1f} TF/s | wgrad {t_w * 1e6:7.1f} us "
+          f"{flops / t_w / 1e12:7.1f} TF/s", flush=True)
