@@ -11,4 +11,8 @@ Pinning status
   * Griffin-Lim (librosa 0.11.0 `griffinlim`, third-party, absent from /root/reference and from this image):
     PARITY UNPINNED.  oracle/griffinlim_ref.py restates the published algorithm; its STFT/iSTFT are pinned
     against torch.stft/istft, the loop is not pinned against librosa itself.
+  * Training step (autograd through `torch_ref.denoise` + the EDM loss), evaluation classifier embedding and Frechet
+    distance: PINNED against the reference's own `LightningEDM.step` under autograd, `LithningClassifier.embed / forward`
+    and `tqdne.metric.frechet_distance` (oracle/make_golden_train.py, oracle/make_golden_classifier.py).
+`tools/bench_train.py --impl reference` (the CPU arm of the training measurement) is the one other executor of this package.
 """
