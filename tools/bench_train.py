@@ -92,8 +92,17 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    dist.init_process_group("nccl", device_id=dev)
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)          # NCCL's version banner goes to stderr, stdout keeps the one JSON line
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
 
 cfg = MovingAverageEnvelopeConfig()
 edm = tq.LightningEDM(tq.get_1d_unet_config(cfg, 6, 6), {"learning_rate": 1e-4, "max_steps": 100000, "eta_min": 0.0},
