@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 12
+#define TQ_ABI_VERSION 13
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -95,26 +95,34 @@ typedef struct {
     int64_t out_sn, out_sy, out_sx;   /* element strides of the output                           */
     int64_t out_class_off[4];         /* element offset of each parity class                     */
     int32_t block_n;          /* 0 = auto, else 64 / 128 / 256                                   */
-    float*  stats;            /* device [N][cout][2] fp32 or NULL: per-(sample, channel) sum and  *
-                               * sum of squares of the STORED output, accumulated with atomics in  *
-                               * the epilogue (feeds tq_gn_desc.stats0/1 of the consuming          *
-                               * GroupNorm: the normalisation never re-reads the tensor for its    *
-                               * statistics).  The caller zeroes it before the conv runs           *
-                               * (tq_plan_add_memset).  bf16 outputs only.                         */
+    float*  stats;            /* device [N][stats_parts][cout][2] fp32 or NULL: (sum, sum of squares) of  *
+                               * the STORED output per sample, PART and channel, written in the epilogue  *
+                               * with plain stores -- a part is one output tile of the sample, every slot  *
+                               * has exactly one writer, nothing is accumulated with atomics.  Feeds      *
+                               * tq_gn_desc.stats0/1 of the consuming GroupNorm, which adds the parts in   *
+                               * index order: the normalisation never re-reads the tensor for its         *
+                               * statistics and the result is bit-reproducible.  Allocate it zero-filled   *
+                               * (slots a geometry never writes stay zero).  bf16 outputs only on the      *
+                               * tensor path.                                                              */
     int32_t cta_group;        /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row   *
                                * tile (tcgen05.mma.cta_group::2)                                    */
+    int32_t stats_parts;      /* parts dimension of `stats`: must equal tq_conv_stats_parts(d)      */
 } tq_conv_desc;
 int tq_plan_add_conv(tq_plan* p, const tq_conv_desc* d);
+/* number of statistics parts per sample the kernel chosen for this geometry (dtype, H, W, num_classes) writes */
+int32_t tq_conv_stats_parts(const tq_conv_desc* d);
 
 /* ---- GroupNorm(32) [+ SiLU] over a (virtual) channel concat -------------------------------- *
  * Replaces: GroupNorm32 / normalization (tqdne/nn.py:11-13,90-105) + nn.SiLU in in_layers /
  * out_layers (unet.py:85-103, blocks.py:238-250), attention norm (blocks.py:126), `out`
  * (unet.py:354-356), fed by th.cat([h, hs.pop()], dim=1) (unet.py:396) without materialising it.
  * x0:[N,P,C0] (+ x1:[N,P,C1]) -> y:[N,P,C0+C1]; stats in fp32; eps as given; 32 groups.
- * `ws` is a caller-provided fp32 scratch of 2*N*(C0+C1) floats, used when the per-channel sums  *
- * are not supplied: stats0 / stats1 ([N][C0][2], [N][C1][2], written by the producing conv's    *
+ * stats0 / stats1 ([N][parts0][C0][2], [N][parts1][C1][2], written by the producing conv's       *
  * epilogue, tq_conv_desc.stats) skip the statistics pass, leaving ONE streaming pass (2 B read  *
- * + 2 B written per element in bf16).  Both or neither must be given for a two-source norm.     */
+ * + 2 B written per element in bf16).  Both or neither must be given for a two-source norm.     *
+ * `ws` is a caller-provided fp32 scratch of tq_groupnorm_ws_floats(d) floats (0 for most fused  *
+ * norms): the stand-alone statistics pass and, for tensors cut into many parts, the per-sample  *
+ * group reduction live there.  No atomics anywhere: results are bit-reproducible.               */
 typedef struct {
     int32_t dtype;         /* TQ_BF16 | TQ_F32 for x0, x1, y                                      */
     int32_t N, P, C0, C1;  /* P = H*W positions                                                   */
@@ -125,11 +133,14 @@ typedef struct {
     void*   y;
     float*  ws;
     const float* stats0; const float* stats1;
+    int32_t parts0, parts1; /* parts dimension of stats0 / stats1 (tq_conv_desc.stats_parts of the producers) */
     /* training only (bf16): y = dropout(act(GroupNorm(x))), nn.Dropout of ResBlock.out_layers (tqdne/unet.py:100-108).
      * The decision of element i is hash(*drop_seed + site, i) < drop_p; NULL / 0 = no dropout (every sampling plan).   */
     const uint64_t* drop_seed; float drop_p; int32_t drop_site;
 } tq_gn_desc;
 int tq_plan_add_groupnorm(tq_plan* p, const tq_gn_desc* d);
+/* fp32 scratch floats `ws` must hold for this op on the current device (0 = none needed), < 0 on bad arguments */
+int64_t tq_groupnorm_ws_floats(const tq_gn_desc* d);
 
 /* ---- attention core -------------------------------------------------------------------------- *
  * Replaces: QKVAttention.forward (tqdne/blocks.py:156-190).  qkv:[N,T,3*heads*d] channels-last
@@ -193,7 +204,8 @@ typedef struct {
     const void* x0; const void* x1; const void* dy;
     const float* gamma; const float* beta;
     float eps; int32_t silu;
-    const float* stats0; const float* stats1;
+    const float* stats0; const float* stats1;   /* [N][parts0][C0][2], [N][parts1][C1][2] (tq_conv_desc.stats) */
+    int32_t parts0, parts1;
     float* ws;
     void* dx0; void* dx1;
     float* dgamma; float* dbeta;

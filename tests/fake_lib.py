@@ -14,6 +14,8 @@ class FakeLib:
             self.calls.append(name)
             if name == "tq_plan_create":
                 return 1
+            if name == "tq_conv_stats_parts":
+                return 3
             if name == "tq_plan_num_ops":
                 return sum(1 for c in self.calls if c.startswith("tq_plan_add_"))
             if name == "tq_plan_add_conv":
@@ -26,10 +28,10 @@ class FakeLib:
                     srcs=[(d.srcs[i].N, d.srcs[i].H, d.srcs[i].W, d.srcs[i].C, d.srcs[i].sn, d.srcs[i].sy, d.srcs[i].sx)
                           for i in range(d.num_srcs)],
                     out_strides=(d.out_sn, d.out_sy, d.out_sx), class_off=list(d.out_class_off), out_dtype=d.out_dtype,
-                    has_emb=bool(d.emb), has_res=bool(d.residual), stats=d.stats))
+                    has_emb=bool(d.emb), has_res=bool(d.residual), stats=d.stats, stats_parts=d.stats_parts))
             if name == "tq_plan_add_groupnorm":
                 d = args[1]._obj if hasattr(args[1], "_obj") else args[1].contents
-                self.gns.append(dict(N=d.N, P=d.P, C0=d.C0, C1=d.C1, stats0=d.stats0, stats1=d.stats1, ws=d.ws))
+                self.gns.append(dict(N=d.N, P=d.P, C0=d.C0, C1=d.C1, stats0=d.stats0, stats1=d.stats1, ws=d.ws, parts0=d.parts0, parts1=d.parts1))
             if name == "tq_last_error":
                 return b""
             return 0

@@ -34,13 +34,15 @@ def test_latent_unet_lowering_op_counts_and_flops(fake):
     # 16.979 GFLOP per sample per call
     assert abs(p.flops / 4 / 16.979e9 - 1) < 0.01
     assert p.out.C == 8 and p.out.t.dtype == torch.float32 and p.cin_pad == 64
-    # every GroupNorm input is a conv output: its statistics come from that conv's epilogue (no stats pass),
-    # each from its own buffer, and the arena is cleared by memset op(s) at the front of the plan
+    # every GroupNorm input is a conv output: its statistics come from that conv's epilogue (no stats pass), each from
+    # its own buffer of per-tile partial sums (plain stores, nothing to clear: no memset op, no atomics)
     produced = {c["stats"] for c in fake.convs if c["stats"]}
     assert len(produced) == sum(1 for c in fake.convs if c["stats"])
+    assert all(c["stats_parts"] == 3 for c in fake.convs if c["stats"])   # what the (fake) tq_conv_stats_parts said
     for g in fake.gns:
         assert g["stats0"] in produced and (g["C1"] == 0 or g["stats1"] in produced) and not g["ws"]
-    assert _count(fake, "tq_plan_add_memset") >= 1
+        assert g["parts0"] == 3 and (g["C1"] == 0 or g["parts1"] == 3)
+    assert _count(fake, "tq_plan_add_memset") == 0
     for c in fake.convs:
         assert c["ktot"] % 64 == 0 and c["cout_pad"] % 64 == 0
         kbs = sorted(s[4] for s in c["slices"][: c["num_slices"]])

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 12  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 13  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -52,6 +52,7 @@ class TqConvDesc(C.Structure):
         ("block_n", C.c_int32),
         ("stats", C.c_void_p),
         ("cta_group", C.c_int32),
+        ("stats_parts", C.c_int32),
     ]
 
 
@@ -66,6 +67,7 @@ class TqGnDesc(C.Structure):
         ("y", C.c_void_p),
         ("ws", C.c_void_p),
         ("stats0", C.c_void_p), ("stats1", C.c_void_p),
+        ("parts0", C.c_int32), ("parts1", C.c_int32),
         ("drop_seed", C.c_void_p), ("drop_p", C.c_float), ("drop_site", C.c_int32),
     ]
 
@@ -92,8 +94,8 @@ class TqLinearDesc(C.Structure):
 class TqGnBwdDesc(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("N", C.c_int32), ("P", C.c_int32), ("C0", C.c_int32), ("C1", C.c_int32),
                 ("x0", C.c_void_p), ("x1", C.c_void_p), ("dy", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
-                ("eps", C.c_float), ("silu", C.c_int32), ("stats0", C.c_void_p), ("stats1", C.c_void_p), ("ws", C.c_void_p),
-                ("dx0", C.c_void_p), ("dx1", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("eps", C.c_float), ("silu", C.c_int32), ("stats0", C.c_void_p), ("stats1", C.c_void_p), ("parts0", C.c_int32), ("parts1", C.c_int32),
+                ("ws", C.c_void_p), ("dx0", C.c_void_p), ("dx1", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
                 ("dx_add0", C.c_void_p), ("dx_add1", C.c_void_p), ("dx_sum", C.c_void_p), ("dx_sum_ld", C.c_int32),
                 ("drop_seed", C.c_void_p), ("drop_p", C.c_float), ("drop_site", C.c_int32)]
 
@@ -114,7 +116,9 @@ SIGNATURES = {
     "tq_plan_op_name": (C.c_char_p, [_VP, C.c_int]),
     "tq_plan_add_memset": (C.c_int, [_VP, _VP, _I64, _I32]),
     "tq_plan_add_conv": (C.c_int, [_VP, C.POINTER(TqConvDesc)]),
+    "tq_conv_stats_parts": (_I32, [C.POINTER(TqConvDesc)]),
     "tq_plan_add_groupnorm": (C.c_int, [_VP, C.POINTER(TqGnDesc)]),
+    "tq_groupnorm_ws_floats": (_I64, [C.POINTER(TqGnDesc)]),
     "tq_plan_add_attention": (C.c_int, [_VP, C.POINTER(TqAttnDesc)]),
     "tq_plan_add_linear": (C.c_int, [_VP, C.POINTER(TqLinearDesc)]),
     "tq_plan_add_fourier": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),

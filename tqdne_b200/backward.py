@@ -77,6 +77,7 @@ def groupnorm_silu_backward(x0: Act, dy: Act, gamma: torch.Tensor, beta: torch.T
     d.x0, d.x1, d.dy = x0.t.data_ptr(), (x1.t.data_ptr() if x1 is not None else None), dy.t.data_ptr()
     d.gamma, d.beta, d.eps, d.silu = g32.data_ptr(), b32.data_ptr(), eps, 1 if silu else 0
     d.stats0, d.stats1 = x0.stats.data_ptr(), (x1.stats.data_ptr() if x1 is not None else None)
+    d.parts0, d.parts1 = x0.stats_parts, (x1.stats_parts if x1 is not None else 1)
     d.ws, d.dx0, d.dx1 = ws.data_ptr(), dx0.data_ptr(), (dx1.data_ptr() if dx1 is not None else None)
     d.dgamma, d.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
     d.dx_sum, d.dx_sum_ld = None, 0

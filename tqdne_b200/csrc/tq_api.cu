@@ -23,14 +23,16 @@ void set_error(const char* fmt, ...) {
 }
 
 int device_sm_count() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            sms <= 0)
-            sms = 148;  // B200
+    // per CURRENT device (plans are built under the device guard of the module that owns them), cached per ordinal
+    static int cache[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;  // B200
+    if (cache[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cache[dev] = sms;
     }
-    return sms;
+    return cache[dev];
 }
 
 static void drop_graph(tq_plan* p) {
@@ -155,14 +157,21 @@ int tq_plan_add_memset(tq_plan* p, void* ptr, int64_t bytes, int32_t at_front) {
     return 0;
 }
 
+static bool conv_on_tensor_path(const tq_conv_desc& d) {
+    const char* force = getenv("TQ_FORCE_SIMT");
+    return d.dtype == TQ_BF16 && !(force && force[0] == '1');
+}
 int tq_plan_add_conv(tq_plan* p, const tq_conv_desc* d) {
     TQ_CHECK(p && d, "null argument");
     TQ_CHECK(d->slices != nullptr && d->weights != nullptr && d->out != nullptr, "conv: null pointer");
     TQ_CHECK(d->N > 0 && d->H > 0 && d->W > 0, "conv: empty grid");
     drop_graph(p);
-    const char* force = getenv("TQ_FORCE_SIMT");
-    if (d->dtype == TQ_BF16 && !(force && force[0] == '1')) return build_conv_sm100(p->ops, *d);
+    if (conv_on_tensor_path(*d)) return build_conv_sm100(p->ops, *d);
     return build_conv_simt(p->ops, *d);
+}
+int32_t tq_conv_stats_parts(const tq_conv_desc* d) {
+    if (!d || d->H <= 0 || d->W <= 0 || d->num_classes <= 0) return -1;
+    return conv_on_tensor_path(*d) ? conv_stats_parts_sm100(*d) : conv_stats_parts_simt(*d);
 }
 int tq_plan_add_groupnorm(tq_plan* p, const tq_gn_desc* d) {
     TQ_CHECK(p && d, "null argument");

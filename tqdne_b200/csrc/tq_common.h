@@ -88,6 +88,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // builders implemented in the kernel translation units; each appends >= 1 Op
 int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d);
 int build_conv_simt(std::vector<Op>& ops, const tq_conv_desc& d);
+// statistics parts per sample (tq_conv_desc.stats) each conv kernel writes for a geometry
+int conv_stats_parts_sm100(const tq_conv_desc& d);
+int conv_stats_parts_simt(const tq_conv_desc& d);
 int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d);
 int build_attention(std::vector<Op>& ops, const tq_attn_desc& d);
 // tcgen05 attention (tq_attn_sm100.cu): bf16, head dim 64 / 128, 32 < T <= 512, all keys resident in shared memory

@@ -29,7 +29,9 @@ struct SimtParams {
     void* out;
     long long out_sn, out_sy, out_sx;
     long long out_class_off[4];
-    float* stats;  // [N][cout][2] or nullptr (same meaning as in the tensor-core kernel)
+    float* stats;  // [N][parts][cout][2] or nullptr (same meaning as in the tensor-core kernel; a part = one 64-row tile)
+    int parts, parts_per_class;
+    long long P;   // rows of one sample inside a class: H * W
 };
 
 __device__ __forceinline__ float to_f(float v) { return v; }
@@ -90,35 +92,73 @@ __global__ void __launch_bounds__(256) igemm_simt_kernel(const SimtParams p) {
         __syncthreads();
     }
 
+    // stored values of the tile, kept for the statistics pass (As is free after the last k loop)
+    float (*tile)[68] = As;  // [row][channel]
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const long long m = m0 + ty * 4 + i;
-        if (m >= p.M) continue;
-        const int x = (int)(m % p.W);
-        const long long r = m / p.W;
+        const bool mv = m < p.M;
+        const int x = mv ? (int)(m % p.W) : 0;
+        const long long r = mv ? m / p.W : 0;
         const int y = (int)(r % p.H);
         const int n = (int)(r / p.H);
         const long long off = p.out_class_off[cls] + (long long)n * p.out_sn + (long long)y * p.out_sy + (long long)x * p.out_sx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = n0 + tx * 4 + j;
-            if (c >= p.cout) continue;
-            float o = acc[i][j];
-            if (p.bias) o += p.bias[c];
-            if (p.emb) o += p.emb[(long long)n * p.emb_ld + c];
-            if (p.residual) o += to_f(static_cast<const T*>(p.residual)[off + c]);
-            if constexpr (OUT_F32) static_cast<float*>(p.out)[off + c] = o;
-            else {
-                const __nv_bfloat16 ob = __float2bfloat16_rn(o);
-                static_cast<__nv_bfloat16*>(p.out)[off + c] = ob;
-                o = __bfloat162float(ob);
+            float o = 0.f;
+            if (mv && c < p.cout) {
+                o = acc[i][j];
+                if (p.bias) o += p.bias[c];
+                if (p.emb) o += p.emb[(long long)n * p.emb_ld + c];
+                if (p.residual) o += to_f(static_cast<const T*>(p.residual)[off + c]);
+                if constexpr (OUT_F32) static_cast<float*>(p.out)[off + c] = o;
+                else {
+                    const __nv_bfloat16 ob = __float2bfloat16_rn(o);
+                    static_cast<__nv_bfloat16*>(p.out)[off + c] = ob;
+                    o = __bfloat162float(ob);
+                }
             }
-            if (p.stats) atomicAdd(reinterpret_cast<float2*>(p.stats) + (long long)n * p.cout + c, make_float2(o, o * o));
+            if (p.stats) tile[ty * 4 + i][tx * 4 + j] = o;
+        }
+    }
+    if (p.stats == nullptr) return;
+    __syncthreads();
+    // GroupNorm statistics of the consumer: thread c walks the 64 rows of its channel in order and leaves one
+    // (sum, sum of squares) per sample the tile touches in the slot [n][part][c], part = tile index relative to the
+    // sample's first tile -- one writer per slot, a fixed summation order, no atomics (bit-reproducible)
+    if (tid < 64) {
+        const int c = n0 + tid;
+        if (c < p.cout) {
+            float sm = 0.f, sq = 0.f;
+            long long cur_n = m0 / p.P;
+            for (int r = 0; r < 64; ++r) {
+                const long long m = m0 + r;
+                if (m >= p.M) break;
+                const long long n = m / p.P;
+                if (n != cur_n) {
+                    const long long part = cls * p.parts_per_class + (blockIdx.x - (cur_n * p.P) / 64);
+                    *reinterpret_cast<float2*>(p.stats + ((cur_n * p.parts + part) * p.cout + c) * 2) = make_float2(sm, sq);
+                    sm = sq = 0.f;
+                    cur_n = n;
+                }
+                const float o = tile[r][tid];
+                sm += o;
+                sq = fmaf(o, o, sq);
+            }
+            if (cur_n * p.P < p.M) {
+                const long long part = cls * p.parts_per_class + (blockIdx.x - (cur_n * p.P) / 64);
+                *reinterpret_cast<float2*>(p.stats + ((cur_n * p.parts + part) * p.cout + c) * 2) = make_float2(sm, sq);
+            }
         }
     }
 }
 
 }  // namespace
+
+// 64-row tiles a sample of P rows can touch: P / 64 when the samples are tile aligned, else one more than the span
+static int simt_parts_per_class(long long P) { return P % 64 == 0 ? (int)(P / 64) : (int)((P - 1) / 64) + 2; }
+int conv_stats_parts_simt(const tq_conv_desc& d) { return d.num_classes * simt_parts_per_class((long long)d.H * d.W); }
 
 int build_conv_simt(std::vector<Op>& ops, const tq_conv_desc& d) {
     TQ_CHECK(d.dtype == TQ_BF16 || d.dtype == TQ_F32, "simt igemm: bad dtype");
@@ -156,7 +196,13 @@ int build_conv_simt(std::vector<Op>& ops, const tq_conv_desc& d) {
     p->out_sn = d.out_sn; p->out_sy = d.out_sy; p->out_sx = d.out_sx;
     for (int i = 0; i < 4; ++i) p->out_class_off[i] = d.out_class_off[i];
     p->stats = d.stats;
+    p->P = (long long)d.H * d.W;
+    p->parts_per_class = simt_parts_per_class(p->P);
+    p->parts = d.num_classes * p->parts_per_class;
     TQ_CHECK(d.stats == nullptr || (reinterpret_cast<uintptr_t>(d.stats) & 7) == 0, "conv statistics buffer must be 8 B aligned");
+    TQ_CHECK(d.stats == nullptr || d.stats_parts == p->parts,
+             "conv statistics: stats_parts = %d, this geometry writes %d parts per sample (tq_conv_stats_parts)", d.stats_parts,
+             p->parts);
 
     dim3 grid((unsigned)((p->M + 63) / 64), (unsigned)(d.cout_pad / 64), (unsigned)d.num_classes);
     TQ_CHECK(grid.y <= 65535, "too many output channels for the simt grid");

@@ -77,7 +77,9 @@ struct alignas(64) IgemmParams {
     void* out;
     long long out_sn, out_sy, out_sx;
     long long out_class_off[4];
-    float* stats;  // [N][cout][2] per-(sample, channel) sum / sum of squares, or nullptr
+    float* stats;  // [N][parts][cout][2] per-(sample, tile, channel) sum / sum of squares, or nullptr
+    int parts;     // num_classes * tiles_x * tiles_y: 128-row tiles per sample
+    int wps;       // epilogue warps (32 rows each) that share one sample inside a tile: 1, 2 or 4
     int seg;       // rows of one sample inside an epilogue warp: min(32, bw*bh)
     unsigned long long* prof;  // debug (TQ_IGEMM_PROF=1): [grid][16] cycle counters, else nullptr
     int probe;  // debug (TQ_IGEMM_PROBE bit mask, results are garbage): 1 = no TMA operand loads, 2 = no MMAs,
@@ -123,6 +125,7 @@ struct Cfg {
 
 struct TileCoord {
     int cls, n_tile, x0, y0, n0;
+    int part;  // statistics slot of this tile inside its samples: cls * tiles_x * tiles_y + ty * tiles_x + tx
 };
 // pair-level tile index -> coordinates of THIS CTA's 128-row tile (rank selects the half of the 256-row tile)
 template <int CG>
@@ -140,6 +143,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile,
     t.x0 = tx * p.bw;
     t.y0 = ty * p.bh;
     t.n0 = tn * p.bn;
+    t.part = (t.cls * p.tiles_y + ty) * p.tiles_x + tx;
     return t;
 }
 
@@ -155,6 +159,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+// named barrier over `count` threads (the four epilogue warps that hold one column half of a tile)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    // immediate barrier ids (a register id makes ptxas reserve all 16 hardware barriers)
+    if (id == 1) asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"r"(count) : "memory");
 }
 
 template <int BN, int CG, bool OUT_F32>
@@ -418,6 +428,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                     unit_on[u] = (BN >= 128 || half == 0) && (t.n_tile * BN + unit_col[u]) < p.cout;
                     n_on += unit_on[u] ? 1 : 0;
                 }
+                // statistics over tiles whose samples span several epilogue warps are read ACROSS the staging buffers
+                // of the four warps of a column half: nobody may refill a buffer before all four have finished reading
+                const bool xstats = p.stats != nullptr && p.wps > 1 && n_on > 0;
+                if (xstats) named_bar_sync(1 + half, 128);
                 // staging buffers are free once the previous tile's TMA stores have finished reading them
                 {
                     const long long t0 = prof ? clk() : 0;
@@ -527,10 +541,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                         bulk_commit();
                     }
                     TQ_EPI_T(4);
-                    if (p.stats != nullptr) {
-                        // GroupNorm statistics of the consumer: lane l owns channels cg0 + 2l, 2l+1 (one 32-bit word
-                        // per row of the staging buffer); rows of one sample are p.seg consecutive rows
-                        // (bw, bh are powers of two, so a warp's 32 rows are 32 / seg whole-sample segments)
+                    if (p.stats != nullptr && p.wps == 1) {
+                        // GroupNorm statistics of the consumer, samples of <= 32 rows: a segment of this warp's rows is a
+                        // whole (tile of a) sample.  Lane l owns channels cg0 + 2l, 2l+1 (one 32-bit word per row of the
+                        // staging buffer); the slot [n][part][c] has exactly one writer: plain stores, no atomics.
                         const uint32_t wsel = lane >> 2, wlo = (lane & 3) << 2;
                         const int ns0 = t.n0 + (q * 32) / rows_per_sample;
                         const int nseg = 32 / p.seg;
@@ -559,9 +573,58 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                             }
                             const int ns = ns0 + (nseg > 1 ? sg : 0);
                             if (ns < p.N)
-                                atomicAdd(reinterpret_cast<float4*>(p.stats + ((long long)ns * p.cout + cg0 + 2 * lane) * 2),
-                                          make_float4(s0, q0, s1, q1));
+                                *reinterpret_cast<float4*>(p.stats + (((long long)ns * p.parts + t.part) * p.cout + cg0 + 2 * lane) * 2) =
+                                    make_float4(s0, q0, s1, q1);
                         }
+                    }
+                    TQ_EPI_T(5);
+                }
+                if (xstats) {
+                    // samples of 64 / 128 rows inside the tile: the wps = 2 / 4 warps that hold one sample split its 64
+                    // channels between them and each sums ITS channels over all wps x 32 rows, reading the staging buffers
+                    // of the whole group (a fixed order: deterministic, and no exchange buffer is needed).  Lane =
+                    // (row group rg = source warp, channel pair cp); the row rotation per rg keeps the four row groups on
+                    // different shared-memory banks (SWIZZLE_128B: the bank depends on chunk ^ (row & 7)).
+                    named_bar_sync(1 + half, 128);  // all four staging buffers of this column half are written
+                    const int wps = p.wps, cpn = 32 / wps;
+                    const int cp = lane % cpn, rg = lane / cpn;
+                    const int qs = q % wps, qg = q - qs;
+                    const int idx = qs * cpn + cp;  // channel pair inside the 64-channel unit
+                    const uint32_t chunk = idx >> 2, wlo = (idx & 3) << 2;
+                    const uint32_t sbuf = epi_base + ((half * 4 + qg + rg) * C::UNITS) * EPI_BUF_BYTES;
+                    const int rot = (8 / wps) * rg;
+                    const int ns = t.n0 + qg / wps;
+#pragma unroll
+                    for (int u = 0; u < C::UNITS; ++u) {
+                        if (!unit_on[u]) continue;  // uniform over the four warps of the half
+                        const uint32_t buf = sbuf + u * EPI_BUF_BYTES;
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int r2 = 0; r2 < 32; r2 += 8) {
+                            uint32_t wv[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int rr = (r2 + k + rot) & 31;
+                                wv[k] = lds32(buf + rr * 128 + (((chunk ^ (rr & 7)) << 4) | wlo));
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&wv[k]);
+                                const float f0 = __low2float(b2), f1 = __high2float(b2);
+                                s0 += f0; q0 = fmaf(f0, f0, q0);
+                                s1 += f1; q1 = fmaf(f1, f1, q1);
+                            }
+                        }
+                        for (int o = cpn; o < 32; o <<= 1) {
+                            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                            q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                            q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+                        }
+                        const int cg0 = t.n_tile * BN + unit_col[u];
+                        if (rg == 0 && ns < p.N)
+                            *reinterpret_cast<float4*>(p.stats + (((long long)ns * p.parts + t.part) * p.cout + cg0 + 2 * idx) * 2) =
+                                make_float4(s0, q0, s1, q1);
                     }
                     TQ_EPI_T(5);
                 }
@@ -764,6 +827,12 @@ void tile_shape_for(int H, int W, int* bw, int* bh, int* bn) {
     *bn = 128 / (w * h);
 }
 
+int conv_stats_parts_sm100(const tq_conv_desc& d) {
+    int bw, bh, bn;
+    tile_shape_for(d.H, d.W, &bw, &bh, &bn);
+    return d.num_classes * ((d.W + bw - 1) / bw) * ((d.H + bh - 1) / bh);
+}
+
 int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     TQ_CHECK(d.dtype == TQ_BF16, "sm100 igemm needs bf16 operands");
     TQ_CHECK(d.num_srcs >= 1 && d.num_srcs <= 4, "num_srcs out of range");
@@ -945,9 +1014,14 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
     {
         const int rows = p->bw * p->bh;
         p->seg = rows < 32 ? rows : 32;
+        p->wps = rows <= 32 ? 1 : rows / 32;
+        p->parts = d.num_classes * p->tiles_x * p->tiles_y;
     }
     TQ_CHECK(d.stats == nullptr || (reinterpret_cast<uintptr_t>(d.stats) & 15) == 0,
              "conv statistics buffer must be 16 B aligned");
+    TQ_CHECK(d.stats == nullptr || d.stats_parts == p->parts,
+             "conv statistics: stats_parts = %d, this geometry writes %d parts per sample (tq_conv_stats_parts)", d.stats_parts,
+             p->parts);
 
     const int clusters = p->total_tiles < sms / cg ? p->total_tiles : sms / cg;
     const int grid = clusters * cg;

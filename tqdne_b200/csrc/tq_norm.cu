@@ -4,16 +4,18 @@
 // th.cat([h, skip], dim=1) (tqdne/unet.py:396) -- the concat is never materialised before the norm.
 //
 // HBM-bound.  The per-(sample, channel) sum / sum-of-squares normally arrive from the epilogue of the
-// convolution that produced the tensor (tq_conv_desc.stats), so the norm is ONE streaming pass:
-// affine + SiLU, 16 B vector loads, four independent loads in flight per thread.  A stand-alone
-// statistics pass (block reduction + one fp32 atomic per channel per block) remains for inputs that
-// did not come out of a conv.  Per-channel partials make groups that straddle the concat boundary
-// (C = 768, 384, 192) free.
+// convolution that produced the tensor (tq_conv_desc.stats: per-tile partial sums, plain stores), so the
+// norm is ONE streaming pass: affine + SiLU, 16 B vector loads, four independent loads in flight per
+// thread.  A stand-alone statistics pass (block reduction, one partial slot per block) remains for inputs
+// that did not come out of a conv.  Nothing is accumulated with atomics: the partials are added in index
+// order (tq_gnstats.cuh), so two runs of the same inputs are bit-identical.  Per-channel partials make
+// groups that straddle the concat boundary (C = 768, 384, 192) free.
 #include <cuda_bf16.h>
 
 #include <memory>
 
 #include "tq_common.h"
+#include "tq_gnstats.cuh"
 
 namespace tq {
 namespace {
@@ -27,9 +29,11 @@ struct GnParams {
     float eps;
     int silu;
     void* y;
-    float* ws;  // [N][C0+C1][2]
-    const float* st0;  // [N][C0][2]  (== ws when the statistics pass ran)
-    const float* st1;  // [N][C1][2]
+    float* ws;  // statistics pass: [N][chunks][C0][2] then [N][chunks][C1][2]; finalize pass: [N][32][2] behind it
+    const float* st0;  // [N][parts0][C0][2]  (== ws when the statistics pass ran)
+    const float* st1;  // [N][parts1][C1][2]
+    int parts0, parts1;
+    const float* gfinal;  // [N][32][2] group mean / rstd from gn_finalize_kernel (many parts), or nullptr
     int chunks;
     const unsigned long long* drop_seed;  // training only: dropout after the activation (nullptr = none)
     float drop_p;
@@ -103,7 +107,7 @@ __device__ void stats_one_source(const T* x, int C, int P, int n, int chunk, int
         float a = 0.f;
         for (int l = 0; l < lanes; ++l) a += red[(l * cv + vi2) * 17 + j];
         const int c = vi2 * 8 + (j & 7);
-        atomicAdd(ws_nc + 2 * c + (j >> 3), a);
+        ws_nc[2 * c + (j >> 3)] = a;   // this block's partial slot: one writer, no atomics
     }
     __syncthreads();
 }
@@ -112,9 +116,10 @@ template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const GnParams p) {
     __shared__ float red[256 * 17];
     const int n = blockIdx.y, chunk = blockIdx.x;
-    // scratch layout: [N][C0][2] followed by [N][C1][2] (the layout a producing conv writes per tensor)
-    float* ws0 = p.ws + (long long)n * p.C0 * 2;
-    float* ws1 = p.ws + (long long)p.N * p.C0 * 2 + (long long)n * p.C1 * 2;
+    // scratch layout: [N][chunks][C0][2] followed by [N][chunks][C1][2] (the layout a producing conv writes per tensor,
+    // parts = chunks)
+    float* ws0 = p.ws + ((long long)n * p.chunks + chunk) * p.C0 * 2;
+    float* ws1 = p.ws + (long long)p.N * p.chunks * p.C0 * 2 + ((long long)n * p.chunks + chunk) * p.C1 * 2;
     stats_one_source<T>(static_cast<const T*>(p.x0), p.C0, p.P, n, chunk, p.chunks, ws0, red);
     if (p.C1 > 0) stats_one_source<T>(static_cast<const T*>(p.x1), p.C1, p.P, n, chunk, p.chunks, ws1, red);
 }
@@ -266,6 +271,20 @@ __device__ __forceinline__ void affine8(const float* gstat, int cpg, int c0, con
     }
 }
 
+// Tensors cut into many tiles per sample (pixel-space 128 x 128 images: 128 parts): the group reduction over
+// [parts][channels of the group] is done ONCE per sample here instead of once per position chunk in the apply kernel.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnParams p, float* gfinal) {
+    __shared__ float gstat[64];
+    const int n = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int cpg = (p.C0 + p.C1) / 32;
+    const GnStatSrc ss{p.st0, p.st1, p.parts0, p.parts1, p.C0, p.C1};
+    gn_group_stats(ss, n, cpg, 1.f / ((float)cpg * (float)p.P), p.eps, gstat);
+    __syncthreads();
+    if (threadIdx.x < 64) gfinal[(long long)n * 64 + threadIdx.x] = gstat[threadIdx.x];
+}
+
 template <typename T, bool DROP>
 __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(const GnParams p) {
     __shared__ float gstat[64];  // [32][2] group mean, rstd
@@ -291,30 +310,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(c
 #pragma unroll
         for (int u = 0; u < GN_UNROLL; ++u) pre[u].load(v0.xb + (long long)(v0.pix + u * v0.lanes) * v0.C);
     }
-    // (2) group statistics from the per-channel sums: 8 threads per group, then a 3-step shuffle
-    {
-        const float* s0 = p.st0 + (long long)n * p.C0 * 2;
-        const float* s1 = p.st1 ? p.st1 + (long long)n * p.C1 * 2 : nullptr;
-        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
-        float s = 0.f, ss = 0.f;
-        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
-            const float2 q = __ldcg(reinterpret_cast<const float2*>(c < p.C0 ? s0 + 2 * c : s1 + 2 * (c - p.C0)));
-            s += q.x;
-            ss += q.y;
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        }
-        if (sub == 0) {
-            const float inv = 1.f / ((float)cpg * (float)p.P);
-            const float mean = s * inv;
-            float var = ss * inv - mean * mean;
-            var = var < 0.f ? 0.f : var;
-            gstat[2 * g] = mean;
-            gstat[2 * g + 1] = 1.f / sqrtf(var + p.eps);
-        }
+    // (2) group statistics from the per-tile partial sums, added in a fixed order (tq_gnstats.cuh)
+    if (p.gfinal) {
+        if (threadIdx.x < 64) gstat[threadIdx.x] = __ldcg(p.gfinal + (long long)n * 64 + threadIdx.x);
+    } else {
+        const GnStatSrc ss{p.st0, p.st1, p.parts0, p.parts1, p.C0, p.C1};
+        gn_group_stats(ss, n, cpg, 1.f / ((float)cpg * (float)p.P), p.eps, gstat);
     }
     __syncthreads();
     float a[8], b[8];
@@ -353,23 +354,15 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(c
 
 }  // namespace
 
-int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
-    TQ_CHECK(d.dtype == TQ_BF16 || d.dtype == TQ_F32, "groupnorm: bad dtype");
+// position chunks per sample, whether the group reduction gets its own launch, and the scratch floats the op needs
+struct GnLayout {
+    int chunks;
+    bool finalize;
+    size_t final_floats, stats_floats;
+};
+static GnLayout gn_layout(const tq_gn_desc& d) {
+    GnLayout L{};
     const int Ct = d.C0 + d.C1;
-    TQ_CHECK(d.C0 > 0 && d.C0 % 8 == 0 && d.C1 % 8 == 0 && d.C1 >= 0, "groupnorm: channel counts must be multiples of 8");
-    TQ_CHECK(Ct % 32 == 0, "groupnorm: 32 groups need C %% 32 == 0 (C=%d)", Ct);
-    TQ_CHECK(d.C0 <= 2048 && d.C1 <= 2048, "groupnorm: at most 2048 channels per source");
-    TQ_CHECK(d.x0 && d.y && d.gamma && d.beta, "groupnorm: null pointer");
-    TQ_CHECK(d.C1 == 0 || d.x1, "groupnorm: second source missing");
-    const bool have_stats = d.stats0 != nullptr;
-    TQ_CHECK(have_stats || d.ws, "groupnorm: neither producer statistics nor a scratch buffer given");
-    TQ_CHECK(!have_stats || d.C1 == 0 || d.stats1, "groupnorm: statistics of the second source missing");
-    TQ_CHECK(have_stats || !d.stats1, "groupnorm: statistics of the first source missing");
-    auto p = std::make_shared<GnParams>();
-    p->x0 = d.x0; p->x1 = d.x1; p->N = d.N; p->P = d.P; p->C0 = d.C0; p->C1 = d.C1;
-    p->gamma = d.gamma; p->beta = d.beta; p->eps = d.eps; p->silu = d.silu; p->y = d.y; p->ws = d.ws;
-    p->st0 = have_stats ? d.stats0 : d.ws;
-    p->st1 = have_stats ? d.stats1 : (d.C1 > 0 ? d.ws + (size_t)d.N * d.C0 * 2 : nullptr);
     // position chunks per sample: the grid (chunks x N CTAs) should fill whole waves of the resident-CTA slots
     // (4 CTAs/SM for bf16, 2 for fp32) -- N = 256 with 5 chunks was 2.16 waves, i.e. a third wave at 16 % occupancy
     const bool f32 = d.dtype == TQ_F32;
@@ -384,16 +377,50 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
         const int c = atoi(e);
         if (c >= 1 && c <= max_chunks) chunks = c;
     }
+    L.chunks = chunks;
+    const bool have_stats = d.stats0 != nullptr;
+    const int parts = have_stats ? (d.parts0 > d.parts1 ? d.parts0 : d.parts1) : chunks;
+    // more than 16 dependent-order loads per thread in the apply prologue (8 threads per group): reduce once per sample
+    L.finalize = chunks > 1 && (long long)parts * (Ct / 32) > 16 * 8;
+    L.final_floats = L.finalize ? (size_t)d.N * 64 : 0;
+    L.stats_floats = have_stats ? 0 : (size_t)d.N * chunks * Ct * 2;
+    return L;
+}
+
+int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
+    TQ_CHECK(d.dtype == TQ_BF16 || d.dtype == TQ_F32, "groupnorm: bad dtype");
+    const int Ct = d.C0 + d.C1;
+    TQ_CHECK(d.C0 > 0 && d.C0 % 8 == 0 && d.C1 % 8 == 0 && d.C1 >= 0, "groupnorm: channel counts must be multiples of 8");
+    TQ_CHECK(Ct % 32 == 0, "groupnorm: 32 groups need C %% 32 == 0 (C=%d)", Ct);
+    TQ_CHECK(d.C0 <= 2048 && d.C1 <= 2048, "groupnorm: at most 2048 channels per source");
+    TQ_CHECK(d.x0 && d.y && d.gamma && d.beta, "groupnorm: null pointer");
+    TQ_CHECK(d.C1 == 0 || d.x1, "groupnorm: second source missing");
+    const bool have_stats = d.stats0 != nullptr;
+    TQ_CHECK(!have_stats || d.C1 == 0 || d.stats1, "groupnorm: statistics of the second source missing");
+    TQ_CHECK(have_stats || !d.stats1, "groupnorm: statistics of the first source missing");
+    TQ_CHECK(!have_stats || (d.parts0 >= 1 && (d.C1 == 0 || d.parts1 >= 1)), "groupnorm: parts0 / parts1 of the producer statistics missing");
+    const GnLayout L = gn_layout(d);
+    TQ_CHECK(L.final_floats + L.stats_floats == 0 || d.ws, "groupnorm: this op needs a scratch buffer (tq_groupnorm_ws_floats)");
+    auto p = std::make_shared<GnParams>();
+    p->x0 = d.x0; p->x1 = d.x1; p->N = d.N; p->P = d.P; p->C0 = d.C0; p->C1 = d.C1;
+    p->gamma = d.gamma; p->beta = d.beta; p->eps = d.eps; p->silu = d.silu; p->y = d.y;
+    const int chunks = L.chunks;
     p->chunks = chunks;
-    const size_t ws_bytes = (size_t)d.N * Ct * 2 * sizeof(float);
+    float* gfinal = L.finalize ? d.ws : nullptr;
+    p->ws = d.ws ? d.ws + L.final_floats : nullptr;
+    p->st0 = have_stats ? d.stats0 : p->ws;
+    p->st1 = have_stats ? d.stats1 : (d.C1 > 0 ? p->ws + (size_t)d.N * chunks * d.C0 * 2 : nullptr);
+    p->parts0 = have_stats ? d.parts0 : chunks;
+    p->parts1 = have_stats ? d.parts1 : chunks;
+    p->gfinal = nullptr;
+    const bool f32 = d.dtype == TQ_F32;
     const size_t smem = 0;
     dim3 grid(chunks, d.N);
 
     if (!have_stats) {
         Op st;
         st.name = f32 ? "gn_stats<f32>" : "gn_stats<bf16>";
-        st.launch = [p, grid, f32, ws_bytes](cudaStream_t s) -> int {
-            TQ_CUDA(cudaMemsetAsync(p->ws, 0, ws_bytes, s));
+        st.launch = [p, grid, f32](cudaStream_t s) -> int {
             if (f32) gn_stats_kernel<float><<<grid, 256, 0, s>>>(*p);
             else gn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(*p);
             TQ_CUDA(cudaGetLastError());
@@ -401,6 +428,21 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
             return 0;
         };
         ops.push_back(std::move(st));
+    }
+    if (L.finalize) {
+        Op fn;
+        fn.name = "gn_finalize";
+        fn.small = true;
+        const int N = d.N;
+        auto pf = std::make_shared<GnParams>(*p);   // reads the partial sums (gfinal unset)
+        fn.launch = [pf, gfinal, N](cudaStream_t s) -> int {
+            TQ_CUDA(launch_pdl(gn_finalize_kernel, dim3(N), dim3(256), 0, s, *pf, gfinal));
+            TQ_CUDA(cudaGetLastError());
+            count_launch();
+            return 0;
+        };
+        ops.push_back(std::move(fn));
+        p->gfinal = gfinal;
     }
     Op ap;
     ap.name = f32 ? "gn_apply<f32>" : "gn_apply<bf16>";
@@ -421,3 +463,9 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
 }
 
 }  // namespace tq
+
+extern "C" int64_t tq_groupnorm_ws_floats(const tq_gn_desc* d) {
+    if (!d || d->N <= 0 || d->P <= 0 || d->C0 <= 0) return -1;
+    const tq::GnLayout L = tq::gn_layout(*d);
+    return (int64_t)(L.final_floats + L.stats_floats);
+}

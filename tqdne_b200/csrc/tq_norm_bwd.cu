@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include "tq_common.h"
+#include "tq_gnstats.cuh"
 
 namespace tq {
 namespace {
@@ -25,7 +26,8 @@ struct GnBwdParams {
     int N, P, C0, C1;
     const float* gamma; const float* beta;
     float eps; int silu;
-    const float* st0; const float* st1;   // forward sums [N][C0][2], [N][C1][2]
+    const float* st0; const float* st1;   // forward partial sums [N][parts0][C0][2], [N][parts1][C1][2]
+    int parts0, parts1;
     float* ws;                            // [N][C0 + C1][2]: A, B
     float* dgamma; float* dbeta;          // [C0 + C1], accumulated into
     const unsigned long long* drop_seed; float drop_p; int drop_site;   // the forward's fused dropout (nullptr = none)
@@ -95,30 +97,10 @@ __device__ __forceinline__ float sigmoid_f(float v) {
     }
 }
 
-// group mean / rstd of sample n from the forward per-channel sums; 8 threads per group (256 threads, 32 groups)
+// group mean / rstd of sample n from the forward partial sums (fixed summation order: tq_gnstats.cuh)
 __device__ __forceinline__ void group_stats(const GnBwdParams& p, int n, int cpg, float* gstat) {
-    const float* s0 = p.st0 + (long long)n * p.C0 * 2;
-    const float* s1 = p.st1 ? p.st1 + (long long)n * p.C1 * 2 : nullptr;
-    const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
-    float s = 0.f, ss = 0.f;
-    for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
-        const float2 q = __ldcg(reinterpret_cast<const float2*>(c < p.C0 ? s0 + 2 * c : s1 + 2 * (c - p.C0)));
-        s += q.x;
-        ss += q.y;
-    }
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    if (sub == 0) {
-        const float inv = 1.f / ((float)cpg * (float)p.P);
-        const float mean = s * inv;
-        float var = ss * inv - mean * mean;
-        var = var < 0.f ? 0.f : var;
-        gstat[2 * g] = mean;
-        gstat[2 * g + 1] = 1.f / sqrtf(var + p.eps);
-    }
+    const GnStatSrc ss{p.st0, p.st1, p.parts0, p.parts1, p.C0, p.C1};
+    gn_group_stats(ss, n, cpg, 1.f / ((float)cpg * (float)p.P), p.eps, gstat);
 }
 
 // the thread's 8-channel vector of the concatenated tensor: pointers into the right source
@@ -306,7 +288,9 @@ extern "C" int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream) {
     GnBwdParams p;
     p.x0 = d->x0; p.x1 = d->x1; p.dy = d->dy; p.dx0 = d->dx0; p.dx1 = d->dx1; p.add0 = d->dx_add0; p.add1 = d->dx_add1;
     p.N = d->N; p.P = d->P; p.C0 = d->C0; p.C1 = d->C1; p.gamma = d->gamma; p.beta = d->beta; p.eps = d->eps;
-    p.silu = d->silu; p.st0 = d->stats0; p.st1 = d->C1 > 0 ? d->stats1 : nullptr; p.ws = d->ws;
+    p.silu = d->silu; p.st0 = d->stats0; p.st1 = d->C1 > 0 ? d->stats1 : nullptr;
+    p.parts0 = d->parts0; p.parts1 = d->C1 > 0 ? d->parts1 : 1;
+    TQ_CHECK(p.parts0 >= 1 && p.parts1 >= 1, "gn_silu_backward: parts0 / parts1 of the forward statistics missing"); p.ws = d->ws;
     p.drop_seed = reinterpret_cast<const unsigned long long*>(d->drop_seed); p.drop_p = d->drop_p; p.drop_site = d->drop_site;
     if (!(d->drop_p > 0.f)) p.drop_seed = nullptr;
     p.dgamma = d->dgamma; p.dbeta = d->dbeta; p.dx_sum = d->dx_sum; p.dx_sum_ld = d->dx_sum_ld > 0 ? d->dx_sum_ld : d->C0;

@@ -145,7 +145,8 @@ class Act:
     H: int
     W: int
     C: int
-    stats: torch.Tensor | None = None   # [N, C, 2] fp32 per-(sample, channel) sum / sum of squares (conv epilogue)
+    stats: torch.Tensor | None = None   # [N, parts, C, 2] fp32 per-(sample, tile, channel) sum / sum of squares (conv epilogue)
+    stats_parts: int = 1
 
     @property
     def P(self) -> int:
@@ -190,7 +191,6 @@ class Plan:
         self.tq_dtype = tq_dtype(act_dtype)
         self.pool = Pool(device, act_dtype)
         self.keep: list = []
-        self.gn_ws = None
         self._stats_block = None   # bump-allocated arena of conv-epilogue GroupNorm statistics
         self._stats_used = 0
         # one entry per kernel launch of the plan: (kind, algorithmic FLOPs, algorithmic HBM bytes)
@@ -215,25 +215,18 @@ class Plan:
     STATS_BLOCK_FLOATS = 4 << 20  # 16 MiB per arena block
 
     def _stats_alloc(self, nfloats: int) -> torch.Tensor:
-        """Statistics buffers are unique per producing conv (never pooled) and live in a few arena blocks, each
-        cleared by ONE memset op placed at the front of the plan."""
+        """Statistics buffers are unique per producing conv (never pooled) and live in a few zero-filled arena blocks.
+        Every slot a conv geometry writes is overwritten (plain stores) on every run and the slots it never writes stay
+        zero, so nothing has to be cleared between runs."""
         nfloats = (nfloats + 3) // 4 * 4
         if self._stats_block is None or self._stats_used + nfloats > self._stats_block.numel():
             size = max(self.STATS_BLOCK_FLOATS, nfloats)
             self._stats_block = torch.zeros(size, device=self.device, dtype=torch.float32)
             self._stats_used = 0
             self.keep.append(self._stats_block)
-            _lib.check(self.lib.tq_plan_add_memset(self.h, self._stats_block.data_ptr(), size * 4, 1), "plan_add_memset")
-            self.op_meta.insert(0, ("memset", 0, 0))
         v = self._stats_block[self._stats_used:self._stats_used + nfloats]
         self._stats_used += nfloats
         return v
-
-    def _gn_scratch(self, nfloats: int) -> torch.Tensor:
-        if self.gn_ws is None or self.gn_ws.numel() < nfloats:
-            self.gn_ws = torch.empty(nfloats, device=self.device, dtype=torch.float32)
-            self.keep.append(self.gn_ws)
-        return self.gn_ws
 
     # -- ops ------------------------------------------------------------------------------------
     def conv(self, pc: PackedConv, srcs: list[Act], *, out: Act | None = None, out_dtype=None, stride: int = 1,
@@ -355,8 +348,13 @@ class Plan:
         d.cta_group = cta_group
         tensor_path = self.act_dtype == torch.bfloat16
         if stats and ((tensor_path and odt == torch.bfloat16 and pc.cout % 64 == 0) or (not tensor_path and pc.cout % 32 == 0)):
-            out.stats = self._stats_alloc(N * pc.cout * 2)
+            parts = int(self.lib.tq_conv_stats_parts(C.byref(d)))
+            if parts < 1:
+                raise RuntimeError("tq_conv_stats_parts failed")
+            out.stats = self._stats_alloc(N * parts * pc.cout * 2)
+            out.stats_parts = parts
             d.stats = out.stats.data_ptr()
+            d.stats_parts = parts
         _lib.check(self.lib.tq_plan_add_conv(self.h, C.byref(d)), "plan_add_conv")
         # algorithmic bytes: every source once, weights once, output once (+ residual once)
         io_bytes = sum(n_ * h_ * w_ * c_ for (_, _, n_, h_, w_, c_, _, _, _) in src_views) * esz
@@ -393,13 +391,24 @@ class Plan:
         if fused:
             d.stats0 = a0.stats.data_ptr()
             d.stats1 = a1.stats.data_ptr() if a1 else None
-        else:
-            d.ws = self._gn_scratch(2 * a0.N * max(Ct, 2048)).data_ptr()
+            d.parts0, d.parts1 = a0.stats_parts, (a1.stats_parts if a1 else 1)
+        need = int(self.lib.tq_groupnorm_ws_floats(C.byref(d)))
+        if need < 0:
+            raise RuntimeError("tq_groupnorm_ws_floats failed")
+        if need > 0:
+            # per-op scratch (the stand-alone statistics pass / the per-sample group reduction of many-part tensors)
+            ws = torch.zeros(need, device=self.device, dtype=torch.float32)
+            self.keep.append(ws)
+            d.ws = ws.data_ptr()
+        before = self.num_ops
         _lib.check(self.lib.tq_plan_add_groupnorm(self.h, C.byref(d)), "plan_add_groupnorm")
+        nops = self.num_ops - before   # [gn_stats] [gn_finalize] gn_apply
         esz = a0.t.element_size()
         nel = a0.N * a0.P * Ct
         if not fused:
             self.op_meta.append(("gn_stats", 0, nel * esz))      # one read
+        if nops == (2 if fused else 3):
+            self.op_meta.append(("gn_finalize", 0, 0))
         self.op_meta.append(("gn_apply", 0, 2 * nel * esz))      # one read + one write
         self.keep += [g, b, a0.t, out.t] + ([a1.t] if a1 else [])
         return out

@@ -395,6 +395,7 @@ class TrainStep1D:
                 d.eps, d.silu = 1e-5, 1 if extra else 0
                 assert x0.stats is not None and (x1 is None or x1.stats is not None), "forward statistics missing"
                 d.stats0, d.stats1 = x0.stats.data_ptr(), (x1.stats.data_ptr() if x1 is not None else None)
+                d.parts0, d.parts1 = x0.stats_parts, (x1.stats_parts if x1 is not None else 1)
                 d.ws, d.dx0, d.dx1 = ws.data_ptr(), dx0.t.data_ptr(), (dx1.t.data_ptr() if dx1 is not None else None)
                 d.dgamma, d.dbeta = st.view(st.G, mod.weight).data_ptr(), st.view(st.G, mod.bias).data_ptr()
                 d.dx_add0 = a0.t.data_ptr() if a0 is not None else None
