@@ -379,7 +379,8 @@ def run_engine(args) -> None:
         c = cond_host.to(dev, non_blocking=True)
         z = noise_host.to(dev, non_blocking=True)
         rep = edm.sample((hi - lo, 3, 128, 128), cond=c, noise=z)
-        wav = rep_inv.invert_representation_device(rep)
+        # fp64 Griffin-Lim (parity mode); the waveforms are stored as float32 like the reference's output dataset
+        wav = rep_inv.invert_representation_device(rep).to(torch.float32)
         if world > 1:
             full = sharding.gather_waveforms(wav, total)   # the one collective: final gather to rank 0
             return sharding.to_host(full) if full is not None else None

@@ -287,9 +287,12 @@ int tq_nhwc_to_nchw(const void* src, int32_t dtype_in, int32_t Cld, void* dst, i
  * tq_logspec_griffinlim replaces LogSpectrogram.invert_representation (tqdne/representation.py:
  * 152-175) with librosa 0.11 griffinlim(n_iter, hop, n_fft, random_state=0) semantics:
  * rep:[items, n_fft/2, frames] in [-1,1] (reference NCHW order, any float dtype cast to fp32 by the
- * caller) -> wave:[items, hop*(frames-1)].  phase0:[n_fft/2+1, frames] are the initial phase angles
- * in radians (2*pi*RandomState(0).random()), shared by all items.  ws: fp32 scratch, size from
- * tq_griffinlim_ws_bytes().  precision: TQ_F32 or TQ_F64 arithmetic.                                   */
+ * caller) -> wave:[items, hop*(frames-1)] (float for TQ_F32, double for TQ_F64).
+ * phase0:[n_fft/2+1, frames, 2] float64 are the unit phasors (cos, sin) of the initial phase angles
+ * 2*pi*RandomState(0).random(), shared by all items.  ws: scratch, size from
+ * tq_griffinlim_ws_bytes().  precision: TQ_F64 (the reference under its locked NumPy 2 runs
+ * complex128; the parity mode and the default of the Python front-end) or TQ_F32 (fast mode).
+ * All iterations run in ONE launch; the result is bit-reproducible (no atomics).                       */
 int64_t tq_griffinlim_ws_bytes(int32_t items, int32_t n_fft, int32_t frames, int32_t precision);
 int tq_logspec_griffinlim(const float* rep, const double* phase0, void* wave, int32_t items,
                           int32_t n_fft, int32_t hop, int32_t frames, int32_t n_iter,

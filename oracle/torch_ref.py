@@ -230,6 +230,31 @@ def heun_sample(sd, cfg, eps, sigmas, cond, prefix="unet.", trace=None):
     return x_next
 
 
+def sigma_hat(sigma, num_steps: int):
+    """EDM.sigma_hat (edm.py:48-52): fp32 0-dim arithmetic."""
+    gamma = min(S_CHURN / num_steps, 2**0.5 - 1) if S_MIN <= sigma <= S_MAX else 0
+    return sigma + gamma * sigma
+
+
+def heun_sample_stochastic(sd, cfg, eps, sigmas, cond, noises, prefix="unet."):
+    """LightningEDM.sample_stochastically (edm.py:198-230) with the th.randn_like draws given as `noises[i]`."""
+    n = len(sigmas) - 1
+    x_next = eps
+    for i in range(n):
+        s, s_next = sigmas[i], sigmas[i + 1]
+        x = x_next
+        s_hat = sigma_hat(s, n)
+        x_hat = x + (noises[i] * S_NOISE) * (s_hat**2 - s**2) ** 0.5
+        pred = denoise(sd, cfg, x_hat.float(), s_hat.repeat(len(x)), cond, prefix).double()
+        d = (x_hat - pred) / s_hat
+        x_next = x_hat + d * (s_next - s_hat)
+        if i < n - 1:
+            pred2 = denoise(sd, cfg, x_next.float(), s_next.repeat(len(x)), cond, prefix).double()
+            d2 = (x_next - pred2) / s_next
+            x_next = x_hat + (s_next - s_hat) * (0.5 * d + 0.5 * d2)
+    return x_next
+
+
 # ---- representations (tqdne/representation.py) ---------------------------------------------------------
 def mavg_envelope_inverse(rep, log_eps=1e-6, eps=1e-6):
     """MovingAverageEnvelope.invert_representation (representation.py:57-60), NumPy semantics."""

@@ -2,7 +2,11 @@
 reference produced (tests/golden, oracle/make_golden.py) and against the oracle on fresh seeded inputs.
 
 Tolerances (north_star): fp32 mode rel-L2 <= 1e-5, bf16 mode <= 1e-2, per denoiser call and on the final
-sample / decoded spectrogram.
+sample / decoded spectrogram of the real configuration (25 Heun steps, batch 256:
+test_full_config_25_steps_bf16_tolerance_and_bit_reproducibility).  The short-ladder goldens (3 / 4 Heun steps end
+with a jump from a high noise level, so the result IS one network output chained into the next network) carry the
+bounds of BF16_CHAIN below: measured values (tools/tolerance_probe.py, bit-reproducible since the GroupNorm
+statistics are deterministic) + 25 % headroom, derived in DESIGN.md section 2.
 """
 import numpy as np
 import pytest
@@ -17,6 +21,11 @@ pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 1e-5, "bf16": 1e-2}
 DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+# bf16 bounds of quantities that chain SEVERAL bf16 network evaluations without the damping of a full noise ladder
+# (measured, profiles/r2_tolerance_probe.json): decoded spectrogram of the 4-step latent run 1.013e-2 = the decoder's own
+# 7.5e-3 (+) the propagated latent error 6.0e-3; 3-step 1D sample 1.10e-2 (two undamped denoiser calls of 7e-3 each);
+# its waveform 1.51e-2 (the envelope inverse multiplies the signal channels by exp(envelope channel): relative errors add)
+BF16_CHAIN = {"decoded_4step": 1.3e-2, "sample_1d_3step": 1.4e-2, "waveform_1d_3step": 1.9e-2}
 
 
 def _unet(kind, seed, mode):
@@ -78,14 +87,17 @@ def test_heun_sampler_and_decode_match_reference_golden(mode, graph):
     edm.use_cuda_graph = graph
     lat = edm.sample_deterministically(g["eps"].cuda(), g["sigmas"], None, g["cond"].cuda())
     assert lat.dtype == torch.float64 and lat.shape == g["latent"].shape
-    # 7 NFE compound the per-call error; the bound is stated on the final sample as north_star asks
-    assert rel_l2(lat.cpu(), g["latent"]) < TOL[mode] * (3 if mode == "bf16" else 1)
+    assert rel_l2(lat.cpu(), g["latent"]) < TOL[mode]           # measured 2.2e-6 / 5.96e-3
+    dec_tol = TOL["fp32"] if mode == "fp32" else BF16_CHAIN["decoded_4step"]
     dec = edm.autoencoder.decode(lat.float())
-    assert rel_l2(dec.cpu(), g["decoded"]) < TOL[mode] * (3 if mode == "bf16" else 1)
+    assert rel_l2(dec.cpu(), g["decoded"]) < dec_tol             # measured 2.9e-6 / 1.013e-2
     # same thing through sample(shape, noise=...): eps = noise * sigma_0
     noise = (g["eps"] / g["sigmas"][0]).cuda()
     out = edm.sample((2, 3, 128, 128), cond=g["cond"].cuda(), noise=noise)
-    assert out.dtype == torch.float32 and rel_l2(out.cpu(), g["decoded"]) < TOL[mode] * (3 if mode == "bf16" else 1)
+    assert out.dtype == torch.float32 and rel_l2(out.cpu(), g["decoded"]) < dec_tol
+    # the sampler is bit-reproducible (no atomics anywhere on the path): eager and graph replays, run twice
+    again = edm.sample((2, 3, 128, 128), cond=g["cond"].cuda(), noise=noise)
+    assert torch.equal(out, again)
 
 
 def test_sample_reproduces_reference_rng_draw_order():
@@ -104,8 +116,7 @@ def test_sample_reproduces_reference_rng_draw_order():
     torch.randn((2, 8, 32, 32), device="cuda", dtype=torch.float32, generator=gen2)
     n2 = torch.randn((2, 8, 32, 32), device="cuda", dtype=torch.float64, generator=gen2)
     b = edm.sample((2, 3, 128, 128), cond=g["cond"].cuda(), noise=n2)
-    # GroupNorm statistics use fp32 atomics: runs agree to rounding, not bit-for-bit
-    assert rel_l2(a, b) < 2e-5
+    assert torch.equal(a, b)   # same draws, deterministic kernels: bit-for-bit
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
@@ -117,10 +128,12 @@ def test_1d_edm_sampler_and_envelope_inverse(mode):
     seeded(edm, g["seed"]).cuda()
     edm.set_engine_precision(mode)
     out = edm.sample_deterministically(g["eps"].cuda(), g["sigmas"], None, g["cond"].cuda())
-    assert rel_l2(out.cpu(), g["sample"]) < TOL[mode] * (3 if mode == "bf16" else 1)
+    assert rel_l2(out.cpu(), g["sample"]) < (TOL["fp32"] if mode == "fp32" else BF16_CHAIN["sample_1d_3step"])  # 3.6e-6 / 1.10e-2
     wave = tq.MovingAverageEnvelope().invert_representation(out.float())
     assert wave.shape == (2, 3, 256)
-    assert rel_l2(wave, g["waveform"]) < TOL[mode] * (30 if mode == "bf16" else 3)
+    assert rel_l2(wave, g["waveform"]) < (TOL["fp32"] if mode == "fp32" else BF16_CHAIN["waveform_1d_3step"])    # 3.8e-6 / 1.51e-2
+    # the inverse kernel itself is exact to fp32 rounding: fed with the REFERENCE sample it reproduces the reference waveform
+    assert rel_l2(tq.MovingAverageEnvelope().invert_representation(g["sample"].float().cuda()), g["waveform"]) < 1e-6
 
 
 def test_fresh_inputs_against_oracle_ragged_batch_and_micro_batching():
@@ -145,13 +158,91 @@ def test_fresh_inputs_against_oracle_ragged_batch_and_micro_batching():
     assert rel_l2(parts.cpu(), ref) < 1e-5
 
 
-def test_stochastic_sampler_runs_and_is_finite():
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,kind", [("edm_stochastic_latent", "latent2d"), ("edm_stochastic_1d", "1d")])
+def test_stochastic_sampler_matches_reference_golden(name, kind, mode):
+    """LightningEDM.sample_stochastically (reference edm.py:198-230, EDM.sigma_hat :48-52) against the reference's own
+    output, fed with the th.randn_like draws the reference consumed (stored in the fixture)."""
     import tqdne_b200 as tq
 
-    edm = tq.LightningEDM(unet_cfg("latent2d"), {}, num_sampling_steps=3, deterministic_sampling=False)
-    seeded(edm, 78).cuda().set_engine_precision("bf16")
-    out = edm.sample((2, 8, 32, 32), cond=torch.zeros(2, 5, device="cuda"))
-    assert out.shape == (2, 8, 32, 32) and bool(torch.isfinite(out).all())
+    g = golden(name)
+    steps = int(g["steps"])
+    edm = tq.LightningEDM(unet_cfg(kind), {}, num_sampling_steps=steps, deterministic_sampling=False)
+    seeded(edm, g["seed"]).cuda().set_engine_precision(mode)
+    noises = [z.cuda() for z in g["noises"]]
+    out = edm.sample_stochastically(g["eps"].cuda(), g["sigmas"], None, g["cond"].cuda(), noises=noises)
+    assert out.dtype == torch.float64 and out.shape == g["sample"].shape
+    err = rel_l2(out.cpu(), g["sample"])
+    # bf16: a 3- / 4-step ladder chains undamped denoiser calls, like BF16_CHAIN["sample_1d_3step"]
+    assert err < (TOL["fp32"] if mode == "fp32" else BF16_CHAIN["sample_1d_3step"]), err
+    # sample() draws the churn noise from the caller's generator, for the whole batch and before the micro-batching:
+    # the same generator state gives the same bits whatever max_positions_per_pass is
+    shape = tuple(g["eps"].shape)
+    cond = g["cond"].cuda()
+    a = edm.sample(shape, cond=cond, generator=torch.Generator(device="cuda").manual_seed(3))
+    edm.max_positions_per_pass = shape[-1] if len(shape) == 3 else 1024   # one sample per pass
+    b = edm.sample(shape, cond=cond, generator=torch.Generator(device="cuda").manual_seed(3))
+    assert bool(torch.isfinite(a).all()) and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,kind", [("unet_1d_4064", "1d"), ("unet_1d_4096", "1d"), ("unet_pixel2d_128", "pixel2d")])
+def test_denoiser_call_at_stated_sizes_matches_reference_golden(name, kind, mode):
+    """One denoiser call at the sizes BASELINE.json configs[0] / configs[3] state -- [1, 6, 4064] and [1, 6, 4096] (508 /
+    512 attention tokens, ragged / full 128-row tiles at every level) and [1, 3, 128, 128] (256 tokens) -- against the
+    unmodified reference's output (oracle/make_golden_r2.py)."""
+    import tqdne_b200 as tq
+
+    g = golden(name)
+    edm = tq.LightningEDM(unet_cfg(kind), {}, num_sampling_steps=4)
+    seeded(edm, g["seed"]).cuda().set_engine_precision(mode)
+    D = edm(g["x"].cuda(), g["sigma"].cuda(), None, g["cond"].cuda())
+    assert D.shape == g["D"].shape
+    assert rel_l2(D.cpu(), g["D"]) < TOL[mode]
+
+
+def test_configs0_and_3_engine_runs_at_stated_size_against_oracle():
+    """BASELINE.json configs[0] (1D EDM UNet, batch 4, 18 Heun steps, 3 x 4064 waveforms through the envelope inverse)
+    and configs[3] (pixel-space 2D UNet, 32 Heun steps; batch 32 in micro-batches of 16 here) on the bf16 tensor path.
+    Every sample is independent of its batch neighbours, so rows picked out of the run are checked against the CPU
+    oracle run on just those rows (fp32), at the north_star bf16 tolerance on the final sample."""
+    import tqdne_b200 as tq
+
+    # ---- configs[0]: full size, full ladder (35 denoiser calls at L = 4064)
+    edm = tq.LightningEDM(unet_cfg("1d"), {}, num_sampling_steps=18)
+    sd = seeded_state_dict(shapes_of(edm), 81)
+    edm.load_state_dict(sd)
+    edm.eval().cuda().set_engine_precision("bf16")
+    gen = torch.Generator().manual_seed(82)
+    noise = torch.randn((4, 6, 4064), generator=gen, dtype=torch.float64)
+    cond = torch.randn((4, 5), generator=gen)
+    out = edm.sample((4, 6, 4064), cond=cond.cuda(), noise=noise.cuda())
+    assert out.shape == (4, 6, 4064) and out.dtype == torch.float32
+    sig = torch_ref.sampling_sigmas(18)
+    with torch.no_grad():
+        ref = torch_ref.heun_sample(sd, unet_cfg("1d"), noise[[1]] * sig[0], sig, cond[[1]])
+    err0 = rel_l2(out[[1]].cpu(), ref)
+    wave = tq.MovingAverageEnvelope().invert_representation(out)
+    assert wave.shape == (4, 3, 4064) and np.isfinite(wave).all()
+    # ---- configs[3]: 32 steps of the pixel-space UNet at 128 x 128, micro-batched (one oracle row: 63 calls of 272 GFLOP)
+    edm3 = tq.LightningEDM(unet_cfg("pixel2d"), {}, num_sampling_steps=32)
+    sd3 = seeded_state_dict(shapes_of(edm3), 83)
+    edm3.load_state_dict(sd3)
+    edm3.eval().cuda().set_engine_precision("bf16")
+    edm3.max_positions_per_pass = 16 * 128 * 128
+    noise3 = torch.randn((32, 3, 128, 128), generator=gen, dtype=torch.float64)
+    cond3 = torch.randn((32, 5), generator=gen)
+    out3 = edm3.sample((32, 3, 128, 128), cond=cond3.cuda(), noise=noise3.cuda())
+    assert out3.shape == (32, 3, 128, 128) and bool(torch.isfinite(out3).all())
+    sig3 = torch_ref.sampling_sigmas(32)
+    with torch.no_grad():
+        ref3 = torch_ref.heun_sample(sd3, unet_cfg("pixel2d"), noise3[[17]] * sig3[0], sig3, cond3[[17]])
+    err3 = rel_l2(out3[[17]].cpu(), ref3)
+    print(f"configs[0] row vs oracle: {err0:.3e}; configs[3] row vs oracle: {err3:.3e}")
+    assert err0 < TOL["bf16"] and err3 < TOL["bf16"]
+    # micro-batch independence, bit for bit: the row computed in the second micro-batch of 16 == alone-in-a-batch-of-16 run
+    again = edm3.sample((16, 3, 128, 128), cond=cond3[16:].cuda(), noise=noise3[16:].cuda())
+    assert torch.equal(again, out3[16:])
 
 
 def test_full_pipeline_latents_to_waveforms_bf16_vs_oracle():
@@ -168,9 +259,9 @@ def test_full_pipeline_latents_to_waveforms_bf16_vs_oracle():
     wave = cfg.representation.invert_representation(rep)
     assert wave.shape == (2, 3, cfg.t)
     ref = griffinlim_ref.logspec_inverse(g["decoded"].numpy(), n_iter=8)
-    # typical 6e-5 .. 1.5e-4; one run in ~10 lands above 2e-4 (fp32 statistics atomics are unordered and 8 Griffin-Lim
-    # iterations amplify the representation error further), so the bound is the amplified fp32 budget x 10
-    assert rel_l2(wave, ref) < 1e-3
+    # fp32 engine: the spectrogram differs from the reference's by 2.9e-6; exp() amplifies that 10.7x and 8 Griffin-Lim
+    # iterations a little further (measured 6e-5 .. 1.5e-4, now bit-reproducible)
+    assert rel_l2(wave, ref) < 3e-4
 
 
 def test_engine_fails_loudly_off_gpu_and_on_unsupported_options():
@@ -226,13 +317,21 @@ def test_generate_waveforms_cli_end_to_end(tmp_path):
     cond = torch.tensor(gw.normalize_features([30.0, 30.0, 120.0], [5.5, 5.5, 6.5], [400.0, 400.0, 760.0], [10.0] * 3,
                                               [130.0] * 3), dtype=torch.float32, device="cuda")
     noise = sharding.global_noise((8, 32, 32), 0, 3, 11, "cuda")
+    # the CLI ran batches of 2 + 1: the module API on the same batches, with the same per-sample noise, gives the same bits
+    # (deterministic kernels; noise is a function of the global sample index)
+    parts = [cfg.representation.invert_representation(edm.sample((n1 - n0, 3, 128, 128), cond=cond[n0:n1], noise=noise[n0:n1]))
+             for n0, n1 in ((0, 2), (2, 3))]
+    # (the output dataset is float32 like the reference's; the fp64 Griffin-Lim result is rounded once on the device)
+    assert w.dtype == np.float32 and np.abs(w).max() < 1e4
+    assert np.array_equal(w, np.concatenate(parts).astype(np.float32))
+    # one batch of 3 instead: the tile shapes the convolutions pick depend on the batch size, which changes the order of
+    # the fp32 accumulation over the taps -- bf16 rounding-level differences of the spectrogram, amplified ~10.7x by exp()
+    # in the representation inverse and further by 8 Griffin-Lim iterations (measured)
     rep = edm.sample((3, 3, 128, 128), cond=cond, noise=noise)
     ref = cfg.representation.invert_representation(rep)
-    # batches of 2 + 1 vs one batch of 3: same per-sample noise; bf16 rounding differences between the two batchings
-    # (GroupNorm atomics order) are amplified ~10.7x by exp() in the representation inverse
-    # (measured 3e-2 .. 6e-2 run to run: the fp32 statistics atomics are unordered, so even the same batching is not
-    # bit-reproducible in bf16 mode); the bound is the waveform-domain bf16 budget 1e-2 x 10.7 of SURVEY section 8(d)
-    assert np.abs(w).max() < 1e4 and rel_l2(w, ref) < 1.1e-1
+    err = rel_l2(w, ref)
+    print(f"CLI batches 2+1 vs one batch of 3, waveform rel-L2 = {err:.3e}")
+    assert err < 1.1e-1
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
@@ -302,7 +401,8 @@ def test_full_size_batch256_properties_against_oracle():
     with torch.no_grad():
         lat = torch_ref.heun_sample(sd, ucfg, noise[pick[:2]] * sig[0], sig, cond[pick[:2]])
         dec = torch_ref.decoder_forward(sd, dec_cfg, lat.float(), prefix="autoencoder.decoder.")
-    assert rel_l2(rep[pick[:2]].cpu(), dec) < 3 * TOL["bf16"]   # 5 calls + decoder: the bf16 budget accumulates
+    # 3-step ladder + decoder: two bf16 networks chained undamped, like BF16_CHAIN["decoded_4step"]
+    assert rel_l2(rep[pick[:2]].cpu(), dec) < BF16_CHAIN["decoded_4step"]
     # (3) Griffin-Lim over all 768 items == the same items inverted in a launch of their own (deterministic kernel)
     cfg.representation.n_iter = 16
     repn = torch.tanh(rep)
@@ -315,3 +415,52 @@ def test_full_size_batch256_properties_against_oracle():
     assert back.shape[-2:] == (128, 128)
     err = float((back - repn[pick]).pow(2).mean().sqrt())
     assert err < 0.25, err
+
+
+def test_full_config_25_steps_bf16_tolerance_and_bit_reproducibility():
+    """north_star tolerance at the REAL step count of BASELINE.json configs[1]: 25 Heun steps (49 denoiser calls), batch
+    256.  The engine's fp32 mode is pinned to the reference at 1e-5 (goldens above, oracle rows below), so the bf16
+    tensor path is measured against it on every sample: final latent and decoded spectrogram, worst sample <= 1e-2.
+    Two bf16 runs of the same inputs must agree bit for bit."""
+    import bench
+    import tqdne_b200 as tq
+    from tqdne_b200 import sharding
+    from tqdne_b200.config import LatentSpectrogramConfig
+
+    B, steps = 256, 25
+    cfg = LatentSpectrogramConfig()
+    enc_cfg, dec_cfg = tq.get_2d_autoencoder_configs(cfg)
+    ucfg = unet_cfg("latent2d")
+    edm = tq.LightningEDM(ucfg, {}, num_sampling_steps=steps, autoencoder=tq.LightningAutoencoder(enc_cfg, dec_cfg, {}))
+    sd = bench.build_state_dict(edm)
+    edm.load_state_dict(sd)
+    edm.eval().cuda()
+    cond = torch.from_numpy(bench.cond_grid(B)).cuda()
+    noise = sharding.global_noise((8, 32, 32), 0, B, seed=1, device="cpu").cuda()
+    sig = edm.edm.sampling_sigmas(steps)
+
+    def run(mode):
+        edm.set_engine_precision(mode)
+        lat = edm.sample_deterministically(noise * sig[0].double().cuda(), sig, None, cond)
+        return lat, edm.autoencoder.decode(lat.float())
+
+    def per_sample(a, b):
+        a, b = a.double().flatten(1), b.double().flatten(1)
+        return (a - b).norm(dim=1) / b.norm(dim=1)
+
+    lat32, rep32 = run("fp32")
+    lat16, rep16 = run("bf16")
+    e_lat, e_rep = per_sample(lat16, lat32), per_sample(rep16, rep32)
+    print(f"25 steps, batch 256, bf16 vs fp32 mode: latent median {float(e_lat.median()):.3e} max {float(e_lat.max()):.3e}; "
+          f"decoded median {float(e_rep.median()):.3e} max {float(e_rep.max()):.3e}")
+    assert float(e_lat.max()) < TOL["bf16"] and float(e_rep.max()) < TOL["bf16"]   # measured 3.7e-3 / 9.8e-3
+    lat16b, rep16b = run("bf16")
+    assert torch.equal(lat16, lat16b) and torch.equal(rep16, rep16b)
+    # rows 0 and 255 against the CPU oracle (fp32 PyTorch restatement of the reference, 49 calls + decoder)
+    pick = [0, B - 1]
+    sig_o = torch_ref.sampling_sigmas(steps)
+    with torch.no_grad():
+        lat_o = torch_ref.heun_sample(sd, ucfg, noise[pick].cpu() * sig_o[0], sig_o, cond[pick].cpu())
+        rep_o = torch_ref.decoder_forward(sd, dec_cfg, lat_o.float(), prefix="autoencoder.decoder.")
+    assert rel_l2(lat32[pick].cpu(), lat_o) < TOL["fp32"] and rel_l2(rep32[pick].cpu(), rep_o) < TOL["fp32"]
+    assert rel_l2(lat16[pick].cpu(), lat_o) < TOL["bf16"] and rel_l2(rep16[pick].cpu(), rep_o) < TOL["bf16"]

@@ -474,21 +474,35 @@ def test_mavg_envelope_inverse_matches_golden():
     assert w.shape == tuple(g["wave"].shape) and rel_l2(w, g["wave"]) < 1e-6
 
 
-@pytest.mark.parametrize("precision,tol", [("fp64", 1e-9), ("fp32", 2e-3)])
-def test_griffinlim_kernel_matches_oracle(precision, tol):
-    """Batched Griffin-Lim kernel vs the NumPy restatement, identical initial phases (full 128 iterations would
-    take the oracle ~1 s per item; 16 iterations on 6 items here, 128 iterations on 1 item below)."""
+def test_griffinlim_kernel_matches_oracle(monkeypatch):
+    """Batched Griffin-Lim kernels vs the NumPy restatement, identical initial phases (full 128 iterations would take
+    the oracle ~1 s per item; 16 iterations on 6 items here, 128 iterations on 1 item below).  fp64 (the default: the
+    reference's locked NumPy 2 runs complex128) is the parity mode: fused kernel, and the independent unfused kernel,
+    to 1e-9.  fp32 is the opt-in fast mode: it is held to NumPy's OWN complex64-vs-complex128 deviation on the same
+    input (Griffin-Lim amplifies rounding), not to a parity bound."""
     from oracle import griffinlim_ref
     from tqdne_b200.representation import LogSpectrogram
 
     g = torch.Generator().manual_seed(4)
     rep = torch.tanh(torch.randn(2, 3, 128, 128, generator=g) * 0.5)
-    ls = LogSpectrogram(stft_channels=256, hop_size=32, precision=precision)
+    ref = griffinlim_ref.logspec_inverse(rep.numpy(), n_iter=16, precision="fp64")
+    ref32 = griffinlim_ref.logspec_inverse(rep.numpy(), n_iter=16, precision="fp32")
+    numpy32 = rel_l2(ref32.astype(np.float64), ref)
+    ls = LogSpectrogram(stft_channels=256, hop_size=32)
+    assert ls.precision == "fp64"
     ls.n_iter = 16
     w = ls.invert_representation(rep.cuda())
-    ref = griffinlim_ref.logspec_inverse(rep.numpy(), n_iter=16, precision="fp64")
-    assert w.shape == (2, 3, 4064)
-    assert rel_l2(w, ref) < tol
+    assert w.shape == (2, 3, 4064) and w.dtype == np.float64
+    assert rel_l2(w, ref) < 1e-9
+    monkeypatch.setenv("TQ_GL_LEGACY", "1")
+    assert rel_l2(ls.invert_representation(rep.cuda()), ref) < 1e-9
+    monkeypatch.delenv("TQ_GL_LEGACY")
+    ls32 = LogSpectrogram(stft_channels=256, hop_size=32, precision="fp32")
+    ls32.n_iter = 16
+    w32 = ls32.invert_representation(rep.cuda())
+    e32 = rel_l2(w32.astype(np.float64), ref)
+    print(f"16 iterations: fp32 kernel vs fp64 oracle {e32:.2e}; NumPy complex64 vs complex128 {numpy32:.2e}")
+    assert w32.dtype == np.float32 and e32 < max(20 * numpy32, 1e-4)
 
 
 def test_griffinlim_full_iterations_and_golden():
@@ -503,10 +517,16 @@ def test_griffinlim_full_iterations_and_golden():
     rep = g["rep"][:, :1]
     ls.n_iter = 128
     ref = griffinlim_ref.logspec_inverse(rep.numpy(), n_iter=128, precision="fp64")
-    assert rel_l2(ls.invert_representation(rep.cuda()), ref) < 1e-7
+    w64 = ls.invert_representation(rep.cuda())
+    assert rel_l2(w64, ref) < 1e-7          # 128 iterations amplify the last-bit differences of the fp64 arithmetic ~1e3x
+    assert np.array_equal(w64, ls.invert_representation(rep.cuda()))   # bit-reproducible
+    ref32 = griffinlim_ref.logspec_inverse(rep.numpy(), n_iter=128, precision="fp32")
+    numpy32 = rel_l2(ref32.astype(np.float64), ref)
     ls32 = LogSpectrogram(stft_channels=256, hop_size=32, precision="fp32")
     w32 = ls32.invert_representation(rep.cuda())
-    assert w32.dtype == np.float32 and rel_l2(w32, ref) < 5e-2
+    e32 = rel_l2(w32.astype(np.float64), ref)
+    print(f"128 iterations: fp32 kernel vs fp64 oracle {e32:.2e}; NumPy complex64 vs complex128 {numpy32:.2e}")
+    assert w32.dtype == np.float32 and e32 < max(20 * numpy32, 1e-3)
     # domain property at full size: kernel and oracle reach the same spectral inconsistency
     S = np.exp((rep.numpy()[0, 0].astype(np.float64) + 1) / 2 * (3 - np.log(1e-8)) + np.log(1e-8))
 
@@ -514,6 +534,7 @@ def test_griffinlim_full_iterations_and_golden():
         return np.linalg.norm(np.abs(griffinlim_ref.stft(wave.astype(np.float64)))[:-1] - S) / np.linalg.norm(S)
 
     assert abs(inconsistency(w32[0, 0]) - inconsistency(ref[0, 0])) < 2e-2
+    assert abs(inconsistency(w64[0, 0]) - inconsistency(ref[0, 0])) < 1e-9
 
 
 # ---- forward representations ---------------------------------------------------------------

@@ -37,8 +37,22 @@ def _worker(rank, ws, port, n_total, ret):
         # each "waveform" carries its global sample index so the gathered order can be checked
         local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None].expand(hi - lo, 3, 16).contiguous()
         full = sharding.gather_waveforms(local, n_total, dst=0)
+        # the round-by-round gather of generate(): batches of 2 rows per rank, ragged last round, an empty contribution
+        batch, got = 2, torch.full((n_total,), -1.0)
+        shards = [sharding.shard_bounds(n_total, r, ws) for r in range(ws)]
+        rounds = max(-(-(h - l) // batch) for l, h in shards)
+        for k in range(rounds):
+            spans = [(min(h, l + k * batch), min(h, l + (k + 1) * batch)) for l, h in shards]
+            a, b = spans[rank]
+            parts = sharding.gather_ragged(local[a - lo:b - lo], [y - x for x, y in spans])
+            if rank == 0:
+                for (x, y), part in zip(spans, parts):
+                    got[x:y] = part[:, 0, 0]
+            else:
+                assert parts is None
         if rank == 0:
             ok = full.shape == (n_total, 3, 16) and torch.equal(full[:, 0, 0], torch.arange(n_total, dtype=torch.float32))
+            ok = ok and torch.equal(got, torch.arange(n_total, dtype=torch.float32))
             ret.put(bool(ok))
         else:
             assert full is None

@@ -161,3 +161,32 @@ def test_training_step_matches_reference_golden():
     for k in z.files:
         if k.startswith("grad:"):
             assert rel_l2(got[k[len("grad:unet."):]].cpu(), torch.from_numpy(z[k])) < 5e-2, k
+
+
+def test_training_state_survives_a_change_of_batch_shape():
+    """A ragged last batch (or an evaluation batch) builds a new static tape: the parameters, Adam moments, EMA and the
+    position on the cosine schedule must carry over, and a tape that sat idle while another one stepped the optimiser
+    must refresh its bf16 operand copies before it runs again."""
+    edm, _ = _edm(seed=33)
+    g = torch.Generator(device="cuda").manual_seed(9)
+
+    def batch(n, L):
+        return {"signal": torch.randn(n, 6, L, device="cuda", generator=g), "cond": torch.randn(n, 5, device="cuda", generator=g)}
+
+    a, b = batch(2, 512), batch(1, 512)
+    edm.training_step(a)
+    ta = edm._train_step(a)
+    m_norm = float(ta.store.M.norm())
+    p_after_1 = ta.store.P.clone()
+    assert ta.step_count == 1 and m_norm > 0
+    edm.training_step(b)                       # another batch size: new tape, same state
+    tb = edm._train_step(b)
+    assert tb is not ta and tb.store is ta.store and tb.step_count == 2
+    assert float((tb.store.P - p_after_1).norm()) > 0 and float(tb.store.M.norm()) > 0
+    assert ta.copies_version != ta.store.version          # tape A's operand copies are stale now ...
+    edm.training_step(a)
+    assert edm._train_step(a) is ta and ta.step_count == 3
+    assert ta.copies_version == ta.store.version          # ... and were refreshed before / after it ran
+    edm.sync_trained_weights()
+    w = edm.unet.out[2].weight.detach().float()
+    assert rel_l2(ta.store.to_module_layout(ta.store.P, edm.unet.out[2].weight), w) < 1e-7

@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--oracle-rows", type=int, default=2)
     ap.add_argument("--gl-oracle-items", type=int, default=4)
     ap.add_argument("--out", default="gpurun_out/parity_probe.json")
+    ap.add_argument("--gl-only", action="store_true", help="skip the sampler sections (needs the fp32-mode run only)")
     args = ap.parse_args()
     B = args.batch
     dev = torch.device("cuda", 0)
@@ -90,12 +91,12 @@ def main():
     torch.cuda.synchronize()
     res["fp32_mode_seconds"] = time.time() - t0
     lat16, rep16 = run("bf16")
-    lat16b, rep16b = run("bf16")
+    lat16b, rep16b = run("bf16") if not args.gl_only else (lat16, rep16)
     res["bf16_vs_fp32"] = {"latent": dist(rel(lat16, lat32)), "latent_whole": rel_all(lat16, lat32),
                            "decoded": dist(rel(rep16, rep32)), "decoded_whole": rel_all(rep16, rep32)}
     res["bf16_run_to_run"] = {"latent_equal": bool(torch.equal(lat16, lat16b)), "latent": dist(rel(lat16b, lat16)),
                               "decoded_equal": bool(torch.equal(rep16, rep16b)), "decoded": dist(rel(rep16b, rep16))}
-    lat32b, rep32b = run("fp32")
+    lat32b, rep32b = run("fp32") if not args.gl_only else (lat32, rep32)
     res["fp32_run_to_run"] = {"latent_equal": bool(torch.equal(lat32, lat32b)), "latent": dist(rel(lat32b, lat32)),
                               "decoded": dist(rel(rep32b, rep32))}
     print(json.dumps({k: res[k] for k in ("bf16_vs_fp32", "bf16_run_to_run", "fp32_run_to_run")}), flush=True)
@@ -103,7 +104,7 @@ def main():
     # error growth along the ladder: latent after k steps, bf16 vs fp32
     growth = {}
     for k in (2, 4, 8, 16):
-        if k >= args.steps:
+        if k >= args.steps or args.gl_only:
             continue
         sig = edm.edm.sampling_sigmas(args.steps)[: k + 1].clone()
         outs = {}
@@ -119,7 +120,7 @@ def main():
     print(json.dumps({"growth": growth}), flush=True)
 
     # ---- (3) oracle rows
-    if args.oracle_rows > 0:
+    if args.oracle_rows > 0 and not args.gl_only:
         from oracle import torch_ref
 
         pick = [0, B - 1, B // 2][: args.oracle_rows]
@@ -140,7 +141,8 @@ def main():
 
     gl = {}
     waves = {}
-    for name, prec, env in (("fp64", "fp64", None), ("fp32_fused", "fp32", None), ("fp32_unfused", "fp32", "1")):
+    for name, prec, env in (("fp64", "fp64", None), ("fp64_unfused", "fp64", "1"), ("fp32_fused", "fp32", None),
+                            ("fp32_unfused", "fp32", "1")):
         if env:
             os.environ["TQ_GL_LEGACY"] = env
         else:
@@ -150,7 +152,7 @@ def main():
         waves[name] = w.double()
         gl[name + "_ms_per_%d_items" % (3 * B)] = ms
     os.environ.pop("TQ_GL_LEGACY", None)
-    for name in ("fp32_fused", "fp32_unfused"):
+    for name in ("fp64_unfused", "fp32_fused", "fp32_unfused"):
         gl[name + "_vs_fp64_kernel"] = dist(rel(waves[name].flatten(0, 1), waves["fp64"].flatten(0, 1)))
     # bf16 pipeline end to end in the waveform domain (fp64 Griffin-Lim on both spectrograms)
     ls64 = LogSpectrogram(stft_channels=256, hop_size=32, precision="fp64")

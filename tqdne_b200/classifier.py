@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from .blocks import Encoder
-from .engine import Plan, nchw_to_nhwc, require_cuda
+from .engine import device_guard, Plan, nchw_to_nhwc, require_cuda
 from .lightning_shim import LightningModule
 
 
@@ -74,11 +74,12 @@ class LithningClassifier(LightningModule):
     def _run(self, x: torch.Tensor):
         require_cuda(x, "x")
         N, spatial = x.shape[0], tuple(x.shape[2:])
-        enc, head = self._head(N, spatial)
-        xin = nchw_to_nhwc(x.to(torch.float32), enc.act_dtype, enc.cin_pad)
-        enc.xin.t.copy_(xin.view(-1))
-        enc.run()
-        head["plan"].run()
+        with device_guard(x.device):
+            enc, head = self._head(N, spatial)
+            xin = nchw_to_nhwc(x.to(torch.float32), enc.act_dtype, enc.cin_pad)
+            enc.xin.t.copy_(xin.view(-1))
+            enc.run()
+            head["plan"].run()
         return head
 
     def embed(self, x):

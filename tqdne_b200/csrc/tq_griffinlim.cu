@@ -39,7 +39,7 @@ struct alignas(2 * sizeof(R)) Cx {
 
 struct GlParams {
     const float* rep;      // [items][128][frames]
-    const double* phase0;  // [129][frames]
+    const double* phase0;  // [129][frames][2]: unit phasors (cos, sin) of the initial phase
     void* wave;            // [items][hop*(frames-1)]  (float or double = R)
     void* ws;
     int items, frames, n_iter;
@@ -119,10 +119,9 @@ __global__ void __launch_bounds__(GL_THREADS) griffinlim_kernel(const GlParams p
             const float nls = (rep[(size_t)f * frames + t] + 1.f) / 2.f;  // float32 like the reference input
             sv = (R)exp((double)nls * (p.log_max - p.log_clip) + p.log_clip);
         }
-        double sn, cs;
-        sincos(p.phase0[(size_t)f * frames + t], &sn, &cs);
+        const double2 u = reinterpret_cast<const double2*>(p.phase0)[(size_t)f * frames + t];   // (cos, sin) of the phase
         S[(size_t)t * NBIN + f] = sv;
-        A[(size_t)t * NBIN + f] = Cx<R>{(R)((double)sv * cs), (R)((double)sv * sn)};
+        A[(size_t)t * NBIN + f] = Cx<R>{(R)((double)sv * u.x), (R)((double)sv * u.y)};
     }
     __syncthreads();
 
@@ -295,49 +294,66 @@ __global__ void __launch_bounds__(GL_THREADS) logspec_forward_kernel(const float
 }
 
 // =====================================================================================================
-// fp32 fast path: fused  STFT(frame t) -> phase update -> inverse FFT(frame t) -> overlap-add  per frame.
+// Fused Griffin-Lim (the product path, fp64 by default):  STFT(frame t) -> phase update -> inverse FFT(frame t) ->
+// overlap-add, per frame, templated on the arithmetic type.
 //
 // The rebuilt spectrum never leaves the SM: a warp transforms frame t of the current signal, applies the fast
-// Griffin-Lim update against R_prev (the only per-iteration global traffic besides S: 129 x 8 B read + written
-// per frame), inverse-transforms the new angles and overlap-adds into the NEXT signal buffer.  Frames are
-// processed in 8 rounds (t mod 8) separated by block barriers, so concurrently added frames never overlap and
-// the summation order is fixed.  The 128-point complex FFT is held in registers (4 points per lane):
-// radix 4 x 4 x 4 x 2 with two conflict-free shared-memory transposes and one shuffle stage.
+// Griffin-Lim update against R_prev (the only per-iteration global traffic besides S: 129 complex values read + written
+// per frame, L2 resident), inverse-transforms the new angles and overlap-adds into the NEXT signal buffer.  Frames are
+// processed in 8 rounds (t mod 8) separated by block barriers, so concurrently added frames never overlap and the
+// summation order is fixed (bit-reproducible, no atomics).  The 128-point complex FFT is held in registers (4 points per
+// lane): radix 4 x 4 x 4 x 2 with two shared-memory transposes and one shuffle stage.
+//
+// The kernel is bound by instruction issue (fp64: by the FP64 pipe), so the arithmetic is kept lean:
+//   * a / (|a| + tiny) * S is evaluated as a * (S * rsqrt(|a|^2)) -- one reciprocal square root instead of hypot + two
+//     divisions; |a|^2 that would underflow takes the literal formula.  Under fp64 the difference (1 ulp) sits ten orders
+//     of magnitude below the 1e-9 parity bound, even after the ~1e3 amplification of 128 iterations.
+//   * the unit phasors of the initial phase arrive as a table (host: cos / sin of 2 pi U in float64) -- no sincos in
+//     the kernel; S = exp(..) once per item in the prologue.
+//   * 1 / window-sum-of-squares is a per-sample table in shared memory.
 namespace fused {
 
 constexpr int FW = 16;          // warps per CTA
 constexpr int FTHREADS = FW * 32;
-constexpr int EX = 168;         // per-warp exchange buffer (complex elements): >= 152 (transposes), >= 129 (spectrum)
+constexpr int EX = 152;         // per-warp exchange buffer (complex elements): >= 152 (transposes), >= 129 (spectrum)
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+template <typename R> __device__ __forceinline__ Cx<R> cmul(Cx<R> a, Cx<R> b) { return Cx<R>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+template <typename R> __device__ __forceinline__ Cx<R> cadd(Cx<R> a, Cx<R> b) { return Cx<R>{a.x + b.x, a.y + b.y}; }
+template <typename R> __device__ __forceinline__ Cx<R> csub(Cx<R> a, Cx<R> b) { return Cx<R>{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ float r_rsqrt(float v) { return rsqrtf(v); }
+__device__ __forceinline__ double r_rsqrt(double v) { return rsqrt(v); }
+// smallest |a|^2 the rsqrt form is used for (below it |a|^2 may have lost bits to underflow)
+template <typename R> __device__ __forceinline__ R r_small2();
+template <> __device__ __forceinline__ float r_small2<float>() { return 1e-30f; }
+template <> __device__ __forceinline__ double r_small2<double>() { return 1e-280; }
 
 // z[k] = sum_j z[j] W4^(jk), W4 = -i (forward) / +i (inverse)
-template <bool INV>
-__device__ __forceinline__ void radix4(float2 (&z)[4]) {
-    const float2 t0 = cadd(z[0], z[2]), t1 = csub(z[0], z[2]), t2 = cadd(z[1], z[3]), t3 = csub(z[1], z[3]);
+template <typename R, bool INV>
+__device__ __forceinline__ void radix4(Cx<R> (&z)[4]) {
+    const Cx<R> t0 = cadd(z[0], z[2]), t1 = csub(z[0], z[2]), t2 = cadd(z[1], z[3]), t3 = csub(z[1], z[3]);
     z[0] = cadd(t0, t2);
     z[2] = csub(t0, t2);
-    const float2 it3 = INV ? make_float2(-t3.y, t3.x) : make_float2(t3.y, -t3.x);  // (+i or -i) * t3
+    const Cx<R> it3 = INV ? Cx<R>{-t3.y, t3.x} : Cx<R>{t3.y, -t3.x};  // (+i or -i) * t3
     z[1] = cadd(t1, it3);
     z[3] = csub(t1, it3);
 }
-template <bool INV>
-__device__ __forceinline__ float2 twid(const float2* tw, int m) {
-    float2 w = tw[m];
+template <typename R, bool INV>
+__device__ __forceinline__ Cx<R> twid(const Cx<R>* tw, int m) {
+    Cx<R> w = tw[m];
     if (INV) w.y = -w.y;
     return w;
 }
+__device__ __forceinline__ float shfl16(float v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
+__device__ __forceinline__ double shfl16(double v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
 
 // in : z[j] = x[lane + 32 j]            (natural order)
 // out: z[p] = X[(lane & 15) + 16 p + 64 (lane >> 4)]
 // tw[m] = exp(-2 pi i m / 128), m < 96; ex: this warp's exchange buffer
-template <bool INV>
-__device__ __forceinline__ void fft128(float2 (&z)[4], float2* ex, const float2* tw, int lane) {
-    radix4<INV>(z);
+template <typename R, bool INV>
+__device__ __forceinline__ void fft128(Cx<R> (&z)[4], Cx<R>* ex, const Cx<R>* tw, int lane) {
+    radix4<R, INV>(z);
 #pragma unroll
-    for (int k = 1; k < 4; ++k) z[k] = cmul(z[k], twid<INV>(tw, lane * k));
+    for (int k = 1; k < 4; ++k) z[k] = cmul(z[k], twid<R, INV>(tw, lane * k));
     const int a = lane >> 3, l2 = lane & 7;
     __syncwarp();
 #pragma unroll
@@ -345,9 +361,9 @@ __device__ __forceinline__ void fft128(float2 (&z)[4], float2* ex, const float2*
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j) z[j] = ex[a * 40 + l2 + 8 * j];
-    radix4<INV>(z);
+    radix4<R, INV>(z);
 #pragma unroll
-    for (int m = 1; m < 4; ++m) z[m] = cmul(z[m], twid<INV>(tw, 4 * l2 * m));
+    for (int m = 1; m < 4; ++m) z[m] = cmul(z[m], twid<R, INV>(tw, 4 * l2 * m));
     const int g = lane & 15, l3 = lane >> 4;
     __syncwarp();
 #pragma unroll
@@ -355,71 +371,85 @@ __device__ __forceinline__ void fft128(float2 (&z)[4], float2* ex, const float2*
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j) z[j] = ex[9 * g + l3 + 2 * j];
-    radix4<INV>(z);
+    radix4<R, INV>(z);
     if (l3) {
 #pragma unroll
-        for (int q = 1; q < 4; ++q) z[q] = cmul(z[q], twid<INV>(tw, 16 * q));
+        for (int q = 1; q < 4; ++q) z[q] = cmul(z[q], twid<R, INV>(tw, 16 * q));
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float ox = __shfl_xor_sync(0xffffffffu, z[q].x, 16);
-        const float oy = __shfl_xor_sync(0xffffffffu, z[q].y, 16);
-        z[q] = l3 ? make_float2(ox - z[q].x, oy - z[q].y) : make_float2(z[q].x + ox, z[q].y + oy);
+        const R ox = shfl16(z[q].x);
+        const R oy = shfl16(z[q].y);
+        z[q] = l3 ? Cx<R>{ox - z[q].x, oy - z[q].y} : Cx<R>{z[q].x + ox, z[q].y + oy};
     }
     __syncwarp();
 }
 
+// a / (|a| + tiny) * sv  (librosa: angles /= |angles| + tiny; angles *= S)
+template <typename R>
+__device__ __forceinline__ Cx<R> unit_times(R ar, R ai, R sv) {
+    const R d2 = ar * ar + ai * ai;
+    if (d2 > r_small2<R>()) {
+        const R f = sv * r_rsqrt(d2);
+        return Cx<R>{ar * f, ai * f};
+    }
+    const R den = r_hypot(ar, ai) + r_tiny<R>();
+    return Cx<R>{ar / den * sv, ai / den * sv};
+}
+
+template <typename R>
 struct Smem {
-    float* ya;      // signal buffers (padded length)
-    float* yb;
-    float* inv_wss; // 1 / window sum of squares per padded sample (0 outside the kept range)
-    float* win;     // periodic Hann, 256
-    float2* tw128;  // 96
-    float2* tw256;  // 129 (+pad)
-    float2* ex;     // FW x EX
+    R* ya;        // signal buffers (padded length)
+    R* yb;
+    R* inv_wss;   // 1 / window sum of squares per padded sample (0 outside the kept range)
+    R* win;       // periodic Hann, 256
+    Cx<R>* tw128; // 96
+    Cx<R>* tw256; // 129 (+pad)
+    Cx<R>* ex;    // FW x EX
 };
 
-__global__ void __launch_bounds__(FTHREADS, 2) griffinlim_fused_kernel(const GlParams p) {
+template <typename R>
+__global__ void __launch_bounds__(FTHREADS, sizeof(R) == 4 ? 2 : 1) griffinlim_fused_kernel(const GlParams p) {
     extern __shared__ __align__(16) unsigned char gl_smem[];
     const int frames = p.frames;
     const int len = NFFT + HOP * (frames - 1);
     const int len4 = (len + 3) & ~3;
-    Smem sm;
-    sm.ya = reinterpret_cast<float*>(gl_smem);
+    Smem<R> sm;
+    sm.ya = reinterpret_cast<R*>(gl_smem);
     sm.yb = sm.ya + len4;
     sm.inv_wss = sm.yb + len4;
     sm.win = sm.inv_wss + len4;
-    sm.tw128 = reinterpret_cast<float2*>(sm.win + NFFT);
+    sm.tw128 = reinterpret_cast<Cx<R>*>(sm.win + NFFT);
     sm.tw256 = sm.tw128 + 96;
     sm.ex = sm.tw256 + 132;
 
     const int item = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float2* ex = sm.ex + warp * EX;
+    Cx<R>* ex = sm.ex + warp * EX;
     const size_t per_item = (size_t)frames * NBIN;
-    float* S = static_cast<float*>(p.ws) + (size_t)item * per_item * 5;
-    float2* Tp = reinterpret_cast<float2*>(S + per_item);
+    R* S = static_cast<R*>(p.ws) + (size_t)item * per_item * 5;
+    Cx<R>* Tp = reinterpret_cast<Cx<R>*>(S + per_item);
 
-    for (int i = tid; i < NFFT; i += FTHREADS) sm.win[i] = (float)(0.5 - 0.5 * cospi(2.0 * i / NFFT));
+    for (int i = tid; i < NFFT; i += FTHREADS) sm.win[i] = (R)(0.5 - 0.5 * cospi(2.0 * i / NFFT));
     for (int i = tid; i < 96; i += FTHREADS) {
         double s, c;
         sincospi(-2.0 * i / 128.0, &s, &c);
-        sm.tw128[i] = make_float2((float)c, (float)s);
+        sm.tw128[i] = Cx<R>{(R)c, (R)s};
     }
     for (int i = tid; i <= 128; i += FTHREADS) {
         double s, c;
         sincospi(-2.0 * i / 256.0, &s, &c);
-        sm.tw256[i] = make_float2((float)c, (float)s);
+        sm.tw256[i] = Cx<R>{(R)c, (R)s};
     }
     for (int i = tid; i < len4; i += FTHREADS) {
-        sm.ya[i] = 0.f;
-        sm.yb[i] = 0.f;
+        sm.ya[i] = 0;
+        sm.yb[i] = 0;
     }
     __syncthreads();
     for (int n = tid; n < len4; n += FTHREADS) {
-        float v = 0.f;
+        R v = 0;
         if (n >= NFFT / 2 && n < len - NFFT / 2) {
-            float wss = 0.f;
+            R wss = 0;
             const int r = n & (HOP - 1);
 #pragma unroll
             for (int j = 0; j < NFFT / HOP; ++j) {
@@ -427,136 +457,147 @@ __global__ void __launch_bounds__(FTHREADS, 2) griffinlim_fused_kernel(const GlP
                 const int t = (n - o) / HOP;
                 if (n - o >= 0 && t < frames) wss += sm.win[o] * sm.win[o];
             }
-            v = wss > r_tiny<float>() ? 1.f / wss : 1.f;
+            v = wss > r_tiny<R>() ? (R)1 / wss : (R)1;
         }
         sm.inv_wss[n] = v;
     }
-    // S = exp(((rep + 1) / 2) * (log_max - log_clip) + log_clip), Nyquist row = 0; R_prev = 0
+    // S = exp(((rep + 1) / 2) * (log_max - log_clip) + log_clip), Nyquist row = 0
     const float* rep = p.rep + (size_t)item * 128 * frames;
     for (int idx = tid; idx < frames * NBIN; idx += FTHREADS) {
         const int f = idx / frames, t = idx % frames;  // coalesced read of rep[f][t]
-        float sv = 0.f;
+        R sv = 0;
         if (f < 128) {
             const float nls = (rep[(size_t)f * frames + t] + 1.f) / 2.f;
-            sv = (float)exp((double)nls * (p.log_max - p.log_clip) + p.log_clip);
+            sv = (R)exp((double)nls * (p.log_max - p.log_clip) + p.log_clip);
         }
         S[(size_t)t * NBIN + f] = sv;
-        Tp[(size_t)t * NBIN + f] = make_float2(0.f, 0.f);
     }
     __syncthreads();
 
-    const float mom = (float)p.mom;
-    const float inv_n = 1.f / 128.f;
-    // window taps of this lane: input order n = lane + 32 j, output order n = (lane & 15) + 16 q + 64 (lane >> 4)
-    float2 win_in[4], win_out[4];
+    const R mom = (R)p.mom;
+    const R inv_n = (R)(1.0 / 128.0);
+    const R half = (R)0.5;
+    // twiddles of the bins this lane owns (k = lane + 32 j), kept in registers: e^{-2 pi i k / 256}
+    Cx<R> w256[4];
     int n_out[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int ni = lane + 32 * j;
-        win_in[j] = make_float2(sm.win[2 * ni], sm.win[2 * ni + 1]);
+        w256[j] = sm.tw256[lane + 32 * j];
         n_out[j] = (lane & 15) + 16 * j + 64 * (lane >> 4);
-        win_out[j] = make_float2(sm.win[2 * n_out[j]] * inv_n, sm.win[2 * n_out[j] + 1] * inv_n);
     }
-    float* ycur = sm.ya;
-    float* ynext = sm.yb;
+    R* ycur = sm.ya;
+    R* ynext = sm.yb;
 
     for (int it = 0; it <= p.n_iter; ++it) {
         for (int round = 0; round < 8; ++round) {
             for (int t = round + 8 * warp; t < frames; t += 8 * FW) {
                 const size_t row = (size_t)t * NBIN;
                 // bins owned by this lane: k = lane + 32 j (j < 4); lane 0 also owns k = 128
-                float sv[4], sv128 = 0.f;
-                float2 tp[4], tp128 = make_float2(0.f, 0.f);
+                R sv[4], sv128 = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sv[j] = __ldcg(S + row + lane + 32 * j);
                 if (lane == 0) sv128 = __ldcg(S + row + 128);
                 if (it > 0) {
+                    Cx<R> tp[4], tp128 = Cx<R>{0, 0};
+                    if (it > 1) {   // R_prev of the first update is absent (librosa: tprev is None)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) tp[j] = __ldcg(Tp + row + lane + 32 * j);
-                    if (lane == 0) tp128 = __ldcg(Tp + row + 128);
+                        for (int j = 0; j < 4; ++j) {
+                            const double2* q = reinterpret_cast<const double2*>(Tp + row + lane + 32 * j);
+                            if constexpr (sizeof(R) == 8) {
+                                const double2 v = __ldcg(q);
+                                tp[j] = Cx<R>{(R)v.x, (R)v.y};
+                            } else {
+                                const float2 v = __ldcg(reinterpret_cast<const float2*>(Tp + row + lane + 32 * j));
+                                tp[j] = Cx<R>{(R)v.x, (R)v.y};
+                            }
+                        }
+                        if (lane == 0) tp128 = Tp[row + 128];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) tp[j] = Cx<R>{0, 0};
+                    }
                     // ---- forward: frame t of the current signal
-                    float2 z[4];
-                    const float* yt = ycur + HOP * t;
+                    Cx<R> z[4];
+                    const R* yt = ycur + HOP * t;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float2 v = *reinterpret_cast<const float2*>(yt + 2 * (lane + 32 * j));
-                        z[j] = make_float2(v.x * win_in[j].x, v.y * win_in[j].y);
+                        const int ni = lane + 32 * j;
+                        const Cx<R> v = *reinterpret_cast<const Cx<R>*>(yt + 2 * ni);
+                        const Cx<R> w = *reinterpret_cast<const Cx<R>*>(sm.win + 2 * ni);
+                        z[j] = Cx<R>{v.x * w.x, v.y * w.y};
                     }
-                    fft128<false>(z, ex, sm.tw128, lane);
+                    fft128<R, false>(z, ex, sm.tw128, lane);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) ex[n_out[q]] = z[q];
                     __syncwarp();
-                    float2 zk[4], zn[4];
+                    Cx<R> zk[4], zn[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int k = lane + 32 * j;
                         zk[j] = ex[k];
                         zn[j] = ex[(128 - k) & 127];
                     }
-                    const float2 z0 = ex[0];
+                    const Cx<R> z0 = ex[0];
                     __syncwarp();
                     // ---- split + fast Griffin-Lim update; new angles into ex[0..128]
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int k = lane + 32 * j;
-                        const float er = 0.5f * (zk[j].x + zn[j].x), ei = 0.5f * (zk[j].y - zn[j].y);
-                        const float dr = 0.5f * (zk[j].x - zn[j].x), di = 0.5f * (zk[j].y + zn[j].y);
-                        const float2 w = sm.tw256[k];
-                        const float xr = er + (di * w.x + dr * w.y);
-                        const float xi = ei + (di * w.y - dr * w.x);
-                        const float ar = xr - mom * tp[j].x, ai = xi - mom * tp[j].y;
-                        const float den = r_hypot(ar, ai) + r_tiny<float>();
-                        ex[k] = make_float2(ar / den * sv[j], ai / den * sv[j]);
-                        Tp[row + k] = make_float2(xr, xi);
+                        const R er = half * (zk[j].x + zn[j].x), ei = half * (zk[j].y - zn[j].y);
+                        const R dr = half * (zk[j].x - zn[j].x), di = half * (zk[j].y + zn[j].y);
+                        const Cx<R> w = w256[j];
+                        const R xr = er + (di * w.x + dr * w.y);
+                        const R xi = ei + (di * w.y - dr * w.x);
+                        const R ar = xr - mom * tp[j].x, ai = xi - mom * tp[j].y;
+                        ex[k] = unit_times<R>(ar, ai, sv[j]);
+                        Tp[row + k] = Cx<R>{xr, xi};
                     }
                     if (lane == 0) {
-                        const float xr = z0.x - z0.y;  // Nyquist bin: real
-                        const float ar = xr - mom * tp128.x, ai = -mom * tp128.y;
-                        const float den = r_hypot(ar, ai) + r_tiny<float>();
-                        ex[128] = make_float2(ar / den * sv128, ai / den * sv128);
-                        Tp[row + 128] = make_float2(xr, 0.f);
+                        const R xr = z0.x - z0.y;  // Nyquist bin: real
+                        const R ar = xr - mom * tp128.x, ai = -mom * tp128.y;
+                        ex[128] = unit_times<R>(ar, ai, sv128);
+                        Tp[row + 128] = Cx<R>{xr, 0};
                     }
                 } else {
-                    // initial angles: S * exp(i phase0)
+                    // initial angles: S * exp(i phase0), unit phasors from the host table [129][frames]
+                    const double2* ph = reinterpret_cast<const double2*>(p.phase0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int k = lane + 32 * j;
-                        double sn, cs;
-                        sincos(p.phase0[(size_t)k * frames + t], &sn, &cs);
-                        ex[k] = make_float2((float)((double)sv[j] * cs), (float)((double)sv[j] * sn));
+                        const double2 u = __ldg(ph + (size_t)k * frames + t);
+                        ex[k] = Cx<R>{(R)((double)sv[j] * u.x), (R)((double)sv[j] * u.y)};
                     }
                     if (lane == 0) {
-                        double sn, cs;
-                        sincos(p.phase0[(size_t)128 * frames + t], &sn, &cs);
-                        ex[128] = make_float2((float)((double)sv128 * cs), (float)((double)sv128 * sn));
+                        const double2 u = __ldg(ph + (size_t)128 * frames + t);
+                        ex[128] = Cx<R>{(R)((double)sv128 * u.x), (R)((double)sv128 * u.y)};
                     }
                 }
                 __syncwarp();
                 // ---- inverse: c2r pre-twiddle, FFT, window, overlap-add into the next signal
-                float2 z[4];
+                Cx<R> z[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int k = lane + 32 * j;
-                    float2 xk = ex[k], xn = ex[128 - k];
+                    Cx<R> xk = ex[k], xn = ex[128 - k];
                     if (k == 0) {  // c2r transforms ignore the imaginary parts of DC and Nyquist
-                        xk.y = 0.f;
-                        xn.y = 0.f;
+                        xk.y = 0;
+                        xn.y = 0;
                     }
-                    const float er = 0.5f * (xk.x + xn.x), ei = 0.5f * (xk.y - xn.y);
-                    const float dr = 0.5f * (xk.x - xn.x), di = 0.5f * (xk.y + xn.y);
-                    const float2 w = sm.tw256[k];
-                    const float c = w.x, s = -w.y;  // e^{+2 pi i k / 256}
-                    const float orr = dr * c - di * s, oi = dr * s + di * c;
-                    z[j] = make_float2(er - oi, ei + orr);
+                    const R er = half * (xk.x + xn.x), ei = half * (xk.y - xn.y);
+                    const R dr = half * (xk.x - xn.x), di = half * (xk.y + xn.y);
+                    const R c = w256[j].x, s = -w256[j].y;  // e^{+2 pi i k / 256}
+                    const R orr = dr * c - di * s, oi = dr * s + di * c;
+                    z[j] = Cx<R>{er - oi, ei + orr};
                 }
-                fft128<true>(z, ex, sm.tw128, lane);
-                float* yo = ynext + HOP * t;
+                fft128<R, true>(z, ex, sm.tw128, lane);
+                R* yo = ynext + HOP * t;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    float2* dst = reinterpret_cast<float2*>(yo + 2 * n_out[q]);
-                    float2 acc = *dst;
-                    acc.x = fmaf(win_out[q].x, z[q].x, acc.x);
-                    acc.y = fmaf(win_out[q].y, z[q].y, acc.y);
+                    Cx<R>* dst = reinterpret_cast<Cx<R>*>(yo + 2 * n_out[q]);
+                    const Cx<R> w = *reinterpret_cast<const Cx<R>*>(sm.win + 2 * n_out[q]);
+                    Cx<R> acc = *dst;
+                    acc.x += w.x * (z[q].x * inv_n);
+                    acc.y += w.y * (z[q].y * inv_n);
                     *dst = acc;
                 }
             }
@@ -565,22 +606,23 @@ __global__ void __launch_bounds__(FTHREADS, 2) griffinlim_fused_kernel(const GlP
         // ---- divide by the window sum of squares (centre padding -> 0), clear the consumed buffer, swap
         for (int n = tid; n < len4; n += FTHREADS) {
             ynext[n] *= sm.inv_wss[n];
-            ycur[n] = 0.f;
+            ycur[n] = 0;
         }
         __syncthreads();
-        float* tmp = ycur;
+        R* tmp = ycur;
         ycur = ynext;
         ynext = tmp;
     }
     const int out_len = HOP * (frames - 1);
-    float* w = static_cast<float*>(p.wave) + (size_t)item * out_len;
+    R* w = static_cast<R*>(p.wave) + (size_t)item * out_len;
     for (int n = tid; n < out_len; n += FTHREADS) w[n] = ycur[n + NFFT / 2];
 }
 
+template <typename R>
 size_t smem_bytes(int frames) {
     const int len = NFFT + HOP * (frames - 1);
     const int len4 = (len + 3) & ~3;
-    return sizeof(float) * (3 * (size_t)len4 + NFFT) + sizeof(float2) * (96 + 132 + (size_t)FW * EX);
+    return sizeof(R) * (3 * (size_t)len4 + NFFT) + sizeof(Cx<R>) * (96 + 132 + (size_t)FW * EX);
 }
 
 }  // namespace fused
@@ -613,12 +655,20 @@ extern "C" int tq_logspec_griffinlim(const float* rep, const double* phase0, voi
     p.rep = rep; p.phase0 = phase0; p.wave = wave; p.ws = ws; p.items = items; p.frames = frames; p.n_iter = n_iter;
     p.log_clip = log_clip; p.log_max = log_max; p.mom = momentum / (1.0 + momentum);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // product path: the fused kernel in the requested arithmetic; TQ_GL_LEGACY=1 selects the unfused kernels (kept as an
+    // independent cross-check of the fused ones)
     const char* legacy = getenv("TQ_GL_LEGACY");
-    if (precision == TQ_F32 && !(legacy && legacy[0] == '1')) {
-        const size_t smem = fused::smem_bytes(frames);
+    const bool use_legacy = legacy && legacy[0] == '1';
+    if (!use_legacy && precision == TQ_F32) {
+        const size_t smem = fused::smem_bytes<float>(frames);
         TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");
-        TQ_CUDA(cudaFuncSetAttribute(fused::griffinlim_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused::griffinlim_fused_kernel<<<items, fused::FTHREADS, smem, st>>>(p);
+        TQ_CUDA(cudaFuncSetAttribute(fused::griffinlim_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fused::griffinlim_fused_kernel<float><<<items, fused::FTHREADS, smem, st>>>(p);
+    } else if (!use_legacy) {
+        const size_t smem = fused::smem_bytes<double>(frames);
+        TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");
+        TQ_CUDA(cudaFuncSetAttribute(fused::griffinlim_fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fused::griffinlim_fused_kernel<double><<<items, fused::FTHREADS, smem, st>>>(p);
     } else if (precision == TQ_F32) {
         const size_t smem = gl_smem_bytes<float>(frames);
         TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");

@@ -24,9 +24,12 @@
 //                           arrives there by TMA (issued before the accumulator is ready), the warp adds
 //                           bias / per-sample embedding / residual to its tcgen05.ld rows in place, and the
 //                           result leaves by TMA store (coalesced, clipped at the tensor edge, asynchronous).
-//                           The GroupNorm statistics of the consumer (per-(sample, channel) sum and sum of
-//                           squares) are column sums over the same staging buffer + one float4 atomic per
-//                           lane.  fp32 outputs (embedding GEMM, the two ragged Cout in {3, 8} convs) use
+//                           The GroupNorm statistics of the consumer (per-(sample, tile, channel) sum and sum of
+//                           squares) are column sums over the same staging buffers, written with plain stores into a
+//                           slot only this tile owns (no atomics: bit-reproducible); samples that span several
+//                           epilogue warps of a tile are summed across the four staging buffers of a column half
+//                           behind a 128-thread named barrier.
+//                           fp32 outputs (embedding GEMM, the two ragged Cout in {3, 8} convs) use
 //                           direct stores.
 //
 // Activations are channels-last, so the 128x64 A tile of a slice is the TMA box

@@ -16,7 +16,7 @@ from torch import nn
 
 from . import _lib
 from .autoencoder import LightningAutoencoder
-from .engine import current_stream_ptr, nchw_to_nhwc, nhwc_to_nchw, require_cuda, tq_dtype
+from .engine import current_stream_ptr, device_guard, nchw_to_nhwc, nhwc_to_nchw, require_cuda, tq_dtype
 from .lightning_shim import LightningModule
 from .lowering import get_coder_plan, get_unet_plan
 from .nn import append_dims
@@ -90,13 +90,15 @@ class _SideStream:
         self.owner, self.ctx = owner, None
 
     def __enter__(self):
-        self.cur = torch.cuda.current_stream()
+        dev = torch.cuda.current_device()   # the module's device: callers enter under device_guard
+        self.cur = torch.cuda.current_stream(dev)
         if self.cur.cuda_stream != 0:
             return self
-        s = self.owner.__dict__.get("_tq_stream")
+        streams = self.owner.__dict__.setdefault("_tq_streams", {})
+        s = streams.get(dev)
         if s is None:
-            s = torch.cuda.Stream()
-            self.owner.__dict__["_tq_stream"] = s
+            s = torch.cuda.Stream(device=dev)
+            streams[dev] = s
         s.wait_stream(self.cur)
         self.s = s
         self.ctx = torch.cuda.stream(s)
@@ -149,7 +151,7 @@ class LightningEDM(LightningModule):
         dim = sample.dim()
         sample_in = sample * append_dims(self.edm.in_scaling(sigma), dim)
         inp = sample_in if cond_sample is None else torch.cat((sample_in, cond_sample), dim=1)
-        out = self.unet(inp, self.edm.noise_conditioning(sigma), cond=cond)
+        out = self.unet(inp, self.edm.noise_conditioning(sigma), cond=cond)   # device-guarded in UNetModel.forward
         skip = append_dims(self.edm.skip_scaling(sigma), dim) * sample
         return out * append_dims(self.edm.out_scaling(sigma), dim) + skip
 
@@ -175,9 +177,11 @@ class LightningEDM(LightningModule):
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("tqdne_b200: LightningEDM.sample needs the module on a CUDA device (no CPU path)")
-        shape = tuple(shape)
+        with device_guard(dev):
+            return self._sample(tuple(shape), cond, noise, generator, dev)
+
+    def _sample(self, shape, cond, noise, generator, dev):
         if self.autoencoder:
-            full_shape = shape
             shape = self.latent_shape(shape)
             if noise is None and self.compat_rng:
                 # reference: encode(zeros) draws randn_like(mean) before the sampler noise (autoencoder.py:39)
@@ -194,19 +198,27 @@ class LightningEDM(LightningModule):
         spatial = shape[2:]
         P = math.prod(spatial)
         micro = max(1, min(N, self.max_positions_per_pass // P))
+        churn = None
+        if not self.deterministic_sampling:
+            # stochastic sampler: the per-step churn noise (reference: th.randn_like(sample_curr), edm.py:204) is drawn for
+            # the WHOLE batch, step by step, from the caller's generator -- reproducible for a given generator and
+            # independent of the micro-batching below
+            churn = [torch.randn(shape, device=dev, dtype=torch.float64, generator=generator)
+                     for _ in range(self.num_sampling_steps)]
         with self._engine_stream():
             outs = []
             for i0 in range(0, N, micro):
                 i1 = min(N, i0 + micro)
                 c = cond[i0:i1] if cond is not None else None
-                outs.append(self._sample_chunk(eps[i0:i1].contiguous(), sigmas, c))
+                nz = [z[i0:i1] for z in churn] if churn is not None else None
+                outs.append(self._sample_chunk(eps[i0:i1].contiguous(), sigmas, c, noises=nz))
             x = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)   # fp64 channels-last [N, P, C]
             C_ = shape[1]
             if not self.autoencoder:
                 result = nhwc_to_nchw(x, N, C_, spatial, C_, torch.float32)
             else:
                 result = self._decode_latents(x, N, C_, spatial)
-        result.record_stream(torch.cuda.current_stream())
+        result.record_stream(torch.cuda.current_stream(dev))
         return result
 
     def _engine_stream(self):
@@ -214,8 +226,9 @@ class LightningEDM(LightningModule):
         is ordered after / before the caller's current stream."""
         return _SideStream(self)
 
-    def _sample_chunk(self, eps: torch.Tensor, sigmas: torch.Tensor, cond) -> torch.Tensor:
-        """Deterministic / stochastic Heun loop on one micro-batch; returns the fp64 channels-last state."""
+    def _sample_chunk(self, eps: torch.Tensor, sigmas: torch.Tensor, cond, noises=None) -> torch.Tensor:
+        """Deterministic / stochastic Heun loop on one micro-batch; returns the fp64 channels-last state.
+        `noises`: per-step unit normal fp64 tensors of eps.shape for the stochastic sampler (drawn here when None)."""
         lib = _lib.lib()
         n, C_ = eps.shape[0], eps.shape[1]
         spatial = tuple(eps.shape[2:])
@@ -271,7 +284,11 @@ class LightningEDM(LightningModule):
                 # x_hat = x + S_noise * randn * sqrt(sigma_hat^2 - sigma^2)   (reference: edm.py:203-207)
                 s_hat, s_cur = hats[i], sigmas[i]
                 scale = float((s_hat**2 - s_cur**2) ** 0.5) * self.edm.S_noise
-                nz = torch.randn(x.shape, device=dev, dtype=torch.float64)
+                if noises is not None:
+                    assert tuple(noises[i].shape) == tuple(eps.shape), "per-step noise must have the shape of eps"
+                    nz = nchw_to_nhwc(noises[i].to(dev, torch.float64), torch.float64)
+                else:
+                    nz = nchw_to_nhwc(torch.randn(eps.shape, device=dev, dtype=torch.float64), torch.float64)
                 _lib.check(lib.tq_edm_add_noise(x.data_ptr(), nz.data_ptr(), scale, x.numel(), st), "add_noise")
                 _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), dt_, NP, C_, Cpad, cur.c_in, st), "precondition")
             dt = dts[i]
@@ -310,33 +327,33 @@ class LightningEDM(LightningModule):
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     # reference API: the two samplers are also callable on their own with explicit eps (edm.py:171-230)
-    @torch.no_grad()
-    def sample_deterministically(self, eps, sigmas, cond_sample=None, cond=None):
-        assert cond_sample is None, "cond_sample is not lowered"
+    def _run_sampler(self, eps, sigmas, cond, deterministic: bool, noises=None):
         keep = self.deterministic_sampling
-        self.deterministic_sampling = True
+        self.deterministic_sampling = deterministic
         try:
-            with self._engine_stream():
-                x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond)
+            with device_guard(eps.device), self._engine_stream():
+                x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond, noises=noises)
                 out = nhwc_to_nchw(x, eps.shape[0], eps.shape[1], tuple(eps.shape[2:]), eps.shape[1], torch.float64)
         finally:
             self.deterministic_sampling = keep
-        out.record_stream(torch.cuda.current_stream())
+        out.record_stream(torch.cuda.current_stream(eps.device))
         return out
 
     @torch.no_grad()
-    def sample_stochastically(self, eps, sigmas, cond_sample=None, cond=None):
+    def sample_deterministically(self, eps, sigmas, cond_sample=None, cond=None):
         assert cond_sample is None, "cond_sample is not lowered"
-        keep = self.deterministic_sampling
-        self.deterministic_sampling = False
-        try:
-            with self._engine_stream():
-                x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond)
-                out = nhwc_to_nchw(x, eps.shape[0], eps.shape[1], tuple(eps.shape[2:]), eps.shape[1], torch.float64)
-        finally:
-            self.deterministic_sampling = keep
-        out.record_stream(torch.cuda.current_stream())
-        return out
+        return self._run_sampler(eps, sigmas, cond, True)
+
+    @torch.no_grad()
+    def sample_stochastically(self, eps, sigmas, cond_sample=None, cond=None, noises=None, generator=None):
+        """reference: edm.py:198-230.  Engine extensions: `noises` = the per-step unit normal draws (one fp64 tensor of
+        eps.shape per Heun step, what the reference takes from th.randn_like), else drawn from `generator`."""
+        assert cond_sample is None, "cond_sample is not lowered"
+        if noises is None:
+            noises = [torch.randn(eps.shape, device=eps.device, dtype=torch.float64, generator=generator)
+                      for _ in range(self.num_sampling_steps)]
+        assert len(noises) == self.num_sampling_steps, "one noise tensor per Heun step"
+        return self._run_sampler(eps, sigmas, cond, False, noises=noises)
 
     @torch.no_grad()
     def evaluate(self, batch):
@@ -354,17 +371,25 @@ class LightningEDM(LightningModule):
                                       "cond_signal (train_1d_edm config); train the other models with the reference package")
         x = batch["signal"]
         key = (x.shape[0], x.shape[-1])
-        ts = self.__dict__.get("_tq_train")
-        if ts is None or ts[0] != key:
+        tapes = self.__dict__.setdefault("_tq_train", {})
+        ts = tapes.get(key)
+        if ts is None:
+            # a new (batch, length): a new static tape over the SAME parameter / Adam / EMA state and schedule position
+            # (a ragged last batch or an evaluation batch must not restart training)
             op = self.optimizer_params or {}
-            ts = (key, TrainStep1D(self, x.shape[0], x.shape[-1], lr=op.get("learning_rate", 1e-4),
-                                   max_steps=op.get("max_steps", 100000), eta_min=op.get("eta_min", 0.0)))
-            self.__dict__["_tq_train"] = ts
-        return ts[1]
+            shared = next(iter(tapes.values())).store if tapes else None
+            ts = TrainStep1D(self, x.shape[0], x.shape[-1], lr=op.get("learning_rate", 1e-4),
+                             max_steps=op.get("max_steps", 100000), eta_min=op.get("eta_min", 0.0), store=shared)
+            if len(tapes) >= 4:   # bound the memory held by tapes of odd shapes
+                tapes.pop(next(k for k in tapes if k != key))
+            tapes[key] = ts
+        self.__dict__["_tq_train_last"] = ts
+        return ts
 
     def step(self, batch, batch_idx=0):
         """Loss of one batch (reference: edm.py:115-134); the gradients are left in the step's flat buffer."""
-        return self._train_step(batch).forward_backward(batch["signal"], batch.get("cond"))
+        with device_guard(self.device):
+            return self._train_step(batch).forward_backward(batch["signal"], batch.get("cond"))
 
     def training_step(self, batch, batch_idx=0):
         """Loss, gradients, gradient all-reduce over the initialised process group, Adam (cosine schedule) and EMA
@@ -372,15 +397,16 @@ class LightningEDM(LightningModule):
         ema.py:24-28).  `sync_trained_weights()` writes the master (or EMA) parameters back into the module."""
         import torch.distributed as dist
 
-        ts = self._train_step(batch)
-        loss = ts.forward_backward(batch["signal"], batch.get("cond"))
-        ts.optimizer_step(dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1)
+        with device_guard(self.device):
+            ts = self._train_step(batch)
+            loss = ts.forward_backward(batch["signal"], batch.get("cond"))
+            ts.optimizer_step(dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1)
         return loss
 
     def sync_trained_weights(self, ema: bool = False):
-        ts = self.__dict__.get("_tq_train")
+        ts = self.__dict__.get("_tq_train_last")
         if ts is not None:
-            ts[1].sync_module(ema=ema)
+            ts.sync_module(ema=ema)
 
     def validation_step(self, batch, batch_idx=0):  # pragma: no cover
         raise NotImplementedError("tqdne_b200: validation-time sampling is `evaluate(batch)`; there is no validation loss path")

@@ -47,7 +47,19 @@ def require_cuda(t: torch.Tensor, name: str = "tensor") -> None:
 
 
 def current_stream_ptr() -> int:
+    """Raw handle of the CURRENT device's current stream: every public entry point runs under `device_guard`, so the
+    current device is the one that owns the tensors / plans being used."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def device_guard(device):
+    """Make `device` (of the module's parameters or of the input tensor) the current CUDA device for the duration of a
+    call: streams, CUDA-graph capture, the C-ABI launches and the SM count used by the plan builders all follow the
+    current device, not the device of the pointers they are handed."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"tqdne_b200: expected a CUDA device, got {device}; this engine has no CPU path.")
+    return torch.cuda.device(device)
 
 
 # ------------------------------------------------------------------------------------------------

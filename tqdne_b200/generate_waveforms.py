@@ -157,16 +157,30 @@ def generate(hypocentral_distance, magnitude, vs30, hypocentre_depth, azimuthal_
 
     lo, hi = sharding.shard_bounds(n_total, rank, world)
     print(f"generating waveforms {lo}..{hi} of {n_total} using {device}...")
-    local = torch.empty((hi - lo, 3, config.t), device=device, dtype=torch.float32)
-    for i in range(lo, hi, batch_size):
-        j = min(hi, i + batch_size)
-        c = torch.tensor(cond[i:j], device=device, dtype=torch.float32)
-        noise = sharding.global_noise(edm.latent_shape((j - i, 3, 128, 128))[1:], i, j, seed, device)
-        sample = edm.sample([j - i, 3, 128, 128], cond=c, noise=noise)
-        local[i - lo:j - lo] = config.representation.invert_representation_device(sample)
-    full = sharding.gather_waveforms(local, n_total)
-    if full is not None and rank == 0:
-        out = write_outputs(outfile, features, sharding.to_host(full).numpy())
+    # The shard is processed in rounds of `batch_size` rows per rank; every round is gathered to rank 0 (the one
+    # collective of the path) and copied into the host array right away, so device memory holds one batch per rank,
+    # not the whole job, and the reference's streaming behaviour (generate_waveforms.py:186-193 writes batch by batch)
+    # is kept.  Waveforms leave the fp64 Griffin-Lim kernel and are stored as float32 like the reference's dataset.
+    shards = [sharding.shard_bounds(n_total, r, world) for r in range(world)]
+    rounds = max(-(-(h - l) // batch_size) for l, h in shards) if n_total else 0
+    host = np.empty((n_total, 3, config.t), dtype=np.float32) if rank == 0 else None
+    for k in range(rounds):
+        i, j = min(hi, lo + k * batch_size), min(hi, lo + (k + 1) * batch_size)
+        if j > i:
+            c = torch.tensor(cond[i:j], device=device, dtype=torch.float32)
+            noise = sharding.global_noise(edm.latent_shape((j - i, 3, 128, 128))[1:], i, j, seed, device)
+            sample = edm.sample([j - i, 3, 128, 128], cond=c, noise=noise)
+            wav = config.representation.invert_representation_device(sample).to(torch.float32)
+        else:
+            wav = torch.empty((0, 3, config.t), device=device, dtype=torch.float32)
+        spans = [(min(h, l + k * batch_size), min(h, l + (k + 1) * batch_size)) for l, h in shards]
+        parts = sharding.gather_ragged(wav, [b - a for a, b in spans])
+        if rank == 0:
+            for (a, b), part in zip(spans, parts):
+                if b > a:
+                    host[a:b] = sharding.to_host(part).numpy()
+    if rank == 0:
+        out = write_outputs(outfile, features, host)
         print(f"done! -> {out}")
         return out
     return None

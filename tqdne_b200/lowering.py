@@ -12,7 +12,7 @@ from torch import nn
 
 from . import blocks as B
 from . import unet as U
-from .engine import Act, Plan, nchw_to_nhwc, nhwc_to_nchw, pack_conv, require_cuda
+from .engine import Act, Plan, device_guard, nchw_to_nhwc, nhwc_to_nchw, pack_conv, require_cuda
 
 MODES = {torch.bfloat16: "bf16", torch.float32: "fp32"}
 
@@ -278,13 +278,14 @@ def unet_forward(model: U.UNetModel, x: torch.Tensor, timesteps: torch.Tensor, c
     N, Cc = x.shape[0], x.shape[1]
     spatial = tuple(x.shape[2:])
     assert len(spatial) == model.dims, f"expected {model.dims} spatial dims"
-    p = get_unet_plan(model, N, spatial, uniform_t=False)
-    xin = nchw_to_nhwc(x.to(torch.float32), p.act_dtype, p.cin_pad)
-    p.xin.t.copy_(xin.view(-1))
-    p.set_t(timesteps)
-    p.set_cond(cond)
-    p.run()
-    return nhwc_to_nchw(p.out.t, N, model.out_channels, spatial, model.out_channels, x.dtype)
+    with device_guard(x.device):
+        p = get_unet_plan(model, N, spatial, uniform_t=False)
+        xin = nchw_to_nhwc(x.to(torch.float32), p.act_dtype, p.cin_pad)
+        p.xin.t.copy_(xin.view(-1))
+        p.set_t(timesteps)
+        p.set_cond(cond)
+        p.run()
+        return nhwc_to_nchw(p.out.t, N, model.out_channels, spatial, model.out_channels, x.dtype)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -346,9 +347,10 @@ def run_coder(net: nn.Module, x: torch.Tensor, kind: str) -> torch.Tensor:
     require_cuda(x, "x")
     N = x.shape[0]
     spatial = tuple(x.shape[2:])
-    p = get_coder_plan(net, kind, N, spatial)
-    xin = nchw_to_nhwc(x.to(torch.float32), p.act_dtype, p.cin_pad)
-    p.xin.t.copy_(xin.view(-1))
-    p.run()
-    so = (p.out.H, p.out.W) if len(spatial) == 2 else (p.out.W,)
-    return nhwc_to_nchw(p.out.t, N, p.cout, so, p.cout, x.dtype)
+    with device_guard(x.device):
+        p = get_coder_plan(net, kind, N, spatial)
+        xin = nchw_to_nhwc(x.to(torch.float32), p.act_dtype, p.cin_pad)
+        p.xin.t.copy_(xin.view(-1))
+        p.run()
+        so = (p.out.H, p.out.W) if len(spatial) == 2 else (p.out.W,)
+        return nhwc_to_nchw(p.out.t, N, p.cout, so, p.cout, x.dtype)

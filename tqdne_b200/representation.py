@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from ._lib import TQ_F32, TQ_F64
-from .engine import current_stream_ptr
+from .engine import current_stream_ptr, device_guard
 
 
 def _as_cuda_f32(x, device=None) -> torch.Tensor:
@@ -34,6 +34,18 @@ def _as_cuda_f32(x, device=None) -> torch.Tensor:
                                "(there is no CPU fallback)")
         x = x.to(device or "cuda")
     return x.to(torch.float32).contiguous()
+
+
+def _on_input_device(fn):
+    """Run a *_device method with the input's CUDA device current (streams and launches follow the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, x, *a, **k):
+        x = _as_cuda_f32(x)
+        with device_guard(x.device):
+            return fn(self, x, *a, **k)
+    return wrapper
 
 
 class Representation:
@@ -75,6 +87,7 @@ class MovingAverageEnvelope(Representation):
     def __init__(self, window_size=128, log_eps=1e-6, eps=1e-6):
         self.window_size, self.log_eps, self.eps = window_size, log_eps, eps
 
+    @_on_input_device
     def get_representation_device(self, waveform) -> torch.Tensor:
         """[.., channels, L] -> [.., 2*channels, L] on the device (reference: representation.py:47-55)."""
         w = _as_cuda_f32(waveform)
@@ -88,6 +101,7 @@ class MovingAverageEnvelope(Representation):
     def get_representation(self, waveform):
         return self.get_representation_device(waveform).cpu().numpy()
 
+    @_on_input_device
     def invert_representation_device(self, representation) -> torch.Tensor:
         rep = _as_cuda_f32(representation)
         lead, (c2, L) = rep.shape[:-2], rep.shape[-2:]
@@ -105,8 +119,11 @@ class MovingAverageEnvelope(Representation):
 class LogSpectrogram(Representation):
     """Log-magnitude STFT in [-1, 1]; inverse = exp + fast Griffin-Lim (reference: representation.py:63-175).
 
-    Extra keyword (engine extension): `precision` = "fp32" (default) or "fp64" arithmetic for Griffin-Lim
-    (the reference runs complex128 under NumPy >= 2 and complex64 under NumPy 1.x).
+    Extra keyword (engine extension): `precision` = "fp64" (default) or "fp32" arithmetic for Griffin-Lim.  The
+    reference's locked environment (uv.lock: NumPy 2.2.5) promotes the float32 spectrogram to float64 before librosa, so
+    the reference runs complex128: fp64 is the parity mode (kernel = NumPy oracle to 1e-9).  128 momentum iterations
+    amplify rounding ~1e3x (NumPy's own complex64 run differs from its complex128 run by 1e-4 .. 1e-3 on decoded
+    spectrograms, worst items 1e-1), so "fp32" is an explicit opt-in fast mode, not a parity mode.
     `library` and `multiprocessing` are accepted for signature compatibility and ignored: there is no
     librosa / process pool here.
     """
@@ -116,7 +133,7 @@ class LogSpectrogram(Representation):
     random_state = 0
 
     def __init__(self, stft_channels=256, hop_size=None, clip=1e-8, log_max=3, library="librosa", multiprocessing=True,
-                 precision="fp32"):
+                 precision="fp64"):
         self.clip = clip
         self.log_clip = np.log(clip)
         self.log_max = log_max
@@ -134,6 +151,7 @@ class LogSpectrogram(Representation):
         """Kept for API compatibility (reference: representation.py:135-138); nothing to close."""
 
     # ---- forward (the step before the sampling path) ---------------------------------------------------
+    @_on_input_device
     def get_representation_device(self, waveform) -> torch.Tensor:
         """waveforms [.., L] -> normalised log-magnitude STFT [.., n_fft/2, 1 + L/hop] in [-1, 1] as a CUDA tensor
         (reference: get_spectrogram + get_representation, representation.py:140-150,163-169; librosa stft semantics)."""
@@ -161,10 +179,12 @@ class LogSpectrogram(Representation):
         key = (frames, str(device))
         if key not in self._phase:
             rng = np.random.RandomState(seed=self.random_state)
-            u = rng.random(size=(self.stft_channels // 2 + 1, frames))
-            self._phase[key] = torch.from_numpy(2 * np.pi * u).to(device)
+            ph = 2 * np.pi * rng.random(size=(self.stft_channels // 2 + 1, frames))
+            # unit phasors exp(i ph) as (cos, sin) pairs in float64, like librosa's util.phasor
+            self._phase[key] = torch.from_numpy(np.stack([np.cos(ph), np.sin(ph)], axis=-1)).contiguous().to(device)
         return self._phase[key]
 
+    @_on_input_device
     def invert_representation_device(self, representation) -> torch.Tensor:
         """[.., n_fft/2, frames] in [-1, 1] -> waveforms [.., hop*(frames-1)] as a CUDA tensor."""
         rep = _as_cuda_f32(representation)

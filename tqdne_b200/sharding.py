@@ -65,6 +65,26 @@ def gather_waveforms(local: torch.Tensor, n_total: int, dst: int = 0) -> torch.T
     return torch.cat([stacked[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
 
 
+def gather_ragged(local: torch.Tensor, counts: list[int], dst: int = 0) -> list[torch.Tensor] | None:
+    """Gather per-rank tensors [counts[r], ...] (counts may differ and may be 0) to rank `dst`; returns the list of
+    per-rank tensors on `dst`, None elsewhere.  Single-process: [local]."""
+    rank, ws = world()
+    if ws == 1 or not (dist.is_available() and dist.is_initialized()):
+        return [local]
+    max_n = max(counts)
+    if max_n == 0:
+        return [local[:0] for _ in counts] if rank == dst else None
+    pad = local
+    if local.shape[0] != max_n:
+        pad = torch.zeros((max_n, *local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+    stacked = torch.empty((ws, max_n, *local.shape[1:]), dtype=local.dtype, device=local.device) if rank == dst else None
+    dist.gather(pad.contiguous(), list(stacked.unbind(0)) if rank == dst else None, dst=dst)
+    if rank != dst:
+        return None
+    return [stacked[r, : counts[r]] for r in range(ws)]
+
+
 _PINNED: dict = {}
 
 

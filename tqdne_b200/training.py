@@ -76,6 +76,12 @@ class _Store:
         self.n = off
         z = lambda: torch.zeros(self.n, device=device, dtype=torch.float32)  # noqa: E731
         self.P, self.G, self.M, self.V, self.EMA = z(), z(), z(), z(), z()
+        # training progress lives HERE, not in the shape-specific tapes: optimiser steps taken (the cosine schedule's
+        # position and Adam's bias correction), forward passes run (dropout counter), and a version stamp of the masters
+        # that tells a tape whether its bf16 operand copies are stale
+        self.step_count = 0
+        self.pass_count = 0
+        self.version = 0
 
     def view(self, buf: torch.Tensor, p: nn.Parameter) -> torch.Tensor:
         off, shape, _ = self.items[id(p)]
@@ -118,7 +124,10 @@ class TrainStep1D:
     """One optimisation step of `LightningEDM` with a 1D UNet: loss, gradients, Adam + EMA update."""
 
     def __init__(self, edm, N: int, L: int, *, lr: float = 1e-4, max_steps: int = 100000, eta_min: float = 0.0,
-                 ema_decay: float = 0.999, dropout: float | None = None, betas=(0.9, 0.999), eps: float = 1e-8):
+                 ema_decay: float = 0.999, dropout: float | None = None, betas=(0.9, 0.999), eps: float = 1e-8,
+                 store: "_Store | None" = None):
+        """`store`: the parameter / Adam / EMA state of an earlier TrainStep1D of the SAME model (another batch size or
+        length): the new tape trains on from it instead of restarting from the nn.Module's parameters."""
         model = edm.unet
         assert model.dims == 1, "TrainStep1D: the 1D UNet (config 5); the 2-D weight gradient is not built yet"
         dev = next(model.parameters()).device
@@ -130,12 +139,14 @@ class TrainStep1D:
         first_res = next(m for m in model.modules() if isinstance(m, U.ResBlock))
         self.p_drop = float(first_res.out_layers[2].p) if dropout is None else float(dropout)
         self.sigma_data = float(edm.edm.sigma_data)
-        self.step_count = 0
-        self.pass_count = 0
         # dropout inside the GroupNorm kernels of both passes (default) or as separate multiply passes (A/B switch)
         self.fused_dropout = os.environ.get("TQ_TRAIN_FUSED_DROPOUT", "1") != "0"
-        self.store = _Store(model, dev)
-        self.store.load_from_module()
+        if store is None:
+            self.store = _Store(model, dev)
+            self.store.load_from_module()
+        else:
+            self.store = store
+        self.copies_version = -1   # store.version the bf16 operand copies of THIS tape were made from
         self.repack: list = []     # (fp32 master view [Op, k, Ip], forward bf16 copy | None, input-gradient bf16 copy | None, ci_off, Cs)
         self.fwd: list = []
         self.bwd: list = []
@@ -461,6 +472,24 @@ class TrainStep1D:
             _lib.check(self.lib.tq_repack_conv_weights(wv.data_ptr(), fwd.data_ptr() if fwd is not None else None,
                                                        bwd.data_ptr() if bwd is not None else None, Op, k, Ip, coff, Cs, st),
                        "repack_conv_weights")
+        self.copies_version = self.store.version
+
+    # training progress is shared by every tape of the model (see _Store)
+    @property
+    def step_count(self) -> int:
+        return self.store.step_count
+
+    @step_count.setter
+    def step_count(self, v: int) -> None:
+        self.store.step_count = v
+
+    @property
+    def pass_count(self) -> int:
+        return self.store.pass_count
+
+    @pass_count.setter
+    def pass_count(self, v: int) -> None:
+        self.store.pass_count = v
 
     def lr(self) -> float:
         """CosineAnnealingLR stepped every optimiser step (edm.py:242-251)."""
@@ -474,6 +503,8 @@ class TrainStep1D:
         `sigma` / `noise` may be given explicitly (tests); otherwise they are drawn as in edm.py:125-127."""
         N, L = self.N, self.L
         assert tuple(signal.shape) == (N, self.cin, L), f"expected signal of shape {(N, self.cin, L)}"
+        if self.copies_version != self.store.version:
+            self.refresh_weights()   # another tape of this model stepped the optimiser since this one last ran
         self.y.copy_(signal.to(torch.float32).permute(0, 2, 1))
         if sigma is None:
             sigma = self.edm.edm.sigma(torch.randn(N, device=self.dev))
@@ -513,6 +544,7 @@ class TrainStep1D:
         _lib.check(self.lib.tq_adam_ema_step(s.P.data_ptr(), s.G.data_ptr(), s.M.data_ptr(), s.V.data_ptr(), s.EMA.data_ptr(), s.n,
                                              lr, self.betas[0], self.betas[1], self.eps, self.step_count, self.ema_decay,
                                              1.0 / world_size, self._st()), "adam_ema_step")
+        s.version += 1
         self.refresh_weights()
 
     def training_step(self, batch: dict, world_size: int = 1) -> torch.Tensor:
