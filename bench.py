@@ -279,6 +279,10 @@ def run_reference(args) -> None:
         "e2e": {"value": val, "unit": "waveforms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.configs != "none":
+        # BASELINE.md section 4, primary CPU config: the reference's 1D sampler, batch 4, 18 Heun steps, on the host cores
+        line["configs"] = {"cfg0": {"workload": "1D EDM UNet (train_1d_edm config), batch 4, 18 Heun steps + envelope inverse",
+                                    **cpu_cfg0()}}
     print(json.dumps(line), flush=True)
 
 
@@ -286,7 +290,12 @@ def run_reference(args) -> None:
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
 def kernel_breakdown(edm, batch, iters=3):
-    """Per-launch CUDA-event timing of one denoiser call (eager replay of the UNet plan, op by op)."""
+    """Per-kernel time of one denoiser call INSIDE the graph that the timed region replays.
+
+    The plan is replayed op by op with a CUDA event after every launch (that gives each kernel's share; the event gaps
+    make the op-by-op sum a few per cent longer than the graph), and the captured graph itself is timed over `iters` x 8
+    replays; every kernel's time is its op-by-op share x the graph time, so the shares are those of the graph that was
+    timed and they add up to it.  profiles/ holds the ncu launch list of the same call for a cross-check of the shares."""
     import torch
 
     from tqdne_b200.lowering import get_unet_plan
@@ -299,6 +308,8 @@ def kernel_breakdown(edm, batch, iters=3):
     assert len(meta) == n, (len(meta), n)
     s = torch.cuda.Stream()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n + 1)] for _ in range(iters)]
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 8 * iters
     with torch.cuda.stream(s):
         for _ in range(2):
             p.run_range(0, n)
@@ -307,7 +318,15 @@ def kernel_breakdown(edm, batch, iters=3):
             for i in range(n):
                 p.run_range(i, i + 1)
                 ev[it][i + 1].record(s)
+        p.enable_graph(True)
+        for _ in range(2):
+            p.run()
+        g0.record(s)
+        for _ in range(reps):
+            p.run()
+        g1.record(s)
     s.synchronize()
+    graph_ms = g0.elapsed_time(g1) / reps
     agg = {}
     for i in range(n):
         ms = sum(ev[it][i].elapsed_time(ev[it][i + 1]) for it in range(iters)) / iters
@@ -317,7 +336,240 @@ def kernel_breakdown(edm, batch, iters=3):
         a["launches"] += 1
         a["flops"] += meta[i][1]
         a["bytes"] += meta[i][2]
-    return agg
+    op_sum = sum(a["ms"] for a in agg.values())
+    for a in agg.values():
+        a["ms_op_by_op"] = a["ms"]
+        a["ms"] = a["ms"] / op_sum * graph_ms
+    return agg, graph_ms, op_sum
+
+
+def source_sha16(*rel_paths) -> str:
+    """Hash of the kernel sources a committed ncu capture belongs to: a capture is only quoted while it matches HEAD."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for rp in rel_paths:
+        h.update((ROOT / rp).read_bytes())
+    return h.hexdigest()[:16]
+
+
+IGEMM_SOURCES = ("tqdne_b200/csrc/tq_igemm_sm100.cu", "tqdne_b200/csrc/tq_ptx.cuh", "tqdne_b200/engine.py", "tqdne_b200/lowering.py")
+
+
+# ------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (secondary measurements inside the same driver-run line)
+# ------------------------------------------------------------------------------------------------------
+FLOP_CFG0 = 35 * 28.436e9            # 1D EDM UNet, 18 Heun steps = 35 denoiser calls at L = 4064 (BASELINE.md section 3)
+FLOP_CFG3 = 63 * 271.89e9            # pixel-space 2D UNet, 32 Heun steps = 63 denoiser calls
+FLOP_CFG4 = 3 * 28.436e9             # training step, forward + backward, per sample
+
+
+def _event_time(fn, steps, warmup, torch, barrier=None):
+    for _ in range(warmup):
+        out = fn()
+    (barrier or torch.cuda.synchronize)()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    (barrier or torch.cuda.synchronize)()
+    return e0.elapsed_time(e1) / steps, (time.perf_counter() - t0) * 1e3 / steps, out
+
+
+def build_1d_edm(steps=18, seed=0):
+    import tqdne_b200 as tq
+    from oracle.weights import seeded_state_dict, shapes_of
+    from tqdne_b200.config import MovingAverageEnvelopeConfig
+
+    cfg = MovingAverageEnvelopeConfig()
+    ucfg = tq.get_1d_unet_config(cfg, 6, 6)
+    edm = tq.LightningEDM(ucfg, {"learning_rate": 1e-4, "max_steps": 100000, "eta_min": 0.0}, num_sampling_steps=steps)
+    sd = seeded_state_dict(shapes_of(edm), seed)
+    for k in ("unet.out.2.weight", "unet.out.2.bias"):
+        sd[k] = sd[k] * 0.05   # keep the random-init output inside the representation's range
+    edm.load_state_dict(sd)
+    return edm, sd, ucfg, cfg
+
+
+def measure_cfg0(dev, pk, cpu: bool):
+    """configs[0]: 1D EDM UNet (train_1d_edm), batch 4, 18 Heun steps, [4, 6, L] -> envelope inverse -> [4, 3, L];
+    L = 4064 (the data set's length) and 4096 (the length BASELINE.json quotes).  With `cpu`, the reference's own CPU
+    path on the same config is timed next to it (primary CPU config)."""
+    import torch
+
+    edm, sd, ucfg, cfg = build_1d_edm()
+    edm.eval().to(dev).set_engine_precision("bf16")
+    out = {"workload": "1D EDM UNet (train_1d_edm config), batch 4, 18 Heun steps (35 NFE) + moving-average-envelope inverse",
+           "dtype": "bf16", "flop_per_waveform": FLOP_CFG0}
+    cond = torch.from_numpy(cond_grid(4)).to(dev)
+    for L in (4064, 4096):
+        noise = torch.randn((4, 6, L), device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(1))
+        noise_h, cond_h = noise.cpu().pin_memory(), cond.cpu().pin_memory()
+
+        def resident():
+            return cfg.representation.invert_representation_device(edm.sample((4, 6, L), cond=cond, noise=noise))
+
+        def e2e():
+            w = cfg.representation.invert_representation_device(
+                edm.sample((4, 6, L), cond=cond_h.to(dev, non_blocking=True), noise=noise_h.to(dev, non_blocking=True)))
+            return w.cpu()
+
+        ms, _, w = _event_time(resident, 10, 3, torch)
+        assert tuple(w.shape) == (4, 3, L) and bool(torch.isfinite(w).all())
+        _, wall, _ = _event_time(e2e, 10, 2, torch)
+        fl = FLOP_CFG0 * L / 4064
+        out[f"L{L}"] = {"value": 4 / ms * 1e3, "unit": "waveforms/s", "ms_per_step": ms, "e2e_value": 4 / wall * 1e3,
+                        "achieved_tflops": 4 / ms * 1e3 * fl / 1e12, "frac_of_bf16_burst_peak": 4 / ms * 1e3 * fl / 1e12 / pk["bf16_tflops"]}
+    # the same pipeline at a batch that fills the GPU (the batch-4 case is launch / latency bound by construction)
+    B = 64
+    noise = torch.randn((B, 6, 4064), device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(2))
+    cond = torch.from_numpy(cond_grid(B)).to(dev)
+    ms, _, w = _event_time(lambda: cfg.representation.invert_representation_device(edm.sample((B, 6, 4064), cond=cond, noise=noise)),
+                           3, 2, torch)
+    out["L4064_batch64"] = {"value": B / ms * 1e3, "unit": "waveforms/s", "ms_per_step": ms,
+                            "achieved_tflops": B / ms * 1e3 * FLOP_CFG0 / 1e12,
+                            "frac_of_bf16_burst_peak": B / ms * 1e3 * FLOP_CFG0 / 1e12 / pk["bf16_tflops"]}
+    if cpu:
+        out["cpu_baseline"] = cpu_cfg0(sd, ucfg)
+    return out
+
+
+def cpu_cfg0(sd=None, ucfg=None, L=4064):
+    """The reference's CPU generate path on configs[0]: LightningEDM.sample_deterministically (unmodified reference when
+    /root/reference exists, else the oracle port) + MovingAverageEnvelope inverse, batch 4, 18 Heun steps, all host cores."""
+    import torch
+
+    from oracle import reference_loader, torch_ref
+
+    if sd is None:
+        _, sd, ucfg, _ = build_1d_edm()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(5)
+    noise = torch.randn((4, 6, L), generator=gen, dtype=torch.float64)
+    cond = torch.from_numpy(cond_grid(4))
+    kind = "port"
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        if reference_loader.available():
+            ref = reference_loader.load()
+            mod = ref.edm.LightningEDM(ucfg, {}, num_sampling_steps=18)
+            mod.load_state_dict(sd)
+            mod.eval()
+            sig = mod.edm.sampling_sigmas(18)
+            t0 = time.perf_counter()
+            x = mod.sample_deterministically(noise * sig[0], sig, None, cond)
+            kind = "reference"
+        else:
+            sig = torch_ref.sampling_sigmas(18)
+            x = torch_ref.heun_sample(sd, ucfg, noise * sig[0], sig, cond)
+        w = torch_ref.mavg_envelope_inverse(x.float().numpy())
+    dt = time.perf_counter() - t0
+    assert w.shape == (4, 3, L)
+    return {"value": 4 / dt, "unit": "waveforms/s", "cores": cores, "kind": kind,
+            "sample": f"the whole config: 4 x [6, {L}], 18 Heun steps (35 NFE) + envelope inverse, {dt:.1f} s on the host"}
+
+
+def measure_cfg3(dev, pk, batch=1024):
+    """configs[3]: pixel-space 2D log-spectrogram EDM UNet (train_edm), batch 1024, 32 Heun steps (63 NFE) at
+    [3, 128, 128] + Griffin-Lim; sample() micro-batches (max_positions_per_pass).  One timed pass (~20 s)."""
+    import torch
+
+    import tqdne_b200 as tq
+    from oracle.weights import seeded_state_dict, shapes_of
+    from tqdne_b200.config import SpectrogramConfig
+
+    cfg = SpectrogramConfig()
+    edm = tq.LightningEDM(tq.get_2d_unet_config(cfg, 3, 3), {}, num_sampling_steps=32)
+    sd = seeded_state_dict(shapes_of(edm), 0)
+    for k in ("unet.out.2.weight", "unet.out.2.bias"):
+        sd[k] = sd[k] * 0.05
+    edm.load_state_dict(sd)
+    edm.eval().to(dev).set_engine_precision("bf16")
+    micro = max(1, edm.max_positions_per_pass // (128 * 128))
+    cond = torch.from_numpy(cond_grid(batch)).to(dev)
+    noise = torch.randn((batch, 3, 128, 128), device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(1))
+
+    def run(n):
+        rep = edm.sample((n, 3, 128, 128), cond=cond[:n], noise=noise[:n])
+        return cfg.representation.invert_representation_device(torch.tanh(rep))
+
+    run(2 * micro)                      # warm-up: builds and captures the micro-batch plan the full pass replays
+    ms, _, w = _event_time(lambda: run(batch), 1, 0, torch)
+    assert tuple(w.shape) == (batch, 3, cfg.t) and bool(torch.isfinite(w).all())
+    tf = batch / ms * 1e3 * FLOP_CFG3 / 1e12
+    return {"workload": "pixel-space 2D log-spectrogram EDM UNet (train_edm config), 32 Heun steps (63 NFE) + Griffin-Lim",
+            "batch": batch, "micro_batch": micro, "dtype": "bf16", "value": batch / ms * 1e3, "unit": "waveforms/s",
+            "ms_per_step": ms, "flop_per_waveform": FLOP_CFG3, "achieved_tflops": tf, "frac_of_bf16_burst_peak": tf / pk["bf16_tflops"],
+            "frac_of_bf16_sustained_peak": tf / pk["bf16_tflops_sustained"]}
+
+
+def measure_cfg4(dev, pk, world, rank, barrier, batch=64):
+    """configs[4]: 1D EDM UNet bf16 training step (forward + backward, NCCL gradient all-reduce, Adam + EMA), batch 64 per
+    GPU (512 at 8 GPUs), dropout active, through LightningEDM.training_step."""
+    import torch
+    import torch.distributed as dist
+
+    edm, _, _, _ = build_1d_edm()
+    edm.to(dev)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    batch_d = {"signal": torch.randn(batch, 6, 4064, device=dev, generator=g), "cond": torch.randn(batch, 5, device=dev, generator=g)}
+    ms, wall, loss = _event_time(lambda: edm.training_step(batch_d), 10, 3, torch, barrier)
+    t = torch.tensor([max(ms, wall)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    assert bool(torch.isfinite(loss)), "non-finite training loss"
+    sps = batch * world / ms * 1e3
+    tf = sps / world * FLOP_CFG4 / 1e12
+    edm.__dict__.pop("_tq_train", None)
+    return {"workload": "1D EDM UNet bf16 training step (fwd + bwd + gradient all-reduce + Adam + EMA), [64, 6, 4064] per GPU",
+            "batch_per_gpu": batch, "global_batch": batch * world, "dtype": "bf16", "value": sps, "unit": "samples/s",
+            "ms_per_step": ms, "flop_per_sample": FLOP_CFG4, "achieved_tflops_per_gpu": tf,
+            "frac_of_bf16_burst_peak": tf / pk["bf16_tflops"], "allreduce": "NCCL, flat fp32 gradient buffer" if world > 1 else None}
+
+
+def measure_cfg2(args, dev, pk, world, rank, barrier, total=8192):
+    """configs[2]: the latent pipeline at a GLOBAL batch of 8192 conditioned on the magnitude / distance / vs30 grid,
+    split over the N ranks (strong scaling of a fixed job); the final gather of 8192 x [3, 4064] float32 waveforms
+    (400 MB) to rank 0 and its read-back to the host are inside the end-to-end time."""
+    import torch
+    import torch.distributed as dist
+
+    import tqdne_b200 as tq
+    from tqdne_b200 import sharding
+    from tqdne_b200.config import LatentSpectrogramConfig
+
+    cfg = LatentSpectrogramConfig()
+    enc_cfg, dec_cfg = tq.get_2d_autoencoder_configs(cfg)
+    edm = tq.LightningEDM(tq.get_2d_unet_config(cfg, cfg.latent_channels, cfg.latent_channels), {}, num_sampling_steps=NFE_STEPS,
+                          autoencoder=tq.LightningAutoencoder(enc_cfg, dec_cfg, {}))
+    edm.load_state_dict(build_state_dict(edm))
+    edm.eval().to(dev).set_engine_precision(args.precision)
+    lo, hi = sharding.shard_bounds(total, rank, world)
+    cond = torch.from_numpy(cond_grid(total))[lo:hi].contiguous().pin_memory()
+    noise = sharding.global_noise((8, 32, 32), lo, hi, seed=1, device="cpu").pin_memory()
+
+    def step():
+        rep = edm.sample((hi - lo, 3, 128, 128), cond=cond.to(dev, non_blocking=True), noise=noise.to(dev, non_blocking=True))
+        wav = cfg.representation.invert_representation_device(rep).to(torch.float32)
+        full = sharding.gather_waveforms(wav, total)
+        return sharding.to_host(full) if full is not None else None
+
+    ms, wall, out = _event_time(step, 2, 1, torch, barrier)
+    t = torch.tensor([max(ms, wall)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank == 0:
+        assert tuple(out.shape) == (total, 3, cfg.t)
+    val = total / ms * 1e3
+    return {"workload": "HighFEM latent EDM, global batch 8192 on the magnitude / distance / vs30 grid, split over the ranks; "
+                        "gather + D2H of all waveforms inside the time", "global_batch": total, "batch_per_gpu": hi - lo,
+            "scaling": "strong", "value": val, "unit": "waveforms/s", "ms_per_step": ms, "gather_bytes": total * 3 * cfg.t * 4,
+            "achieved_tflops_per_gpu": val / world * FLOP_PER_WAVEFORM / 1e12,
+            "frac_of_bf16_burst_peak": val / world * FLOP_PER_WAVEFORM / 1e12 / pk["bf16_tflops"]}
 
 
 def run_engine(args) -> None:
@@ -432,7 +684,8 @@ def run_engine(args) -> None:
         "config": {"workload": "HighFEM latent EDM: latent UNet Heun sampling + autoencoder decode + log-spectrogram "
                                "inverse, batch 256 per B200 (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "global_batch": total, "heun_steps": NFE_STEPS, "nfe": 2 * NFE_STEPS - 1,
-                   "griffinlim_iters": 128, "weights": "random-init (seeded)", "parallelism": f"batch-sharded x{world}",
+                   "griffinlim_iters": 128, "griffinlim_precision": "fp64 (the reference's locked NumPy 2 runs complex128)",
+                   "weights": "random-init (seeded)", "parallelism": f"batch-sharded x{world}",
                    "cache": "activations of one denoiser call (~1.5 GB) exceed the 126 MB L2; no L2 flush needed",
                    "cuda_graph": bool(edm.use_cuda_graph)},
         "e2e": {"value": e2e_value, "unit": "waveforms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -444,8 +697,8 @@ def run_engine(args) -> None:
         "wall_ms_per_step": wall_ms / args.steps,
     }
     if rank == 0 and world == 1:
-        agg = kernel_breakdown(edm, hi - lo)
-        tot_ms = sum(a["ms"] for a in agg.values())
+        agg, graph_ms, op_sum_ms = kernel_breakdown(edm, hi - lo)
+        tot_ms = graph_ms
         conv = agg.get("igemm_sm100") or agg.get("igemm_simt")
         ach = conv["flops"] / (conv["ms"] / 1e3) / 1e12
         line["roofline"] = {
@@ -454,15 +707,20 @@ def run_engine(args) -> None:
             "peak_source": f"{pk['source']} bf16 burst (MEASURED_PEAKS.json)", "traffic": None,
             "launches_per_call": conv["launches"], "share_of_denoiser_call": conv["ms"] / tot_ms,
             "frac_of_sustained_peak": ach / pk["bf16_tflops_sustained"],
+            "timing": "per-kernel share (op-by-op CUDA events) x the time of the captured graph the step replays",
+            "graph_ms_per_denoiser_call": graph_ms, "op_by_op_ms_per_denoiser_call": op_sum_ms,
         }
-        # DRAM bytes per launch from the committed ncu capture of the same launches (tools/summarize_dram.py)
+        # DRAM bytes per launch from the committed ncu capture of the same launches (tools/summarize_dram.py); quoted only
+        # while the capture belongs to the kernel sources of this checkout (hash), never a stale number
         tfile = ROOT / "profiles" / "igemm_dram_traffic.json"
         if tfile.exists():
             tj = json.loads(tfile.read_text())
-            if tj.get("launches") == conv["launches"]:
+            if tj.get("launches") == conv["launches"] and tj.get("source_sha16") == source_sha16(*IGEMM_SOURCES):
                 line["roofline"]["traffic"] = tj["bytes_per_launch"]
-                line["roofline"]["traffic_unit"] = "DRAM bytes per launch (read + write), ncu"
-                line["roofline"]["algorithmic_bytes_per_launch"] = conv.get("bytes", 0) / conv["launches"] or None
+                line["roofline"]["traffic_unit"] = "DRAM bytes per launch (read + write), ncu --set full, " + tj.get("capture", "")
+            else:
+                line["roofline"]["traffic_note"] = "committed ncu capture belongs to other kernel sources: not quoted"
+            line["roofline"]["algorithmic_bytes_per_launch"] = conv.get("bytes", 0) / conv["launches"] or None
         gn = {k: agg[k] for k in agg if k.startswith("gn_")}
         if gn:
             gb = sum(a["bytes"] for a in gn.values())
@@ -471,8 +729,15 @@ def run_engine(args) -> None:
                                           "unit": "GB/s", "frac": gb / (gms / 1e3) / 1e9 / pk["hbm_gbs"],
                                           "share_of_denoiser_call": gms / tot_ms}
         line["kernel_ms_per_denoiser_call"] = {k: round(a["ms"], 4) for k, a in sorted(agg.items())}
+        # the step outside the denoiser calls: decode and the fp64 Griffin-Lim launch
+        rep = edm.sample((hi - lo, 3, 128, 128), cond=cond_dev, noise=noise_dev)
+        gl_ms, _, _ = _event_time(lambda: rep_inv.invert_representation_device(rep), 3, 1, torch)
+        lat = torch.randn((hi - lo, 8, 32, 32), device=dev)
+        dec_ms, _, _ = _event_time(lambda: edm.autoencoder.decode(lat), 3, 1, torch)
+        line["step_parts_ms"] = {"denoiser_calls_49x": 49 * graph_ms, "decode": dec_ms, "griffinlim_fp64_768_items": gl_ms}
         if not args.no_cpu_baseline:
             pipe = CpuPipeline(args.cpu_batch)
+            pipe.step(100)     # warm-up (thread pools, first-touch)
             t0 = time.perf_counter()
             pipe.step(0)
             dt = time.perf_counter() - t0
@@ -480,7 +745,28 @@ def run_engine(args) -> None:
             line["cpu_baseline"] = {"value": args.cpu_batch / dt, "unit": "waveforms/s", "cores": pipe.cores,
                                     "kind": pipe.kind,
                                     "sample": f"{args.cpu_batch} waveforms, full 25-step Heun + decode + 128-iter "
-                                              f"Griffin-Lim, {dt:.1f} s on the host"}
+                                              f"Griffin-Lim, {dt:.1f} s on the host (after one warm-up pass)"}
+    # ---- the other BASELINE.json configs, in the same line
+    which = set(args.configs.split(",")) if args.configs not in ("all", "none") else (
+        {"cfg0", "cfg2", "cfg3", "cfg4"} if args.configs == "all" else set())
+    configs = {}
+    del edm
+    torch.cuda.empty_cache()
+    if world == 1 and rank == 0:
+        if "cfg0" in which:
+            configs["cfg0"] = measure_cfg0(dev, pk, cpu=not args.no_cpu_baseline)
+        if "cfg3" in which:
+            configs["cfg3"] = measure_cfg3(dev, pk, args.cfg3_batch)
+    if "cfg4" in which:
+        c4 = measure_cfg4(dev, pk, world, rank, barrier)
+        if rank == 0:
+            configs["cfg4"] = c4
+    if "cfg2" in which and world > 1:
+        c2 = measure_cfg2(args, dev, pk, world, rank, barrier)
+        if rank == 0:
+            configs["cfg2"] = c2
+    if configs:
+        line["configs"] = configs
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -497,6 +783,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=4, help="waveforms per step of the CPU arm / CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="all",
+                    help="secondary BASELINE.json configs measured after the headline: all | none | comma list of cfg0,cfg2,cfg3,cfg4")
+    ap.add_argument("--cfg3-batch", type=int, default=1024, help="batch of the pixel-space config (configs[3] names 1024)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -8,6 +8,9 @@ import csv
 import io
 import json
 import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0,
         "msecond": 1e3, "ms": 1e3}
@@ -24,7 +27,11 @@ def main(src, dst):
     rd = sum(p.get("dram__bytes_read.sum", 0.0) for p in per.values())
     wr = sum(p.get("dram__bytes_write.sum", 0.0) for p in per.values())
     us = sum(p.get("gpu__time_duration.sum", 0.0) for p in per.values())
+    from bench import IGEMM_SOURCES, source_sha16
+
+    # the hash ties the capture to the kernel sources it was taken from: bench.py quotes `traffic` only while it matches
     out = {"kernel": "igemm_sm100_kernel (all launches of one latent-UNet denoiser call, batch 256, bf16)", "launches": n,
+           "source_sha16": source_sha16(*IGEMM_SOURCES), "capture": Path(src).name,
            "dram_read_bytes": rd, "dram_write_bytes": wr, "bytes_per_launch": (rd + wr) / max(n, 1),
            "ncu_time_us": us, "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum ({src}); cold cache per launch"}
     json.dump(out, open(dst, "w"), indent=1)

@@ -346,14 +346,22 @@ __device__ __forceinline__ Cx<R> twid(const Cx<R>* tw, int m) {
 __device__ __forceinline__ float shfl16(float v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
 __device__ __forceinline__ double shfl16(double v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
 
+// Twiddle tables of the 128-point FFT, laid out so that every load is bank-conflict free (the generic table
+// exp(-2 pi i m / 128) read at m = lane k or 4 l2 m puts the eight lanes of a quarter warp on 1-2 banks: measured 104 extra
+// shared-memory wavefronts per frame, 20 % of the kernel's shared-memory traffic, which is what bounds it):
+//   tw1[k - 1][lane] = W^(lane k), k = 1..3     tw2[m - 1][l2] = W^(4 l2 m), l2 < 8, m = 1..3     (W = exp(-2 pi i / 128))
+constexpr int TW_ELEMS = 3 * 32 + 3 * 8;
+
 // in : z[j] = x[lane + 32 j]            (natural order)
 // out: z[p] = X[(lane & 15) + 16 p + 64 (lane >> 4)]
-// tw[m] = exp(-2 pi i m / 128), m < 96; ex: this warp's exchange buffer
+// ex: this warp's exchange buffer
 template <typename R, bool INV>
 __device__ __forceinline__ void fft128(Cx<R> (&z)[4], Cx<R>* ex, const Cx<R>* tw, int lane) {
+    const Cx<R>* tw1 = tw;
+    const Cx<R>* tw2 = tw + 96;
     radix4<R, INV>(z);
 #pragma unroll
-    for (int k = 1; k < 4; ++k) z[k] = cmul(z[k], twid<R, INV>(tw, lane * k));
+    for (int k = 1; k < 4; ++k) z[k] = cmul(z[k], twid<R, INV>(tw1, (k - 1) * 32 + lane));
     const int a = lane >> 3, l2 = lane & 7;
     __syncwarp();
 #pragma unroll
@@ -363,7 +371,7 @@ __device__ __forceinline__ void fft128(Cx<R> (&z)[4], Cx<R>* ex, const Cx<R>* tw
     for (int j = 0; j < 4; ++j) z[j] = ex[a * 40 + l2 + 8 * j];
     radix4<R, INV>(z);
 #pragma unroll
-    for (int m = 1; m < 4; ++m) z[m] = cmul(z[m], twid<R, INV>(tw, 4 * l2 * m));
+    for (int m = 1; m < 4; ++m) z[m] = cmul(z[m], twid<R, INV>(tw2, (m - 1) * 8 + l2));
     const int g = lane & 15, l3 = lane >> 4;
     __syncwarp();
 #pragma unroll
@@ -373,8 +381,18 @@ __device__ __forceinline__ void fft128(Cx<R> (&z)[4], Cx<R>* ex, const Cx<R>* tw
     for (int j = 0; j < 4; ++j) z[j] = ex[9 * g + l3 + 2 * j];
     radix4<R, INV>(z);
     if (l3) {
-#pragma unroll
-        for (int q = 1; q < 4; ++q) z[q] = cmul(z[q], twid<R, INV>(tw, 16 * q));
+        // W^16 = (1 - i) / sqrt 2, W^32 = -i, W^48 = -(1 + i) / sqrt 2 (forward); conjugates for the inverse
+        const R h = (R)0.70710678118654752440;
+        const Cx<R> z1 = z[1], z2 = z[2], z3 = z[3];
+        if (!INV) {
+            z[1] = Cx<R>{h * (z1.x + z1.y), h * (z1.y - z1.x)};
+            z[2] = Cx<R>{z2.y, -z2.x};
+            z[3] = Cx<R>{h * (z3.y - z3.x), -h * (z3.x + z3.y)};
+        } else {
+            z[1] = Cx<R>{h * (z1.x - z1.y), h * (z1.x + z1.y)};
+            z[2] = Cx<R>{-z2.y, z2.x};
+            z[3] = Cx<R>{-h * (z3.x + z3.y), h * (z3.x - z3.y)};
+        }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -403,7 +421,7 @@ struct Smem {
     R* yb;
     R* inv_wss;   // 1 / window sum of squares per padded sample (0 outside the kept range)
     R* win;       // periodic Hann, 256
-    Cx<R>* tw128; // 96
+    Cx<R>* tw128; // TW_ELEMS: the conflict-free stage tables of fft128
     Cx<R>* tw256; // 129 (+pad)
     Cx<R>* ex;    // FW x EX
 };
@@ -420,7 +438,7 @@ __global__ void __launch_bounds__(FTHREADS, sizeof(R) == 4 ? 2 : 1) griffinlim_f
     sm.inv_wss = sm.yb + len4;
     sm.win = sm.inv_wss + len4;
     sm.tw128 = reinterpret_cast<Cx<R>*>(sm.win + NFFT);
-    sm.tw256 = sm.tw128 + 96;
+    sm.tw256 = sm.tw128 + TW_ELEMS;
     sm.ex = sm.tw256 + 132;
 
     const int item = blockIdx.x;
@@ -431,9 +449,11 @@ __global__ void __launch_bounds__(FTHREADS, sizeof(R) == 4 ? 2 : 1) griffinlim_f
     Cx<R>* Tp = reinterpret_cast<Cx<R>*>(S + per_item);
 
     for (int i = tid; i < NFFT; i += FTHREADS) sm.win[i] = (R)(0.5 - 0.5 * cospi(2.0 * i / NFFT));
-    for (int i = tid; i < 96; i += FTHREADS) {
+    for (int i = tid; i < TW_ELEMS; i += FTHREADS) {
+        // exponent of W = exp(-2 pi i / 128): lane * k for the stage-1 table, 4 * l2 * m for the stage-2 table
+        const int e = i < 96 ? (i & 31) * (i / 32 + 1) : 4 * ((i - 96) & 7) * ((i - 96) / 8 + 1);
         double s, c;
-        sincospi(-2.0 * i / 128.0, &s, &c);
+        sincospi(-2.0 * e / 128.0, &s, &c);
         sm.tw128[i] = Cx<R>{(R)c, (R)s};
     }
     for (int i = tid; i <= 128; i += FTHREADS) {
@@ -622,7 +642,7 @@ template <typename R>
 size_t smem_bytes(int frames) {
     const int len = NFFT + HOP * (frames - 1);
     const int len4 = (len + 3) & ~3;
-    return sizeof(R) * (3 * (size_t)len4 + NFFT) + sizeof(Cx<R>) * (96 + 132 + (size_t)FW * EX);
+    return sizeof(R) * (3 * (size_t)len4 + NFFT) + sizeof(Cx<R>) * (TW_ELEMS + 132 + (size_t)FW * EX);
 }
 
 }  // namespace fused
