@@ -158,3 +158,36 @@ def kernel_model_irfft256(X: np.ndarray) -> np.ndarray:
     x = np.empty(256)
     x[0::2], x[1::2] = z.real, z.imag
     return x
+
+
+# ---- lane / register model of the fused kernel's 128-point FFT network (csrc/tq_griffinlim.cu, namespace fused) ----
+def _radix4(z: np.ndarray, inv: bool) -> np.ndarray:
+    t0, t1, t2, t3 = z[:, 0] + z[:, 2], z[:, 0] - z[:, 2], z[:, 1] + z[:, 3], z[:, 1] - z[:, 3]
+    it3 = (1j if inv else -1j) * t3
+    out = np.empty_like(z)
+    out[:, 0], out[:, 2], out[:, 1], out[:, 3] = t0 + t2, t0 - t2, t1 + it3, t1 - it3
+    return out
+
+
+def kernel_model_fft128_dif(x: np.ndarray) -> np.ndarray:
+    """fft128<R, false>: x natural -> z[lane, p] = X[(lane & 15) + 16 p + 64 (lane >> 4)] (32 lanes x 4 registers)."""
+    L = np.arange(32)
+    W = lambda e: np.exp(-2j * np.pi * e / 128)  # noqa: E731
+    a, l2, g, l3 = L >> 3, L & 7, L & 15, L >> 4
+    z = _radix4(np.stack([x[L + 32 * j] for j in range(4)], 1).astype(complex), False)
+    for k in range(1, 4):
+        z[:, k] *= W(L * k)
+    ex = np.zeros(152, complex)
+    for k in range(4):
+        ex[k * 40 + L] = z[:, k]
+    z = _radix4(np.stack([ex[a * 40 + l2 + 8 * j] for j in range(4)], 1), False)
+    for m in range(1, 4):
+        z[:, m] *= W(4 * l2 * m)
+    ex = np.zeros(152, complex)
+    for m in range(4):
+        ex[9 * (a + 4 * m) + l2] = z[:, m]
+    z = _radix4(np.stack([ex[9 * g + l3 + 2 * j] for j in range(4)], 1), False)
+    for q in range(1, 4):
+        z[l3 == 1, q] *= W(16 * q)
+    other = z[L ^ 16]
+    return np.where((l3 == 1)[:, None], other - z, z + other)

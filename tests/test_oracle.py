@@ -262,3 +262,14 @@ def test_denoiser_restatement_at_stated_sizes(name, kind):
     with torch.no_grad():
         D = torch_ref.denoise(sd, cfg, g["x"], g["sigma"], g["cond"])
     assert rel_l2(D, g["D"]) < TOL
+
+
+def test_kernel_fft_network_model_is_exact():
+    """The lane / register model of the fused Griffin-Lim kernel's 128-point FFT network (radix 4 x 4 x 4 x 2, two
+    shared-memory transposes, one shuffle stage; output order (lane & 15) + 16 p + 64 (lane >> 4)) against np.fft."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(128) + 1j * rng.standard_normal(128)
+    X = np.fft.fft(x)
+    L = np.arange(32)
+    kk = np.stack([(L & 15) + 16 * p + 64 * (L >> 4) for p in range(4)], 1)
+    assert np.abs(griffinlim_ref.kernel_model_fft128_dif(x) - X[kk]).max() < 1e-12
