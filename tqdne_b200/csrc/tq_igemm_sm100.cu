@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), CG * kEpiWarps);
+            // N = 64 tiles with bf16 output: the two column halves of the epilogue warps take ALTERNATE tiles (one
+            // accumulator buffer each), so a buffer is handed back by the four warps of one half only
+            mbar_init(tempty_bar(a), (BN == 64 && !OUT_F32) ? CG * (kEpiWarps / 2) : CG * kEpiWarps);
         }
         for (int w = 0; w < kEpiWarps; ++w) mbar_init(res_bar(w), 1);
         fence_mbar_init();
@@ -392,14 +394,24 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
         const uint32_t rbar = res_bar(ew);
         uint32_t rphase = 0;
         const uint32_t tempty0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
-        int acc = 0;
+        // N = 64, bf16 output: a tile has ONE 64-channel unit, which would leave the four warps of column half 1 idle while
+        // the epilogue -- not the 5-9 slice mainloop -- bounds the kernel (64->64 k5 @4064: 4 560 cycles per tile against
+        // 640 tensor-pipe cycles).  Instead half h takes every second tile of the CTA (always accumulator buffer h): two
+        // tiles drain concurrently, each through its own staging buffers and its own named barrier
+        // (64->64 k5 @4064 x 64: 44.4 -> 29.7 us; 64->64 3x3 @128^2 x 64: 166 -> 139 us).
+        constexpr bool ALT = BN == 64 && !OUT_F32;
+        int acc = ALT ? half : 0;
         uint32_t acc_phase = 0;
+        int iter = 0;
         const bool prof = p.prof != nullptr && ew == 0;
         long long w_tfull = 0, w_res = 0, w_store = 0;
         uint32_t et[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;  // prof: pre / waits / ld+math+sts / hand-back / store / statistics
 #define TQ_EPI_T(i) do { if (prof) { const uint32_t n_ = (uint32_t)clock(); et[i] += n_ - tlast; tlast = n_; } } while (0)
         const long long e_begin = clk();
-        for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+        for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++iter) {
+            if constexpr (ALT) {
+                if ((iter & 1) != half) continue;
+            }
             if (prof) tlast = (uint32_t)clock();
             const TileCoord t = decode_tile<CG>(p, tile, rank);
             const int n = t.n0 + dnr, y = t.y0 + dyr, x = t.x0 + dxr;
@@ -416,8 +428,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                     if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
                     else mbar_arrive(tempty_bar(acc));
                 }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                if constexpr (ALT) acc_phase ^= 1u;
+                else {
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                }
                 continue;
             }
             if constexpr (!OUT_F32) {
@@ -428,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
 #pragma unroll
                 for (int u = 0; u < C::UNITS; ++u) {
                     unit_col[u] = (BN >= 128 ? half + 2 * u : 0) * 64;
-                    unit_on[u] = (BN >= 128 || half == 0) && (t.n_tile * BN + unit_col[u]) < p.cout;
+                    unit_on[u] = (t.n_tile * BN + unit_col[u]) < p.cout;   // N = 64: both halves work (alternate tiles)
                     n_on += unit_on[u] ? 1 : 0;
                 }
                 // statistics over tiles whose samples span several epilogue warps are read ACROSS the staging buffers
@@ -701,8 +716,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_sm100_kernel(const __grid_c
                     else mbar_arrive(tempty_bar(acc));
                 }
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
+            if constexpr (ALT) acc_phase ^= 1u;   // this half owns accumulator buffer `half`: every tile it takes flips the phase
+            else {
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
         }
         if constexpr (!OUT_F32) {
             if (lane == 0) bulk_wait_read<0>();  // smem must stay alive until the last TMA stores have read it
@@ -833,6 +851,8 @@ void tile_shape_for(int H, int W, int* bw, int* bh, int* bn) {
 int conv_stats_parts_sm100(const tq_conv_desc& d) {
     int bw, bh, bn;
     tile_shape_for(d.H, d.W, &bw, &bh, &bn);
+    // one slot per 128-row tile: a slot per epilogue WARP (no cross-warp pass, no named barriers, 4x the partials for the
+    // consuming GroupNorm to add) measured slower end to end -- latent UNet call 4.405 -> 4.481 ms, 1D EDM step 124 -> 141 ms
     return d.num_classes * ((d.W + bw - 1) / bw) * ((d.H + bh - 1) / bh);
 }
 
