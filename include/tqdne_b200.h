@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 13
+#define TQ_ABI_VERSION 14
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -262,17 +262,20 @@ int tq_adam_ema_step(float* param, const float* grad, float* m, float* v, float*
  *                         optionally xin = dtype(float(x1) * c_in_next)
  *   tq_edm_heun         : D' = F*c_out' + c_skip'*float(x1); d' = (x1 - D')/sigma';
  *                         x = x + dt*(0.5*d + 0.5*d');  optionally xin = dtype(float(x)*c_in_next)
- * F is the fp32 channels-last network output [N,P,Cf] (row stride Cf >= C).                        */
+ * F is the fp32 channels-last network output [N,P,Cf] (row stride Cf >= C).
+ * t_next / t_value (t_next may be NULL): also store the NEXT denoiser call's noise-conditioning scalar
+ * c_noise = ln(sigma)/4 (edm.py:36-37) into the plan's time input -- a 4-byte cudaMemcpyAsync between two graph
+ * replays cost 0.22 ms per call (copy-engine hand-over), a store from the kernel that runs there anyway is free.   */
 int tq_edm_precondition(const double* x, void* xin, int32_t dtype, int64_t NP, int32_t C, int32_t Cpad,
-                        float c_in, void* stream);
+                        float c_in, float* t_next, float t_value, void* stream);
 int tq_edm_euler(const double* x, const float* F, int32_t Cf, double* d, double* x1,
                  void* xin, int32_t dtype, int64_t NP, int32_t C, int32_t Cpad,
                  float c_out, float c_skip, float sigma, float dt, float c_in_next, int32_t write_xin,
-                 void* stream);
+                 float* t_next, float t_value, void* stream);
 int tq_edm_heun(double* x, const double* x1, const double* d, const float* F, int32_t Cf,
                 void* xin, int32_t dtype, int64_t NP, int32_t C, int32_t Cpad,
                 float c_out, float c_skip, float sigma_next, float dt, float c_in_next, int32_t write_xin,
-                void* stream);
+                float* t_next, float t_value, void* stream);
 /* x += noise * scale  (stochastic sampler churn, edm.py:205-207), fp64 */
 int tq_edm_add_noise(double* x, const double* noise, double scale, int64_t n, void* stream);
 

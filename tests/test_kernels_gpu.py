@@ -429,13 +429,16 @@ def test_edm_update_kernels(dtype):
     (ci, co, cs), (ci2, co2, cs2) = c(sig), c(sig_n)
     dt = float(sig_n - sig)
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), tq_dtype(dtype), NP, C, Cpad, ci, st))
+    tnext = torch.zeros(1, device="cuda")     # the plan's time input: the sampler kernels also store the next c_noise
+    _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), tq_dtype(dtype), NP, C, Cpad, ci, tnext.data_ptr(), 0.25, st))
     torch.cuda.synchronize()
+    assert float(tnext) == 0.25
     ref_in = (x.float() * ci).to(dtype)
     assert torch.equal(xin[:, :C], ref_in) and float(xin[:, C:].abs().max()) == 0.0
     _lib.check(lib.tq_edm_euler(x.data_ptr(), Fo.data_ptr(), Cf, d.data_ptr(), x1.data_ptr(), xin.data_ptr(), tq_dtype(dtype),
-                                NP, C, Cpad, co, cs, float(sig), dt, ci2, 1, st))
+                                NP, C, Cpad, co, cs, float(sig), dt, ci2, 1, tnext.data_ptr(), -1.5, st))
     torch.cuda.synchronize()
+    assert float(tnext) == -1.5
     D = (Fo * co + cs * x.float()).double()
     d_ref = (x - D) / float(sig)
     x1_ref = x + d_ref * dt
@@ -443,8 +446,9 @@ def test_edm_update_kernels(dtype):
     assert rel_l2(xin[:, :C].float(), (x1_ref.float() * ci2)) < (4e-3 if dtype == torch.bfloat16 else 1e-6)
     xs = x.clone()
     _lib.check(lib.tq_edm_heun(xs.data_ptr(), x1.data_ptr(), d.data_ptr(), F2.data_ptr(), Cf, xin.data_ptr(), tq_dtype(dtype),
-                               NP, C, Cpad, co2, cs2, float(sig_n), dt, ci2, 1, st))
+                               NP, C, Cpad, co2, cs2, float(sig_n), dt, ci2, 1, None, 0.0, st))
     torch.cuda.synchronize()
+    assert float(tnext) == -1.5               # NULL t_next: left alone
     D2 = (F2 * co2 + cs2 * x1.float()).double()
     x_ref = x + dt * (0.5 * d_ref + 0.5 * (x1 - D2) / float(sig_n))
     assert rel_l2(xs, x_ref) < 1e-12

@@ -55,12 +55,12 @@ with torch.cuda.stream(s):
 
 def euler():
     _lib.check(lib.tq_edm_euler(x.data_ptr(), F.data_ptr(), Cf, d.data_ptr(), x1.data_ptr(), xin.data_ptr(), dt_, NP, 8, Cpad,
-                                0.5, 0.5, 1.0, -0.1, 1.0, 1, current_stream_ptr()), "euler")
+                                0.5, 0.5, 1.0, -0.1, 1.0, 1, plan.t.data_ptr(), 0.3, current_stream_ptr()), "euler")
 
 
 def heun():
     _lib.check(lib.tq_edm_heun(x.data_ptr(), x1.data_ptr(), d.data_ptr(), F.data_ptr(), Cf, xin.data_ptr(), dt_, NP, 8, Cpad,
-                               0.5, 0.5, 1.0, -0.1, 1.0, 1, current_stream_ptr()), "heun")
+                               0.5, 0.5, 1.0, -0.1, 1.0, 1, plan.t.data_ptr(), 0.3, current_stream_ptr()), "heun")
 
 
 timed("plan.run (graph)", lambda: plan.run())
@@ -68,6 +68,26 @@ timed("t.copy_ + plan.run", lambda: (plan.t.copy_(tdev[3:4]), plan.run()))
 timed("euler kernel alone", euler)
 timed("heun kernel alone", heun)
 timed("t.copy_ + plan.run + euler", lambda: (plan.t.copy_(tdev[3:4]), plan.run(), euler()))
+timed("plan.run + euler (t written by the kernel)", lambda: (plan.run(), euler()))
+# the plan's kernels + the update kernel captured into ONE graph (tq_plan_run records into a caller-owned capture)
+g1 = torch.cuda.CUDAGraph()
+with torch.cuda.stream(s):
+    s.synchronize()
+    with torch.cuda.graph(g1, stream=s):
+        plan.run()
+        euler()
+timed("ONE graph = plan + euler", lambda: g1.replay())
+g2 = torch.cuda.CUDAGraph()
+with torch.cuda.stream(s):
+    s.synchronize()
+    with torch.cuda.graph(g2, stream=s):
+        plan.run()
+        euler()
+        plan.run()
+        heun()
+ITER = 10
+timed("ONE graph = 2 x (plan + update), per pair", lambda: g2.replay())
+ITER = 20
 cond = torch.from_numpy(cond_grid(B)).cuda()
 noise = torch.randn(B, 8, 32, 32, device="cuda", dtype=torch.float64)
 ae, edm.autoencoder = edm.autoencoder, None

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 13  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 14  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -136,9 +136,9 @@ SIGNATURES = {
     "tq_repack_conv_weights": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "tq_dropout_apply": (C.c_int, [_VP, _VP, _I64, C.c_uint64, _F, _VP]),
     "tq_adam_ema_step": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _I64, _F, _F, _VP]),
-    "tq_edm_precondition": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _I32, _F, _VP]),
-    "tq_edm_euler": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _F, _F, _F, _F, _F, _I32, _VP]),
-    "tq_edm_heun": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _I32, _I64, _I32, _I32, _F, _F, _F, _F, _F, _I32, _VP]),
+    "tq_edm_precondition": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _I32, _F, _VP, _F, _VP]),
+    "tq_edm_euler": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _F, _F, _F, _F, _F, _I32, _VP, _F, _VP]),
+    "tq_edm_heun": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _I32, _I64, _I32, _I32, _F, _F, _F, _F, _F, _I32, _VP, _F, _VP]),
     "tq_edm_add_noise": (C.c_int, [_VP, _VP, _D, _I64, _VP]),
     "tq_nchw_to_nhwc": (C.c_int, [_VP, _I32, _VP, _I32, _I32, _I32, _I64, _I32, _VP]),
     "tq_nhwc_to_nchw": (C.c_int, [_VP, _I32, _I32, _VP, _I32, _I32, _I32, _I64, _VP]),

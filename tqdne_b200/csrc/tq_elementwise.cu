@@ -92,7 +92,9 @@ __device__ __forceinline__ void st_as<__nv_bfloat16>(__nv_bfloat16* p, float v) 
 
 // Reference: LightningEDM.forward (tqdne/edm.py:105-113): sample_in = sample.to(fp32) * c_in(sigma)
 template <typename T>
-__global__ void precondition_kernel(const double* x, T* xin, long long NP, int C, int Cpad, float c_in) {
+__global__ void precondition_kernel(const double* x, T* xin, long long NP, int C, int Cpad, float c_in, float* t_next,
+                                    float t_value) {
+    if (t_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *t_next = t_value;   // the NEXT denoiser call's c_noise
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NP * Cpad) return;
     const long long r = i / Cpad;
@@ -105,7 +107,9 @@ __global__ void precondition_kernel(const double* x, T* xin, long long NP, int C
 // (edm.py:111-113): D = F*c_out + c_skip*x32;  d = (x - D)/sigma;  x1 = x + d*dt  (fp64 like the reference)
 template <typename T>
 __global__ void euler_kernel(const double* x, const float* F, int Cf, double* d, double* x1, T* xin, long long NP, int C,
-                             int Cpad, float c_out, float c_skip, float sigma, float dt, float c_in_next, int write_xin) {
+                             int Cpad, float c_out, float c_skip, float sigma, float dt, float c_in_next, int write_xin,
+                             float* t_next, float t_value) {
+    if (t_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *t_next = t_value;   // the NEXT denoiser call's c_noise
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NP * Cpad) return;
     const long long r = i / Cpad;
@@ -129,7 +133,8 @@ __global__ void euler_kernel(const double* x, const float* F, int Cf, double* d,
 template <typename T>
 __global__ void heun_kernel(double* x, const double* x1, const double* d, const float* F, int Cf, T* xin, long long NP,
                             int C, int Cpad, float c_out, float c_skip, float sigma_next, float dt, float c_in_next,
-                            int write_xin) {
+                            int write_xin, float* t_next, float t_value) {
+    if (t_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *t_next = t_value;   // the NEXT denoiser call's c_noise
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NP * Cpad) return;
     const long long r = i / Cpad;
@@ -172,7 +177,8 @@ __device__ __forceinline__ void store_group8<__nv_bfloat16>(__nv_bfloat16* dst, 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) edm_group_kernel(double* x, double* x1, double* d, const float* F, int Cf, T* xin,
                                                         long long NP, int C, int Cpad, float c_out, float c_skip, float sigma,
-                                                        float dt, float c_in_next, int write_xin) {
+                                                        float dt, float c_in_next, int write_xin, float* t_next, float t_value) {
+    if (t_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *t_next = t_value;   // the NEXT denoiser call's c_noise
     const int gpr = Cpad >> 3;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NP * gpr) return;
@@ -211,17 +217,17 @@ __global__ void __launch_bounds__(256) edm_group_kernel(double* x, double* x1, d
 template <int MODE>
 int launch_edm_group(double* x, double* x1, double* d, const float* F, int Cf, void* xin, int dtype, long long NP, int C,
                      int Cpad, float c_out, float c_skip, float sigma, float dt, float c_in_next, int write_xin,
-                     cudaStream_t st) {
+                     float* t_next, float t_value, cudaStream_t st) {
     const long long threads = write_xin ? NP * (Cpad >> 3) : NP * ((C + 7) >> 3);
     const unsigned g = (unsigned)((threads + 255) / 256);
     // without the padded output only the groups that hold real channels are needed
     const int cp = write_xin ? Cpad : ((C + 7) >> 3) * 8;
     if (dtype == TQ_F32)
         edm_group_kernel<float, MODE><<<g, 256, 0, st>>>(x, x1, d, F, Cf, static_cast<float*>(xin), NP, C, cp, c_out, c_skip,
-                                                         sigma, dt, c_in_next, write_xin);
+                                                         sigma, dt, c_in_next, write_xin, t_next, t_value);
     else
         edm_group_kernel<__nv_bfloat16, MODE><<<g, 256, 0, st>>>(x, x1, d, F, Cf, static_cast<__nv_bfloat16*>(xin), NP, C, cp,
-                                                                 c_out, c_skip, sigma, dt, c_in_next, write_xin);
+                                                                 c_out, c_skip, sigma, dt, c_in_next, write_xin, t_next, t_value);
     return 0;
 }
 inline bool group_ok(const void* xin, int Cpad, int dtype) {
@@ -403,20 +409,21 @@ int build_spatial_mean(std::vector<Op>& ops, const float* x, int N, int P, int C
 using namespace tq;
 
 extern "C" int tq_edm_precondition(const double* x, void* xin, int32_t dtype, int64_t NP, int32_t C, int32_t Cpad,
-                                   float c_in, void* stream) {
+                                   float c_in, float* t_next, float t_value, void* stream) {
     TQ_CHECK(x && xin && NP > 0 && C > 0 && Cpad >= C, "edm_precondition: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (group_ok(xin, Cpad, dtype)) {
         launch_edm_group<0>(const_cast<double*>(x), nullptr, nullptr, nullptr, 0, xin, dtype, NP, C, Cpad, 0.f, 0.f, 1.f, 0.f,
-                            c_in, 1, st);
+                            c_in, 1, t_next, t_value, st);
         TQ_CUDA(cudaGetLastError());
         count_launch();
         return 0;
     }
     const unsigned g = blocks_for(NP * Cpad, 256);
-    if (dtype == TQ_F32) precondition_kernel<float><<<g, 256, 0, st>>>(x, static_cast<float*>(xin), NP, C, Cpad, c_in);
+    if (dtype == TQ_F32) precondition_kernel<float><<<g, 256, 0, st>>>(x, static_cast<float*>(xin), NP, C, Cpad, c_in, t_next, t_value);
     else if (dtype == TQ_BF16)
-        precondition_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(xin), NP, C, Cpad, c_in);
+        precondition_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(xin), NP, C, Cpad, c_in, t_next,
+                                                               t_value);
     else TQ_CHECK(false, "edm_precondition: bad dtype");
     TQ_CUDA(cudaGetLastError());
     count_launch();
@@ -425,13 +432,13 @@ extern "C" int tq_edm_precondition(const double* x, void* xin, int32_t dtype, in
 
 extern "C" int tq_edm_euler(const double* x, const float* F, int32_t Cf, double* d, double* x1, void* xin, int32_t dtype,
                             int64_t NP, int32_t C, int32_t Cpad, float c_out, float c_skip, float sigma, float dt,
-                            float c_in_next, int32_t write_xin, void* stream) {
+                            float c_in_next, int32_t write_xin, float* t_next, float t_value, void* stream) {
     TQ_CHECK(x && F && x1 && NP > 0 && C > 0 && Cpad >= C && Cf >= C, "edm_euler: bad arguments");
     TQ_CHECK(!write_xin || xin, "edm_euler: xin missing");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (group_ok(write_xin ? xin : nullptr, Cpad, dtype)) {
         launch_edm_group<1>(const_cast<double*>(x), x1, d, F, Cf, xin, dtype, NP, C, Cpad, c_out, c_skip, sigma, dt, c_in_next,
-                            write_xin, st);
+                            write_xin, t_next, t_value, st);
         TQ_CUDA(cudaGetLastError());
         count_launch();
         return 0;
@@ -439,10 +446,10 @@ extern "C" int tq_edm_euler(const double* x, const float* F, int32_t Cf, double*
     const unsigned g = blocks_for(NP * Cpad, 256);
     if (dtype == TQ_F32)
         euler_kernel<float><<<g, 256, 0, st>>>(x, F, Cf, d, x1, static_cast<float*>(xin), NP, C, Cpad, c_out, c_skip, sigma,
-                                               dt, c_in_next, write_xin);
+                                               dt, c_in_next, write_xin, t_next, t_value);
     else if (dtype == TQ_BF16)
         euler_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, F, Cf, d, x1, static_cast<__nv_bfloat16*>(xin), NP, C, Cpad, c_out,
-                                                       c_skip, sigma, dt, c_in_next, write_xin);
+                                                       c_skip, sigma, dt, c_in_next, write_xin, t_next, t_value);
     else TQ_CHECK(false, "edm_euler: bad dtype");
     TQ_CUDA(cudaGetLastError());
     count_launch();
@@ -451,13 +458,13 @@ extern "C" int tq_edm_euler(const double* x, const float* F, int32_t Cf, double*
 
 extern "C" int tq_edm_heun(double* x, const double* x1, const double* d, const float* F, int32_t Cf, void* xin,
                            int32_t dtype, int64_t NP, int32_t C, int32_t Cpad, float c_out, float c_skip, float sigma_next,
-                           float dt, float c_in_next, int32_t write_xin, void* stream) {
+                           float dt, float c_in_next, int32_t write_xin, float* t_next, float t_value, void* stream) {
     TQ_CHECK(x && x1 && d && F && NP > 0 && C > 0 && Cpad >= C && Cf >= C, "edm_heun: bad arguments");
     TQ_CHECK(!write_xin || xin, "edm_heun: xin missing");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (group_ok(write_xin ? xin : nullptr, Cpad, dtype)) {
         launch_edm_group<2>(x, const_cast<double*>(x1), const_cast<double*>(d), F, Cf, xin, dtype, NP, C, Cpad, c_out, c_skip,
-                            sigma_next, dt, c_in_next, write_xin, st);
+                            sigma_next, dt, c_in_next, write_xin, t_next, t_value, st);
         TQ_CUDA(cudaGetLastError());
         count_launch();
         return 0;
@@ -465,10 +472,10 @@ extern "C" int tq_edm_heun(double* x, const double* x1, const double* d, const f
     const unsigned g = blocks_for(NP * Cpad, 256);
     if (dtype == TQ_F32)
         heun_kernel<float><<<g, 256, 0, st>>>(x, x1, d, F, Cf, static_cast<float*>(xin), NP, C, Cpad, c_out, c_skip,
-                                              sigma_next, dt, c_in_next, write_xin);
+                                              sigma_next, dt, c_in_next, write_xin, t_next, t_value);
     else if (dtype == TQ_BF16)
         heun_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, x1, d, F, Cf, static_cast<__nv_bfloat16*>(xin), NP, C, Cpad, c_out,
-                                                      c_skip, sigma_next, dt, c_in_next, write_xin);
+                                                      c_skip, sigma_next, dt, c_in_next, write_xin, t_next, t_value);
     else TQ_CHECK(false, "edm_heun: bad dtype");
     TQ_CUDA(cudaGetLastError());
     count_launch();

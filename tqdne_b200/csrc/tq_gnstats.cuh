@@ -73,4 +73,58 @@ __device__ __forceinline__ void gn_group_stats(const GnStatSrc& s, int n, int cp
     }
 }
 
+// The same reduction by ONE WARP for one (sample, group): lane l takes items l, l + 32, ... in order, then a fixed
+// xor-shuffle tree.  Used by the stand-alone finalize kernel (grid = 32 groups x N samples) for tensors cut into many parts.
+__device__ __forceinline__ void gn_group_stats_warp(const GnStatSrc& s, int n, int g, int cpg, float inv_count, float eps,
+                                                    float* mean_rstd) {
+    const int lane = threadIdx.x & 31;
+    float sm = 0.f, sq = 0.f;
+    const int ca = g * cpg, cb = ca + cpg;
+#pragma unroll 1
+    for (int src = 0; src < 2; ++src) {
+        const int lo = src == 0 ? ca : (ca > s.C0 ? ca : s.C0);
+        const int hi = src == 0 ? (cb < s.C0 ? cb : s.C0) : cb;
+        if (hi <= lo) continue;
+        const int C = src == 0 ? s.C0 : s.C1;
+        const int parts = src == 0 ? s.parts0 : s.parts1;
+        const int cl = lo - (src == 0 ? 0 : s.C0);
+        const int w = hi - lo;
+        const float* base = (src == 0 ? s.st0 : s.st1) + (long long)n * parts * C * 2;
+        const int items = w * parts;
+        int it = lane;
+        for (; it + 96 < items; it += 128) {
+            float2 q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i2 = it + 32 * j;
+                const int k = i2 / w, c = cl + (i2 - k * w);
+                q[j] = __ldcg(reinterpret_cast<const float2*>(base + ((long long)k * C + c) * 2));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sm += q[j].x;
+                sq += q[j].y;
+            }
+        }
+        for (; it < items; it += 32) {
+            const int k = it / w, c = cl + (it - k * w);
+            const float2 q = __ldcg(reinterpret_cast<const float2*>(base + ((long long)k * C + c) * 2));
+            sm += q.x;
+            sq += q.y;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+        const float mean = sm * inv_count;
+        float var = sq * inv_count - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        mean_rstd[0] = mean;
+        mean_rstd[1] = 1.f / sqrtf(var + eps);
+    }
+}
+
 }  // namespace tq

@@ -273,16 +273,14 @@ __device__ __forceinline__ void affine8(const float* gstat, int cpg, int c0, con
 
 // Tensors cut into many tiles per sample (pixel-space 128 x 128 images: 128 parts): the group reduction over
 // [parts][channels of the group] is done ONCE per sample here instead of once per position chunk in the apply kernel.
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnParams p, float* gfinal) {
-    __shared__ float gstat[64];
-    const int n = blockIdx.x;
+// One warp per (group, sample): 32 x N warps in flight, each adding its items in a fixed order.
+__global__ void __launch_bounds__(32) gn_finalize_kernel(const GnParams p, float* gfinal) {
+    const int g = blockIdx.x, n = blockIdx.y;
     pdl_launch_dependents();
     pdl_wait();
     const int cpg = (p.C0 + p.C1) / 32;
     const GnStatSrc ss{p.st0, p.st1, p.parts0, p.parts1, p.C0, p.C1};
-    gn_group_stats(ss, n, cpg, 1.f / ((float)cpg * (float)p.P), p.eps, gstat);
-    __syncthreads();
-    if (threadIdx.x < 64) gfinal[(long long)n * 64 + threadIdx.x] = gstat[threadIdx.x];
+    gn_group_stats_warp(ss, n, g, cpg, 1.f / ((float)cpg * (float)p.P), p.eps, gfinal + ((long long)n * 32 + g) * 2);
 }
 
 template <typename T, bool DROP>
@@ -436,7 +434,7 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
         const int N = d.N;
         auto pf = std::make_shared<GnParams>(*p);   // reads the partial sums (gfinal unset)
         fn.launch = [pf, gfinal, N](cudaStream_t s) -> int {
-            TQ_CUDA(launch_pdl(gn_finalize_kernel, dim3(N), dim3(256), 0, s, *pf, gfinal));
+            TQ_CUDA(launch_pdl(gn_finalize_kernel, dim3(32, N), dim3(32), 0, s, *pf, gfinal));
             TQ_CUDA(cudaGetLastError());
             count_launch();
             return 0;

@@ -267,17 +267,18 @@ class LightningEDM(LightningModule):
                 dts = [float((sigmas[i + 1] - hats[i]).to(torch.float32)) for i in range(nsteps)]
             else:
                 dts = [float(sigmas[i + 1] - sigmas[i]) for i in range(nsteps)]  # fp32 subtraction, like the reference
-            sched = (co, hats, co_hat, torch.tensor(tvals, dtype=torch.float32, device=dev), dts)
+            sched = (co, hats, co_hat, tvals, dts)
             self.__dict__["_tq_sched"][key] = sched
-        co, hats, co_hat, tdev, dts = sched
+        co, hats, co_hat, tvals, dts = sched
         st = current_stream_ptr()
-
-        def denoise(k):
-            plan.t.copy_(tdev[k:k + 1])
-            plan.run()
+        # The time input of denoiser call k (c_noise of its noise level, tvals[k]) is written by the sampler kernel that runs
+        # right before that call anyway (tq_edm_* `t_next`): a separate 4-byte copy between two graph replays cost 0.22 ms
+        # per call (4.41 -> 4.63 ms, tools/sampler_breakdown.py) -- 5 % of the whole sampler.
+        tp = plan.t.data_ptr()
 
         if not stochastic:
-            _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), dt_, NP, C_, Cpad, co[0].c_in, st), "precondition")
+            _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), dt_, NP, C_, Cpad, co[0].c_in, tp, tvals[0], st),
+                       "precondition")
         for i in range(nsteps):
             cur, nxt = (co_hat[i] if stochastic else co[i]), co[i + 1]
             if stochastic:
@@ -290,21 +291,22 @@ class LightningEDM(LightningModule):
                 else:
                     nz = nchw_to_nhwc(torch.randn(eps.shape, device=dev, dtype=torch.float64), torch.float64)
                 _lib.check(lib.tq_edm_add_noise(x.data_ptr(), nz.data_ptr(), scale, x.numel(), st), "add_noise")
-                _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), dt_, NP, C_, Cpad, cur.c_in, st), "precondition")
+                _lib.check(lib.tq_edm_precondition(x.data_ptr(), xin.data_ptr(), dt_, NP, C_, Cpad, cur.c_in, tp, tvals[2 * i], st),
+                           "precondition")
             dt = dts[i]
             last = i == nsteps - 1
-            denoise(2 * i)
+            plan.run()                                           # denoiser call 2i
             _lib.check(lib.tq_edm_euler(x.data_ptr(), F.data_ptr(), Cf, d.data_ptr(), x1.data_ptr(), xin.data_ptr(), dt_,
-                                        NP, C_, Cpad, cur.c_out, cur.c_skip, cur.sigma, dt, nxt.c_in, 0 if last else 1, st),
-                       "euler")
+                                        NP, C_, Cpad, cur.c_out, cur.c_skip, cur.sigma, dt, nxt.c_in, 0 if last else 1,
+                                        None if last else tp, 0.0 if last else tvals[2 * i + 1], st), "euler")
             if last:
                 x, x1 = x1, x
                 break
-            denoise(2 * i + 1)
+            plan.run()                                           # denoiser call 2i + 1
             nn_cin = co[i + 1].c_in  # the next step starts at sigma_{i+1}
             _lib.check(lib.tq_edm_heun(x.data_ptr(), x1.data_ptr(), d.data_ptr(), F.data_ptr(), Cf, xin.data_ptr(), dt_, NP,
-                                       C_, Cpad, nxt.c_out, nxt.c_skip, nxt.sigma, dt, nn_cin, 0 if stochastic else 1, st),
-                       "heun")
+                                       C_, Cpad, nxt.c_out, nxt.c_skip, nxt.sigma, dt, nn_cin, 0 if stochastic else 1,
+                                       None if stochastic else tp, 0.0 if stochastic else tvals[2 * i + 2], st), "heun")
         return x
 
     def _decode_latents(self, x: torch.Tensor, N: int, C_: int, spatial: tuple) -> torch.Tensor:
@@ -320,7 +322,7 @@ class LightningEDM(LightningModule):
             p = get_coder_plan(dec, "decoder", n, spatial)
             xs = x[i0:i0 + n]
             _lib.check(lib.tq_edm_precondition(xs.data_ptr(), p.xin.t.data_ptr(), tq_dtype(p.act_dtype), n * P, C_,
-                                               p.cin_pad, 1.0, st), "decode input")
+                                               p.cin_pad, 1.0, None, 0.0, st), "decode input")
             p.run()
             so = (p.out.H, p.out.W) if len(spatial) == 2 else (p.out.W,)
             outs.append(nhwc_to_nchw(p.out.t, n, p.cout, so, p.cout, torch.float32))
