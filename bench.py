@@ -45,7 +45,7 @@ def peaks() -> dict:
 # model construction (shared by both arms): named architecture, seeded synthetic weights
 # ------------------------------------------------------------------------------------------------------
 def build_state_dict(edm, seed=0):
-    from oracle.weights import seeded_state_dict, shapes_of
+    from tqdne_b200.synthetic_weights import seeded_state_dict, shapes_of
 
     sd = seeded_state_dict(shapes_of(edm), seed)
     # keep the random-init decoder's output inside the normalised log-spectrogram range [-1, 1]
@@ -380,7 +380,7 @@ def _event_time(fn, steps, warmup, torch, barrier=None):
 
 def build_1d_edm(steps=18, seed=0):
     import tqdne_b200 as tq
-    from oracle.weights import seeded_state_dict, shapes_of
+    from tqdne_b200.synthetic_weights import seeded_state_dict, shapes_of
     from tqdne_b200.config import MovingAverageEnvelopeConfig
 
     cfg = MovingAverageEnvelopeConfig()
@@ -478,7 +478,7 @@ def measure_cfg3(dev, pk, batch=1024):
     import torch
 
     import tqdne_b200 as tq
-    from oracle.weights import seeded_state_dict, shapes_of
+    from tqdne_b200.synthetic_weights import seeded_state_dict, shapes_of
     from tqdne_b200.config import SpectrogramConfig
 
     cfg = SpectrogramConfig()

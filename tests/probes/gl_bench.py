@@ -1,6 +1,6 @@
 """Griffin-Lim kernel timing + parity on decoded-spectrogram-like inputs: fused fp64 / fp32 kernels, 768 items, 128 iterations.
 
-    python tools/gl_bench.py [items=768] [n_iter=128]
+    python tests/probes/gl_bench.py [items=768] [n_iter=128]
 """
 import json
 import os
@@ -10,7 +10,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 from oracle import griffinlim_ref  # noqa: E402
 from tqdne_b200.representation import LogSpectrogram  # noqa: E402
 

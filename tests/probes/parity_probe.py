@@ -8,7 +8,7 @@
   (4) Griffin-Lim precision on the 768 decoded spectrograms: fp32 fused kernel / fp32 unfused kernel / fp64 kernel,
       against each other and (a few items) against the NumPy oracle in fp64 and fp32; kernel times
 
-    python tools/parity_probe.py [--batch 256] [--steps 25] [--oracle-rows 2] [--out gpurun_out/parity_probe.json]
+    python tests/probes/parity_probe.py [--batch 256] [--steps 25] [--oracle-rows 2] [--out gpurun_out/parity_probe.json]
 """
 import argparse
 import json
@@ -20,7 +20,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
 import bench  # noqa: E402

@@ -4,7 +4,7 @@ prints rel-L2 of the engine against the reference goldens for the short-ladder c
 domain (sampler state, decoded spectrogram, waveform) and per precision, so that the bounds can be stated with their
 derivation instead of a safety factor.
 
-    python tools/tolerance_probe.py > gpurun_out/tolerance_probe.json
+    python tests/probes/tolerance_probe.py > gpurun_out/tolerance_probe.json
 """
 import json
 import sys
@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
 import tqdne_b200 as tq  # noqa: E402

@@ -5,7 +5,7 @@ Tolerances (north_star): fp32 mode rel-L2 <= 1e-5, bf16 mode <= 1e-2, per denois
 sample / decoded spectrogram of the real configuration (25 Heun steps, batch 256:
 test_full_config_25_steps_bf16_tolerance_and_bit_reproducibility).  The short-ladder goldens (3 / 4 Heun steps end
 with a jump from a high noise level, so the result IS one network output chained into the next network) carry the
-bounds of BF16_CHAIN below: measured values (tools/tolerance_probe.py, bit-reproducible since the GroupNorm
+bounds of BF16_CHAIN below: measured values (tests/probes/tolerance_probe.py, bit-reproducible since the GroupNorm
 statistics are deterministic) + 25 % headroom, derived in DESIGN.md section 2.
 """
 import numpy as np
@@ -464,3 +464,52 @@ def test_full_config_25_steps_bf16_tolerance_and_bit_reproducibility():
         rep_o = torch_ref.decoder_forward(sd, dec_cfg, lat_o.float(), prefix="autoencoder.decoder.")
     assert rel_l2(lat32[pick].cpu(), lat_o) < TOL["fp32"] and rel_l2(rep32[pick].cpu(), rep_o) < TOL["fp32"]
     assert rel_l2(lat16[pick].cpu(), lat_o) < TOL["bf16"] and rel_l2(rep16[pick].cpu(), rep_o) < TOL["bf16"]
+
+
+def test_evaluation_loop_matches_direct_calls():
+    """tqdne_b200.evaluate.predict (the batch loop of experiments/evaluate.py:103-147): ragged batches, both classifier-input
+    branches (same representation type: the EDM's signal goes in directly; different type: waveform -> classifier's forward
+    representation), against the module API called by hand with the same RNG state."""
+    import tqdne_b200 as tq
+    from tests.test_oracle import CLASSIFIER_ENCODER
+    from tqdne_b200 import evaluate
+    from tqdne_b200.classifier import LithningClassifier
+    from tqdne_b200.representation import LogSpectrogram
+
+    edm = _latent_edm(91, 2, "bf16")
+    clf = seeded(LithningClassifier(CLASSIFIER_ENCODER, 5), 21).cuda().eval()
+    class Squashed(LogSpectrogram):
+        """A random-init decoder does not emit a normalised spectrogram: squash into [-1, 1] so exp() stays finite."""
+
+        def invert_representation_device(self, representation):
+            return super().invert_representation_device(torch.tanh(torch.as_tensor(representation)))
+
+    rep = Squashed(stft_channels=256, hop_size=32)
+    rep.n_iter = 4
+
+    class OtherSpectrogram(LogSpectrogram):     # a different representation type for the classifier
+        pass
+
+    g = torch.Generator().manual_seed(12)
+    batches = [{"signal": torch.tanh(torch.randn(n, 3, 128, 128, generator=g)), "waveform": torch.randn(n, 3, 4064, generator=g),
+                "cond": torch.randn(n, 5, generator=g)} for n in (2, 1)]
+    for crep in (None, OtherSpectrogram(stft_channels=256, hop_size=32)):
+        torch.manual_seed(77)
+        out = evaluate.predict(batches, edm, clf, rep, crep)
+        assert set(out) == set(evaluate.KEYS)
+        assert out["predicted_waveform"].shape == (3, 3, 4064) and out["predicted_signal"].shape == (3, 3, 128, 128)
+        assert out["target_classifier_embedding"].shape == (3, 256) and out["predicted_classifier_pred"].shape == (3, 5)
+        torch.manual_seed(77)
+        row = 0
+        for b in batches:
+            n = len(b["signal"])
+            sig = edm.sample(tuple(b["signal"].shape), None, b["cond"].cuda())
+            wav = rep.invert_representation_device(sig)
+            assert np.array_equal(out["predicted_signal"][row:row + n], sig.cpu().numpy())
+            assert np.array_equal(out["predicted_waveform"][row:row + n], wav.float().cpu().numpy())
+            cin = sig if crep is None else crep.get_representation_device(wav.float()).float()
+            tin = b["signal"].cuda() if crep is None else crep.get_representation_device(b["waveform"].cuda()).float()
+            assert np.array_equal(out["predicted_classifier_embedding"][row:row + n], clf.embed(cin).cpu().numpy())
+            assert np.array_equal(out["target_classifier_pred"][row:row + n], clf(tin).cpu().numpy())
+            row += n
+        assert all(np.isfinite(v).all() for v in out.values())

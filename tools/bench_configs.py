@@ -16,7 +16,7 @@ import torch  # noqa: E402
 
 import tqdne_b200 as tq  # noqa: E402
 from bench import cond_grid  # noqa: E402
-from oracle.weights import seeded_state_dict, shapes_of  # noqa: E402
+from tqdne_b200.synthetic_weights import seeded_state_dict, shapes_of  # noqa: E402
 from tqdne_b200.config import MovingAverageEnvelopeConfig, SpectrogramConfig  # noqa: E402
 from tqdne_b200.lowering import get_unet_plan  # noqa: E402
 

@@ -20,7 +20,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import tqdne_b200 as tq  # noqa: E402
-from oracle.weights import seeded_state_dict, shapes_of  # noqa: E402
+from tqdne_b200.synthetic_weights import seeded_state_dict, shapes_of  # noqa: E402
 from tqdne_b200.config import MovingAverageEnvelopeConfig  # noqa: E402
 from tqdne_b200.training import TrainStep1D  # noqa: E402
 

@@ -9,7 +9,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch  # noqa: E402
 
 import tqdne_b200 as tq  # noqa: E402
-from oracle.weights import seeded_state_dict, shapes_of  # noqa: E402
+from tqdne_b200.synthetic_weights import seeded_state_dict, shapes_of  # noqa: E402
 from tqdne_b200.config import MovingAverageEnvelopeConfig  # noqa: E402
 from tqdne_b200.training import TrainStep1D  # noqa: E402
 
