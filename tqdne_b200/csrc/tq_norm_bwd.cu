@@ -8,6 +8,12 @@
 //             dx = rstd_g ( gamma_c dv - M1_{n,g} - xh M2_{n,g} ),
 //                  M1 = mean over the group of gamma_c dv,  M2 = mean over the group of gamma_c dv xh
 //
+// Product path (`gn_bwd_cluster_kernel`): ONE launch, one thread-block cluster (<= 8 CTAs) per sample.  Every CTA streams
+// its position chunk once for the per-channel sums A, B, the cluster exchanges them through distributed shared memory
+// (fixed rank order: deterministic, no atomics, no scratch memset), and every CTA streams the SAME chunk again for dx -- a
+// re-read that comes out of L2 (a chunk is ~130 KB) instead of HBM: 6 B per element of HBM traffic instead of 10, one launch
+// instead of two + a memset.  The two-kernel version below stays as the fallback / A-B switch (TQ_GN_BWD_2PASS=1).
+//
 // HBM-bound, two streaming passes over (x, dy): pass 1 leaves A[n][c] = sum_p dv and B[n][c] = sum_p dv xh in a
 // scratch buffer laid out like the forward statistics; pass 2 forms M1 / M2 from them and writes dx (10 B per element in
 // bf16).  mu / rstd come from the per-(sample, channel) sums the FORWARD conv epilogue left behind (tq_conv_desc.stats).
@@ -15,6 +21,7 @@
 
 #include "tq_common.h"
 #include "tq_gnstats.cuh"
+#include "tq_ptx.cuh"
 
 namespace tq {
 namespace {
@@ -270,6 +277,224 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
     }
 }
 
+
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
+    return v;
+}
+
+// One cluster per sample (gridDim.x = cluster size = position chunks, blockIdx.y = sample): see the file header.
+template <typename T>
+__global__ void __launch_bounds__(256, 2) gn_bwd_cluster_kernel(const GnBwdParams p) {
+    __shared__ float gstat[64];   // mean, rstd per group
+    __shared__ float gm[64];      // M1, M2 per group
+    __shared__ float red[256 * 17];
+    extern __shared__ float part[];   // [Ct][2]: this CTA's per-channel (A, B) over its chunk -- read by the whole cluster
+    const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int Ct = p.C0 + p.C1, cpg = Ct / 32;
+    const int cv = Ct >> 3, lanes = 256 / cv;
+    const int vi = threadIdx.x % cv, pl = threadIdx.x / cv;
+    const bool on = pl < lanes;
+    const int c0 = vi * 8;
+    group_stats(p, n, cpg, gstat);
+    __syncthreads();
+    float ga[8], be[8], mu[8], rs[8];
+    if (on) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c0 + j) / cpg;
+            ga[j] = __ldg(p.gamma + c0 + j);
+            be[j] = __ldg(p.beta + c0 + j);
+            mu[j] = gstat[2 * g];
+            rs[j] = gstat[2 * g + 1];
+        }
+    }
+    const int per = (p.P + nchunks - 1) / nchunks;
+    const int p0 = chunk * per, p1 = min(p.P, p0 + per);
+    const VecSrc<T> s = pick_src<T>(p, n, on ? c0 : 0);
+    const T* dyb = static_cast<const T*>(p.dy) + (long long)n * p.P * Ct + (on ? c0 : 0);
+    const bool drop = p.drop_seed != nullptr;
+    const unsigned long long dseed = drop ? *p.drop_seed + 0x632BE59BD9B4E019ull * (unsigned long long)(p.drop_site + 1) : 0ull;
+    const float dkeep = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    // dv = dL/dv of one vector (dropout mask and the SiLU derivative applied to dy), xh = normalised input
+    auto grad8 = [&](const float (&xv)[8], const float (&dv)[8], int pix, float (&xh)[8], float (&d)[8]) {
+        const long long idx0 = ((long long)n * p.P + pix) * Ct + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            xh[j] = (xv[j] - mu[j]) * rs[j];
+            float dd = dv[j];
+            if (drop) dd *= dropout_scale(dseed, idx0 + j, p.drop_p, dkeep);
+            if (p.silu) {
+                const float v = fmaf(xh[j], ga[j], be[j]);
+                const float sg = sigmoid_f<T>(v);
+                dd *= sg * fmaf(v, 1.f - sg, 1.f);
+            }
+            d[j] = dd;
+        }
+    };
+    constexpr int UN = 2;   // positions in flight per thread (two CTAs per SM: 128 registers per thread)
+    using Raw = typename Vec8<T>::Raw;
+    // ---------------------------------------------------------------- phase 1: A_c = sum dv, B_c = sum dv xh over the chunk
+    float A[8] = {}, B[8] = {};
+    if (on) {
+        int pix = p0 + pl;
+        for (; pix + (UN - 1) * lanes < p1; pix += UN * lanes) {
+            Raw rx[UN], rd[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                rx[u] = Vec8<T>::ldraw(s.x + (long long)(pix + u * lanes) * s.C);
+                rd[u] = Vec8<T>::ldraw(dyb + (long long)(pix + u * lanes) * Ct);
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                float xv[8], dv[8], xh[8], d[8];
+                Vec8<T>::cvt(rx[u], xv);
+                Vec8<T>::cvt(rd[u], dv);
+                grad8(xv, dv, pix + u * lanes, xh, d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    A[j] += d[j];
+                    B[j] = fmaf(d[j], xh[j], B[j]);
+                }
+            }
+        }
+        for (; pix < p1; pix += lanes) {
+            float xv[8], dv[8], xh[8], d[8];
+            Vec8<T>::load(s.x + (long long)pix * s.C, xv);
+            Vec8<T>::load(dyb + (long long)pix * Ct, dv);
+            grad8(xv, dv, pix, xh, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                A[j] += d[j];
+                B[j] = fmaf(d[j], xh[j], B[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[threadIdx.x * 17 + j] = on ? A[j] : 0.f;
+        red[threadIdx.x * 17 + 8 + j] = on ? B[j] : 0.f;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < cv * 16; o += 256) {
+        const int vi2 = o >> 4, j = o & 15;
+        float a = 0.f;
+        for (int l = 0; l < lanes; ++l) a += red[(l * cv + vi2) * 17 + j];
+        const int c = vi2 * 8 + (j & 7);
+        part[2 * c + (j >> 3)] = a;
+        float* par = (j >> 3) ? p.dgamma : p.dbeta;   // dbeta_c = sum_n A, dgamma_c = sum_n B
+        if (par) atomicAdd(par + c, a);
+    }
+    cluster_sync_all();   // every CTA's partials are in its shared memory and visible to the cluster
+    // ---------------------------------------------------------------- M1_g, M2_g from the partials of all ranks (fixed order)
+    {
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+        const uint32_t part_addr = smem_u32(part);
+        float m1 = 0.f, m2 = 0.f;
+        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
+            float a = 0.f, b = 0.f;
+            for (int r = 0; r < nchunks; ++r) {
+                const uint32_t ra = mapa_shared(part_addr + 8u * c, (uint32_t)r);
+                a += ld_dsmem_f32(ra);
+                b += ld_dsmem_f32(ra + 4u);
+            }
+            const float gmm = __ldg(p.gamma + c);
+            m1 = fmaf(gmm, a, m1);
+            m2 = fmaf(gmm, b, m2);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+        }
+        if (sub == 0) {
+            const float inv = 1.f / ((float)cpg * (float)p.P);
+            gm[2 * g] = m1 * inv;
+            gm[2 * g + 1] = m2 * inv;
+        }
+    }
+    cluster_sync_all();   // nobody leaves (or reuses `part`) while a peer may still read its shared memory; also orders gm
+    // ---------------------------------------------------------------- phase 2: dx over the same chunk (L2-resident re-read)
+    float M1[8], M2[8], S[8] = {};
+    if (on) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c0 + j) / cpg;
+            M1[j] = gm[2 * g];
+            M2[j] = gm[2 * g + 1];
+        }
+        const bool has_add = s.add != nullptr;
+        auto emit = [&](const float (&xv)[8], const float (&dv)[8], const float (&ad)[8], int pix) {
+            float xh[8], d[8], out[8];
+            grad8(xv, dv, pix, xh, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                out[j] = rs[j] * (fmaf(ga[j], d[j], -M1[j]) - xh[j] * M2[j]) + ad[j];
+                S[j] += out[j];
+            }
+            Vec8<T>::store(s.dx + (long long)pix * s.C, out);
+        };
+        int pix = p0 + pl;
+        for (; pix + (UN - 1) * lanes < p1; pix += UN * lanes) {
+            Raw rx[UN], rd[UN], ra[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                rx[u] = Vec8<T>::ldraw(s.x + (long long)(pix + u * lanes) * s.C);
+                rd[u] = Vec8<T>::ldraw(dyb + (long long)(pix + u * lanes) * Ct);
+                if (has_add) ra[u] = Vec8<T>::ldraw(s.add + (long long)(pix + u * lanes) * s.C);
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                float xv[8], dv[8], ad[8] = {};
+                Vec8<T>::cvt(rx[u], xv);
+                Vec8<T>::cvt(rd[u], dv);
+                if (has_add) Vec8<T>::cvt(ra[u], ad);
+                emit(xv, dv, ad, pix + u * lanes);
+            }
+        }
+        for (; pix < p1; pix += lanes) {
+            float xv[8], dv[8], ad[8] = {};
+            Vec8<T>::load(s.x + (long long)pix * s.C, xv);
+            Vec8<T>::load(dyb + (long long)pix * Ct, dv);
+            if (has_add) Vec8<T>::load(s.add + (long long)pix * s.C, ad);
+            emit(xv, dv, ad, pix);
+        }
+    }
+    if (p.dx_sum != nullptr) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 17 + j] = (on && c0 < p.C0) ? S[j] : 0.f;
+        __syncthreads();
+        for (int o = threadIdx.x; o < cv * 8; o += 256) {
+            const int vi2 = o >> 3, j = o & 7;
+            const int c = vi2 * 8 + j;
+            if (c >= p.C0) continue;
+            float a = 0.f;
+            for (int l = 0; l < lanes; ++l) a += red[(l * cv + vi2) * 17 + j];
+            atomicAdd(p.dx_sum + (long long)n * p.dx_sum_ld + c, a);
+        }
+    }
+}
+
+template <typename T>
+int launch_gn_bwd_cluster(const GnBwdParams& p, int chunks, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)chunks, (unsigned)p.N);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = (size_t)(p.C0 + p.C1) * 2 * sizeof(float);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)chunks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TQ_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_cluster_kernel<T>, p));
+    return 0;
+}
+
 }  // namespace
 }  // namespace tq
 
@@ -299,6 +524,25 @@ extern "C" int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream) {
     int chunks = slots / d->N;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
+    const char* two = getenv("TQ_GN_BWD_2PASS");
+    if (!(two && two[0] == '1')) {
+        // one cluster of <= 8 CTAs (the portable cluster size) per sample, both phases in one launch; two CTAs per SM
+        // (128 registers per thread), one wave
+        int cl = (device_sm_count() * 2) / d->N;
+        if (cl > max_chunks) cl = max_chunks;
+        if (cl > 8) cl = 8;
+        if (cl < 1) cl = 1;
+        while (cl & (cl - 1)) cl &= cl - 1;   // power of two
+        p.chunks = cl;
+        if (d->dtype == TQ_F32) {
+            if (launch_gn_bwd_cluster<float>(p, cl, st)) return 1;
+        } else {
+            if (launch_gn_bwd_cluster<__nv_bfloat16>(p, cl, st)) return 1;
+        }
+        TQ_CUDA(cudaGetLastError());
+        count_launch(1);
+        return 0;
+    }
     p.chunks = chunks;
     TQ_CUDA(cudaMemsetAsync(d->ws, 0, (size_t)d->N * Ct * 2 * sizeof(float), st));
     const dim3 grid(chunks, d->N);
