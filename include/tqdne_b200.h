@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 14
+#define TQ_ABI_VERSION 15
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -212,6 +212,8 @@ typedef struct {
     const void* dx_add0; const void* dx_add1;   /* optional: gradient of x0 / x1 from their other consumer, added to dx */
     float* dx_sum; int32_t dx_sum_ld;            /* optional: dx_sum[n*ld + c] += sum_p dx0[n][p][c] (embedding gradient) */
     const uint64_t* drop_seed; float drop_p; int32_t drop_site;   /* the forward's fused dropout (tq_gn_desc), or NULL */
+    float* dbias0; float* dbias1;   /* optional: dbias[c] += sum over samples and positions of dx0 / dx1 -- the bias gradient of
+                                     * the convolution that produced x0 / x1 when dx (with dx_add) is that tensor's WHOLE gradient */
 } tq_gn_bwd_desc;
 int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream);
 

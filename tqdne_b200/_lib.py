@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 14  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 15  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -97,7 +97,8 @@ class TqGnBwdDesc(C.Structure):
                 ("eps", C.c_float), ("silu", C.c_int32), ("stats0", C.c_void_p), ("stats1", C.c_void_p), ("parts0", C.c_int32), ("parts1", C.c_int32),
                 ("ws", C.c_void_p), ("dx0", C.c_void_p), ("dx1", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
                 ("dx_add0", C.c_void_p), ("dx_add1", C.c_void_p), ("dx_sum", C.c_void_p), ("dx_sum_ld", C.c_int32),
-                ("drop_seed", C.c_void_p), ("drop_p", C.c_float), ("drop_site", C.c_int32)]
+                ("drop_seed", C.c_void_p), ("drop_p", C.c_float), ("drop_site", C.c_int32),
+                ("dbias0", C.c_void_p), ("dbias1", C.c_void_p)]
 
 
 # name -> (restype, argtypes): every symbol include/tqdne_b200.h declares

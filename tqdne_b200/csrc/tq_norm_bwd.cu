@@ -39,6 +39,8 @@ struct GnBwdParams {
     float* dgamma; float* dbeta;          // [C0 + C1], accumulated into
     const unsigned long long* drop_seed; float drop_p; int drop_site;   // the forward's fused dropout (nullptr = none)
     float* dx_sum; int dx_sum_ld;         // optional: dx_sum[n * ld + c] += sum over positions of dx0 (embedding gradient)
+    float* dbias0; float* dbias1;         // optional: dbias[c] += sum over samples and positions of dx0 / dx1 (the bias gradient
+                                          // of the convolution that produced x0 / x1, when dx is that tensor's whole gradient)
     int chunks;
 };
 
@@ -261,18 +263,22 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
             float* par = (j >> 3) ? p.dgamma : p.dbeta;   // dbeta_c = sum_n A, dgamma_c = sum_n B
             if (par) atomicAdd(par + c, a);
         }
-    } else if (p.dx_sum != nullptr) {
-        // per-sample channel sums of dx0 (first source only): same smem tree as pass 1
+    } else if (p.dx_sum != nullptr || p.dbias0 != nullptr || p.dbias1 != nullptr) {
+        // channel sums of dx over this block's positions: same smem tree as pass 1
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[threadIdx.x * 17 + j] = (on && c0 < p.C0) ? S[j] : 0.f;
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 17 + j] = on ? S[j] : 0.f;
         __syncthreads();
         for (int o = threadIdx.x; o < cv * 8; o += 256) {
             const int vi2 = o >> 3, j = o & 7;
             const int c = vi2 * 8 + j;
-            if (c >= p.C0) continue;
             float a = 0.f;
             for (int l = 0; l < lanes; ++l) a += red[(l * cv + vi2) * 17 + j];
-            atomicAdd(p.dx_sum + (long long)n * p.dx_sum_ld + c, a);
+            if (c < p.C0) {
+                if (p.dx_sum) atomicAdd(p.dx_sum + (long long)n * p.dx_sum_ld + c, a);
+                if (p.dbias0) atomicAdd(p.dbias0 + c, a);
+            } else if (p.dbias1) {
+                atomicAdd(p.dbias1 + (c - p.C0), a);
+            }
         }
     }
 }
@@ -461,18 +467,22 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_cluster_kernel(const GnBwdParam
             emit(xv, dv, ad, pix);
         }
     }
-    if (p.dx_sum != nullptr) {
+    if (p.dx_sum != nullptr || p.dbias0 != nullptr || p.dbias1 != nullptr) {
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[threadIdx.x * 17 + j] = (on && c0 < p.C0) ? S[j] : 0.f;
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 17 + j] = on ? S[j] : 0.f;
         __syncthreads();
         for (int o = threadIdx.x; o < cv * 8; o += 256) {
             const int vi2 = o >> 3, j = o & 7;
             const int c = vi2 * 8 + j;
-            if (c >= p.C0) continue;
             float a = 0.f;
             for (int l = 0; l < lanes; ++l) a += red[(l * cv + vi2) * 17 + j];
-            atomicAdd(p.dx_sum + (long long)n * p.dx_sum_ld + c, a);
+            if (c < p.C0) {
+                if (p.dx_sum) atomicAdd(p.dx_sum + (long long)n * p.dx_sum_ld + c, a);
+                if (p.dbias0) atomicAdd(p.dbias0 + c, a);
+            } else if (p.dbias1) {
+                atomicAdd(p.dbias1 + (c - p.C0), a);
+            }
         }
     }
 }
@@ -518,6 +528,7 @@ extern "C" int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream) {
     TQ_CHECK(p.parts0 >= 1 && p.parts1 >= 1, "gn_silu_backward: parts0 / parts1 of the forward statistics missing"); p.ws = d->ws;
     p.drop_seed = reinterpret_cast<const unsigned long long*>(d->drop_seed); p.drop_p = d->drop_p; p.drop_site = d->drop_site;
     if (!(d->drop_p > 0.f)) p.drop_seed = nullptr;
+    p.dbias0 = d->dbias0; p.dbias1 = d->C1 > 0 ? d->dbias1 : nullptr;
     p.dgamma = d->dgamma; p.dbeta = d->dbeta; p.dx_sum = d->dx_sum; p.dx_sum_ld = d->dx_sum_ld > 0 ? d->dx_sum_ld : d->C0;
     const int slots = device_sm_count() * 4;
     const int max_chunks = (d->P + 31) / 32;

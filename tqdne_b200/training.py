@@ -339,7 +339,25 @@ class TrainStep1D:
             self._direct(ops, lambda: _lib.check(lib.tq_rows_op(src.t.data_ptr(), aux.t.data_ptr() if aux is not None else None,
                                                                 dst.t.data_ptr(), mode, N, dst.W, dst.C, self._st()), "rows_op"))
 
-        for kind, mod, srcs, out, extra in reversed(self.nodes):
+        # Bias gradients ride on the GroupNorm backward where they can: dL/db of a convolution is the sum of its output's
+        # gradient over samples and positions, and when the FIRST consumer (in forward order) of that output is a GroupNorm,
+        # the norm's backward kernel -- the last contributor in backward order, with the other paths folded in through
+        # dx_add -- holds exactly that gradient in registers (tq_gn_bwd_desc.dbias0/1).  Saves the separate reduction pass of
+        # tq_conv1d_wgrad over dY for all but the attention qkv convolutions and the output head.
+        first_use: dict[int, int] = {}
+        producer_gb: dict[int, torch.Tensor] = {}
+        for i, (kind, mod, srcs, out, extra) in enumerate(self.nodes):
+            used = list(srcs)
+            if kind == "conv":
+                producer_gb[id(out)] = st.view(st.G, mod.bias)
+                if extra.get("residual") is not None:
+                    used.append(extra["residual"])
+            for t in used:
+                first_use.setdefault(id(t), i)
+        bias_done: set[int] = set()
+
+        for idx in range(len(self.nodes) - 1, -1, -1):
+            kind, mod, srcs, out, extra = self.nodes[idx]
             if kind == "conv":
                 dy = extra.get("dy") or grad.get(id(out))
                 assert dy is not None, "gradient of a convolution output is missing"
@@ -365,8 +383,10 @@ class TrainStep1D:
                 # weight / bias gradient, one call per concat source
                 coff = 0
                 for si, xs in enumerate(x_eff):
-                    self._direct(ops, lambda xs=xs, dy_eff=dy_eff, gw=gw, gb=gb, si=si, coff=coff, k=k, Ip=Ip: _lib.check(
-                        lib.tq_conv1d_wgrad(xs.t.data_ptr(), dy_eff.t.data_ptr(), gw.data_ptr(), gb.data_ptr() if si == 0 else None,
+                    want_gb = si == 0 and id(out) not in bias_done   # else: already summed by the consumer norm's backward
+                    self._direct(ops, lambda xs=xs, dy_eff=dy_eff, gw=gw, gb=gb, want_gb=want_gb, coff=coff, k=k, Ip=Ip: _lib.check(
+                        lib.tq_conv1d_wgrad(xs.t.data_ptr(), dy_eff.t.data_ptr(), gw.data_ptr(),
+                                            gb.data_ptr() if want_gb else None,
                                             N, xs.W, xs.C, dy_eff.C, k, Ip, coff, self._st()), "conv1d_wgrad"))
                     coff += xs.C
                 if extra.get("no_dgrad"):
@@ -414,6 +434,10 @@ class TrainStep1D:
                 site = self.drop_of_act.get(id(out))
                 if site is not None:
                     d.drop_seed, d.drop_p, d.drop_site = self.drop_seed.data_ptr(), self.p_drop, site
+                for which, xs in ((0, x0), (1, x1)):
+                    if xs is not None and first_use.get(id(xs)) == idx and id(xs) in producer_gb:
+                        setattr(d, f"dbias{which}", producer_gb[id(xs)].data_ptr())
+                        bias_done.add(id(xs))
                 if id(x0) in self.emb_of_act:   # x0 = conv1(h0) + e: de[n][c] = sum over positions of d(x0), fused here
                     d.dx_sum = self.de_all[:, self.emb_of_act[id(x0)]:].data_ptr()
                     d.dx_sum_ld = R
