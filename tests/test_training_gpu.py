@@ -190,3 +190,25 @@ def test_training_state_survives_a_change_of_batch_shape():
     edm.sync_trained_weights()
     w = edm.unet.out[2].weight.detach().float()
     assert rel_l2(ta.store.to_module_layout(ta.store.P, edm.unet.out[2].weight), w) < 1e-7
+
+
+def test_training_tape_graph_replay_equals_eager_passes():
+    """From the third pass on the tape is ONE CUDA-graph replay (all launch arguments are static; dropout decisions come
+    from a device counter): with dropout off and the same explicit sigma / noise it must give the loss and gradients of the
+    eager passes (up to the order of the fp32 atomics in the weight-gradient split-K)."""
+    from tqdne_b200.training import TrainStep1D
+
+    edm, _ = _edm(seed=35)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(2, 6, 512, device="cuda", generator=g)
+    cond = torch.randn(2, 5, device="cuda", generator=g)
+    sigma = torch.tensor([0.7, 3.0], device="cuda")
+    noise = torch.randn(2, 6, 512, device="cuda", generator=g)
+    step = TrainStep1D(edm, 2, 512, dropout=0.0)
+    losses, grads = [], []
+    for _ in range(4):
+        losses.append(float(step.forward_backward(x, cond, sigma=sigma, noise=noise)))
+        grads.append(step.store.G.clone())
+    assert isinstance(step._graph, torch.cuda.CUDAGraph), "the third pass should have captured the tape"
+    assert abs(losses[3] - losses[1]) < 1e-6 * abs(losses[1]) and abs(losses[2] - losses[1]) < 1e-6 * abs(losses[1])
+    assert rel_l2(grads[3], grads[1]) < 1e-5 and rel_l2(grads[2], grads[1]) < 1e-5

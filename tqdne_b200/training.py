@@ -147,6 +147,7 @@ class TrainStep1D:
         else:
             self.store = store
         self.copies_version = -1   # store.version the bf16 operand copies of THIS tape were made from
+        self._graph = None         # CUDA graph of the tape (None: not captured yet, False: capture failed -> eager)
         self.repack: list = []     # (fp32 master view [Op, k, Ip], forward bf16 copy | None, input-gradient bf16 copy | None, ci_off, Cs)
         self.fwd: list = []
         self.bwd: list = []
@@ -489,13 +490,37 @@ class TrainStep1D:
     # ------------------------------------------------------------------------------------------ running
     @torch.no_grad()
     def refresh_weights(self):
-        """bf16 operand copies (forward, and tap-flipped / transposed for the input gradient) from the fp32 masters."""
-        st = self._st()
-        for wv, fwd, bwd, coff, Cs in self.repack:
-            Op, k, Ip = wv.shape
-            _lib.check(self.lib.tq_repack_conv_weights(wv.data_ptr(), fwd.data_ptr() if fwd is not None else None,
-                                                       bwd.data_ptr() if bwd is not None else None, Op, k, Ip, coff, Cs, st),
-                       "repack_conv_weights")
+        """bf16 operand copies (forward, and tap-flipped / transposed for the input gradient) from the fp32 masters: ~170
+        small launches with static arguments, replayed as one CUDA graph from the third call on."""
+        def launch_all():
+            st = self._st()
+            for wv, fwd, bwd, coff, Cs in self.repack:
+                Op, k, Ip = wv.shape
+                _lib.check(self.lib.tq_repack_conv_weights(wv.data_ptr(), fwd.data_ptr() if fwd is not None else None,
+                                                           bwd.data_ptr() if bwd is not None else None, Op, k, Ip, coff, Cs, st),
+                           "repack_conv_weights")
+
+        g = self.__dict__.get("_repack_graph")
+        if os.environ.get("TQ_TRAIN_GRAPH", "1") == "0" or g is False:
+            launch_all()
+        elif g is None:
+            self._repack_calls = getattr(self, "_repack_calls", 0) + 1
+            if self._repack_calls <= 2:
+                launch_all()
+            else:
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize(self.dev)
+                    with torch.cuda.graph(g):
+                        launch_all()
+                    self._repack_graph = g
+                    g.replay()
+                except Exception:  # noqa: BLE001
+                    self._repack_graph = False
+                    torch.cuda.synchronize(self.dev)
+                    launch_all()
+        else:
+            g.replay()
         self.copies_version = self.store.version
 
     # training progress is shared by every tape of the model (see _Store)
@@ -541,10 +566,16 @@ class TrainStep1D:
         if self.cond is not None:
             assert cond is not None, "must specify cond if and only if the model is conditioned"
             self.cond.copy_(cond.to(torch.float32))
-        self.store.G.zero_()
-        self.de_all.zero_()
         self.pass_count += 1
         self.drop_seed.fill_((self.pass_count * 0x9E3779B1) & 0x7FFFFFFFFFFF)   # fresh dropout decisions every pass
+        self._run_tape()
+        return self.loss[0]
+
+    def _tape(self):
+        """Everything between the step's inputs and its gradients: ~550 launches with static arguments."""
+        N, L = self.N, self.L
+        self.store.G.zero_()
+        self.de_all.zero_()
         st = self._st()
         for f in self.fwd:
             f()
@@ -553,7 +584,32 @@ class TrainStep1D:
                                         st), "edm_loss")
         for b in self.bwd:
             b()
-        return self.loss[0]
+
+    def _run_tape(self):
+        """The tape as ONE CUDA graph (captured on the third pass, after two eager ones): the launches all have static
+        arguments -- the dropout decisions come from a counter in device memory -- so a replay replaces ~550 host-side ctypes
+        calls.  TQ_TRAIN_GRAPH=0, separate (host-seeded) dropout passes or a capture failure fall back to eager launches."""
+        use = os.environ.get("TQ_TRAIN_GRAPH", "1") != "0" and (self.fused_dropout or self.p_drop == 0.0)
+        if not use or self._graph is False:
+            return self._tape()
+        if self._graph is None:
+            self._eager_passes = getattr(self, "_eager_passes", 0) + 1
+            if self._eager_passes <= 2:
+                return self._tape()
+            try:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(self.dev)
+                with torch.cuda.graph(g):
+                    self._tape()
+                self._graph = g      # capturing does not execute: the replay below runs this pass
+            except Exception as e:  # noqa: BLE001
+                self._graph = False
+                import warnings
+
+                warnings.warn(f"tqdne_b200: CUDA-graph capture of the training tape failed ({e}); running eager")
+                torch.cuda.synchronize(self.dev)
+                return self._tape()
+        self._graph.replay()
 
     @torch.no_grad()
     def optimizer_step(self, world_size: int = 1):
