@@ -294,8 +294,8 @@ def kernel_breakdown(edm, batch, iters=3):
 
     The plan is replayed op by op with a CUDA event after every launch (that gives each kernel's share; the event gaps
     make the op-by-op sum a few per cent longer than the graph), and the captured graph itself is timed over `iters` x 8
-    replays; every kernel's time is its op-by-op share x the graph time, so the shares are those of the graph that was
-    timed and they add up to it.  profiles/ holds the ncu launch list of the same call for a cross-check of the shares."""
+    replays; every kind's time is its op-by-op time minus its launches' share of (op-by-op sum - graph time) -- the event gap
+    is a per-launch cost -- so the times are those inside the graph that was timed and add up to it.  profiles/ holds the ncu launch list of the same call for a cross-check of the shares."""
     import torch
 
     from tqdne_b200.lowering import get_unet_plan
@@ -337,9 +337,15 @@ def kernel_breakdown(edm, batch, iters=3):
         a["flops"] += meta[i][1]
         a["bytes"] += meta[i][2]
     op_sum = sum(a["ms"] for a in agg.values())
+    # the event after every launch costs a roughly constant gap PER LAUNCH (not per microsecond of kernel): remove each
+    # kind's launches' share of (op-by-op sum - graph time); the per-kind times then add up to the timed graph
+    gap = max(0.0, op_sum - graph_ms) / n
     for a in agg.values():
         a["ms_op_by_op"] = a["ms"]
-        a["ms"] = a["ms"] / op_sum * graph_ms
+        a["ms"] = max(a["ms"] - gap * a["launches"], 0.25 * a["ms"])
+    scale = graph_ms / sum(a["ms"] for a in agg.values())   # exact closure (the floor above can leave a few microseconds)
+    for a in agg.values():
+        a["ms"] *= scale
     return agg, graph_ms, op_sum
 
 
@@ -707,7 +713,8 @@ def run_engine(args) -> None:
             "peak_source": f"{pk['source']} bf16 burst (MEASURED_PEAKS.json)", "traffic": None,
             "launches_per_call": conv["launches"], "share_of_denoiser_call": conv["ms"] / tot_ms,
             "frac_of_sustained_peak": ach / pk["bf16_tflops_sustained"],
-            "timing": "per-kernel share (op-by-op CUDA events) x the time of the captured graph the step replays",
+            "timing": "op-by-op CUDA-event time minus the per-launch event gap, so that the kernel times add up to the captured "
+                      "graph the step replays",
             "graph_ms_per_denoiser_call": graph_ms, "op_by_op_ms_per_denoiser_call": op_sum_ms,
         }
         # DRAM bytes per launch from the committed ncu capture of the same launches (tools/summarize_dram.py); quoted only

@@ -130,7 +130,9 @@ class LightningEDM(LightningModule):
                 p.requires_grad = False
         self.save_hyperparameters(ignore=("autoencoder"))
         # engine knobs (not part of the reference API)
-        self.max_positions_per_pass = 256 * 1024   # micro-batch = this / (H*W) samples per Heun pass
+        # micro-batch = this / (H*W) samples per Heun pass: 1024 latent (32 x 32), 64 pixel-space (128 x 128: 843 -> 953 TFLOP/s
+        # against micro-batches of 16, tools/pixel_microbatch.py), 258 1-D (L = 4064) samples
+        self.max_positions_per_pass = 1024 * 1024
         self.decode_micro_batch = 64
         self.use_cuda_graph = True
         self.compat_rng = True    # reproduce the reference's RNG draw order inside sample()
