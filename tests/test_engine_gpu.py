@@ -513,3 +513,23 @@ def test_evaluation_loop_matches_direct_calls():
             assert np.array_equal(out["target_classifier_pred"][row:row + n], clf(tin).cpu().numpy())
             row += n
         assert all(np.isfinite(v).all() for v in out.values())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two CUDA devices")
+def test_module_on_second_device_without_set_device():
+    """streams, graph capture and the C-ABI launches must follow the MODULE's device, not the process's
+    current device.  A sampler moved to cuda:1 while cuda:0 stays current gives the bits of the cuda:0 run."""
+    import tqdne_b200 as tq
+
+    g = golden("edm_heun4_latent")
+    noise = (g["eps"] / g["sigmas"][0])
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        edm = _latent_edm(g["seed"], 4, "bf16").to(dev)
+        assert torch.cuda.current_device() == 0
+        rep = edm.sample((2, 3, 128, 128), cond=g["cond"].to(dev), noise=noise.to(dev))
+        assert rep.device == torch.device(dev)
+        wav = tq.LogSpectrogram(stft_channels=256, hop_size=32).invert_representation_device(torch.tanh(rep))
+        assert wav.device == torch.device(dev) and torch.cuda.current_device() == 0
+        outs.append((rep.cpu(), wav.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

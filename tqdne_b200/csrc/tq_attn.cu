@@ -243,10 +243,9 @@ int launch_attn(const AttnParams& p, cudaStream_t st) {
     if (p.T <= 32) {
         const int tp = (p.T + 1) & ~1;
         const size_t smem = (size_t)(3 * tp * (D + 4) + p.T * (tp + 1)) * sizeof(float);
-        static bool attr_small = false;
-        if (!attr_small) {
+        static PerDeviceOnce attr_small;
+        if (attr_small.first()) {
             TQ_CUDA(cudaFuncSetAttribute(attention_small_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            attr_small = true;
         }
         TQ_CUDA(launch_pdl(attention_small_kernel<T, D>, dim3(p.N * p.heads), dim3(128), smem, st, p));
         TQ_CUDA(cudaGetLastError());
@@ -254,10 +253,9 @@ int launch_attn(const AttnParams& p, cudaStream_t st) {
         return 0;
     }
     const size_t smem = (size_t)(2 * KBLK * (D + 1) + QB * D + 4 * KBLK) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         TQ_CUDA(cudaFuncSetAttribute(attention_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     const int qblocks = (p.T + QB - 1) / QB;
     TQ_CUDA(launch_pdl(attention_kernel<T, D>, dim3(p.N * p.heads * qblocks), dim3(128), smem, st, p));

@@ -462,11 +462,10 @@ extern "C" int tq_attention_backward(const void* qkv, const void* out, const voi
     const int blocks = (T + BLK - 1) / BLK;
     const size_t smem_q = 1024 + 4 * TILE + 2 * (size_t)p.Tk * 128;
     const size_t smem_kv = 1024 + 8 * TILE;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         TQ_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 4 * TILE + 2 * 512 * 128));
         TQ_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
-        attr = true;
     }
     attn_bwd_dq_kernel<<<N * heads * blocks, BWD_THREADS, smem_q, st>>>(p);
     TQ_CUDA(cudaGetLastError());

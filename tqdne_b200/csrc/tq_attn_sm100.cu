@@ -455,11 +455,9 @@ size_t attn_tc_smem(int Tk, int d) { return 1024 + (size_t)(d / 64) * 16384 + (s
 template <int D>
 int launch_attn_tc(const AttnTcParams& p, cudaStream_t st) {
     const size_t smem = attn_tc_smem(p.Tk, D);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    static PerDeviceMax attr_smem;
+    if (attr_smem.raise(smem))
         TQ_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
     const int qblocks = (p.T + kQB - 1) / kQB;
     TQ_CUDA(launch_pdl(attention_tc_kernel<D>, dim3(p.N * p.heads * qblocks), dim3(kThreadsTc), smem, st, p));
     TQ_CUDA(cudaGetLastError());
@@ -470,10 +468,9 @@ int launch_attn_tc(const AttnTcParams& p, cudaStream_t st) {
 template <int D, int T>
 int launch_attn_packed(const AttnPackParams& p, cudaStream_t st) {
     constexpr size_t smem = 1024 + (size_t)(D / 64) * 16384 * 2 + 32768;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         TQ_CUDA(cudaFuncSetAttribute(attention_tc_packed_kernel<D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
     }
     constexpr int PP = 128 / T;
     TQ_CUDA(launch_pdl(attention_tc_packed_kernel<D, T>, dim3((p.pairs + PP - 1) / PP), dim3(128), smem, st, p));

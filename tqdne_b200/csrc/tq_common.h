@@ -42,6 +42,30 @@ struct Op {
 };
 
 int device_sm_count();
+// cudaFuncSetAttribute (opt-in shared-memory sizes) is PER DEVICE: `static PerDeviceOnce once; if (once.first()) { ... }`
+// runs an initialiser once per device ordinal (a process-wide `static bool` left every device but the first without the
+// attribute: launches on cuda:1 failed with "invalid argument")
+// the same for attributes that grow with the request: the largest size set so far on the current device
+struct PerDeviceMax {
+    size_t cur[64] = {};
+    bool raise(size_t v) {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (v <= cur[d]) return false;
+        cur[d] = v;
+        return true;
+    }
+};
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
 // Programmatic dependent launch (opt-in: TQ_PDL=1): consecutive kernels of a plan overlap the next kernel's
 // launch latency and prologue with the previous kernel's drain; every kernel launched this way executes
 // griddepcontrol.wait before it touches memory a predecessor may still be writing.

@@ -799,11 +799,10 @@ int pow2_floor(int v) {
 template <int BN, int CG, bool OUT_F32>
 int launch_igemm(const IgemmParams& p, int grid, cudaStream_t st) {
     using C = Cfg<BN, CG>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         TQ_CUDA(cudaFuncSetAttribute(igemm_sm100_kernel<BN, CG, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);

@@ -235,10 +235,9 @@ extern "C" int tq_conv2d_wgrad(const void* x, const void* dy, float* dw, int32_t
     if (encode_nhwc(&p.ymap, dy, N, H, W, cout, p.bw, p.bh, p.bn, "dY")) return 1;
     if (encode_nhwc(&p.xmap, x, N, H, W, cin, p.bw, p.bh, p.bn, "X")) return 1;
     const size_t smem = 1024 + (size_t)W2_STAGES * (W2_A + W2_MAXT * W2_B);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         TQ_CUDA(cudaFuncSetAttribute(wgrad2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
     }
     wgrad2d_kernel<<<tiles * p.kchunks, W2_THREADS, smem, st>>>(p);
     TQ_CUDA(cudaGetLastError());

@@ -272,11 +272,8 @@ extern "C" int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* 
     if (encode_nlc(&p.ymap, dy, N, (int)L, cout, KSTEP, "dY")) return 1;
     if (encode_nlc(&p.xmap, x, N, (int)L, cin, p.b_rows, "X")) return 1;
     const size_t smem = 1024 + (size_t)WG_STAGES * (A_STAGE + p.b_stage);
-    static size_t attr = 0;
-    if (smem > attr) {
-        TQ_CUDA(cudaFuncSetAttribute(wgrad1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    static PerDeviceMax attr;
+    if (attr.raise(smem)) TQ_CUDA(cudaFuncSetAttribute(wgrad1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad1d_kernel<<<tiles * p.kchunks, WG_THREADS, smem, st>>>(p);
     TQ_CUDA(cudaGetLastError());
     count_launch();
