@@ -53,7 +53,8 @@ def test_struct_layouts_match_the_header_field_for_field():
     text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
     bodies = {name: body for body, name in re.findall(r"typedef struct \{([^{}]*)\}\s*(\w+)\s*;", text)}
     for cname, cls in (("tq_conv_desc", _lib.TqConvDesc), ("tq_gn_desc", _lib.TqGnDesc), ("tq_attn_desc", _lib.TqAttnDesc),
-                       ("tq_linear_desc", _lib.TqLinearDesc), ("tq_src", _lib.TqSrc), ("tq_slice", _lib.TqSlice)):
+                       ("tq_linear_desc", _lib.TqLinearDesc), ("tq_src", _lib.TqSrc), ("tq_slice", _lib.TqSlice),
+                       ("tq_gn_bwd_desc", _lib.TqGnBwdDesc)):
         body = bodies[cname]
         names = []
         for decl in body.split(";"):

@@ -90,6 +90,23 @@ def test_minimal_hdf5_writer_structures(tmp_path):
         hdf5_min.write(tmp_path / "bad.h5", {"a/b": np.zeros(2)})
 
 
+def test_minimal_hdf5_file_opens_with_h5py_when_available(tmp_path):
+    """wherever h5py (libhdf5) IS installed, a file written by hdf5_min must open with it and give back the
+    same datasets.  Skipped in this image (no libhdf5); runs on any machine that has h5py."""
+    h5py = pytest.importorskip("h5py")
+    from tqdne_b200 import hdf5_min
+
+    rng = np.random.default_rng(2)
+    data = {"waveforms": rng.standard_normal((5, 3, 64)).astype(np.float32), "magnitude": rng.standard_normal(5),
+            "vs30s": np.arange(5, dtype=np.float64), "counts": np.arange(9, dtype=np.int64)}
+    path = tmp_path / "w.h5"
+    hdf5_min.write(path, data)
+    with h5py.File(path, "r") as f:
+        assert sorted(f.keys()) == sorted(data)
+        for k, v in data.items():
+            assert f[k].dtype == v.dtype and f[k].shape == v.shape and np.array_equal(f[k][...], v)
+
+
 def test_reference_checkpoint_loads_without_the_reference_package(monkeypatch):
     """tests/golden/tiny_edm_reference.ckpt was written with the reference's own classes (oracle/make_golden_ckpt.py):
     its hyper_parameters pickle `tqdne.edm.EDM`.  The loader must resolve it to tqdne_b200.edm.EDM with no `tqdne`
