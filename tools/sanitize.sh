@@ -1,0 +1,11 @@
+#!/bin/bash
+# compute-sanitizer passes over the kernels that changed in round 2 (run under gpurun; slow: small cases only).
+#   memcheck : out-of-bounds / misaligned accesses
+#   racecheck: shared-memory hazards (the named-barrier statistics pass of the igemm epilogue, the Griffin-Lim frame rounds,
+#              the distributed-shared-memory exchange of the GroupNorm backward)
+set -x
+SEL='test_conv_epilogue_statistics_feed_groupnorm and bf16 and (16x16 or 8x8 or 1d_ragged or up_16x16)'
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "$SEL" 2>&1 | tail -6
+compute-sanitizer --tool racecheck --racecheck-report hazard --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "$SEL" 2>&1 | tail -8
+compute-sanitizer --tool racecheck --racecheck-report hazard --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "groupnorm_silu_backward and bf16" 2>&1 | tail -6
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "griffinlim_kernel_matches_oracle or groupnorm_silu_backward" 2>&1 | tail -6
