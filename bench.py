@@ -788,7 +788,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="waveforms per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-batch", type=int, default=4, help="waveforms per step of the CPU arm / CPU baseline sample")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="waveforms per step of the CPU arm / CPU baseline sample "
+                                                              "(8 = ~5 s per pass on 16 cores, one warm-up pass + one timed pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--configs", default="all",
                     help="secondary BASELINE.json configs measured after the headline: all | none | comma list of cfg0,cfg2,cfg3,cfg4")
