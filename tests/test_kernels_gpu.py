@@ -916,3 +916,49 @@ def test_conv2d_wgrad_matches_autograd(N, H, W, cin, cout, k):
     w = torch.zeros(cout, cin, k, k, device="cuda", dtype=torch.float64, requires_grad=True)
     F.conv2d(x.double().permute(0, 3, 1, 2), w, padding=k // 2).backward(dy.double().permute(0, 3, 1, 2))
     assert rel_l2(dw.view(cout, k, k, cin).permute(0, 3, 1, 2), w.grad) < 2e-5
+
+
+def test_conv_random_shape_sweep_bf16():
+    """Seeded sweep over shapes nobody hand-picked: odd widths / heights / batches (ragged tiles in every direction),
+    1-D lengths that are not multiples of the tile, every channel count of the networks, k in {1, 3, 5}, with the whole
+    bf16 epilogue (bias, residual, fused GroupNorm statistics) -- output against torch, statistics against the stored
+    output, and the GroupNorm that consumes them against torch."""
+    from tqdne_b200.engine import pack_conv
+
+    rng = np.random.default_rng(2024)
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    cases = []
+    for _ in range(14):
+        N = int(rng.integers(1, 10))
+        if rng.random() < 0.5:
+            sp = (int(rng.integers(2, 41)), int(rng.integers(2, 41)))
+            k = int(rng.choice([1, 3]))
+        else:
+            sp = (int(rng.integers(8, 700)),)
+            k = int(rng.choice([1, 3, 5]))
+        cin, cout = int(rng.choice([64, 128, 192, 256])), int(rng.choice([64, 128, 256, 320]))
+        cases.append((N, sp, cin, cout, k, bool(rng.random() < 0.5)))
+    for N, sp, cin, cout, k, res in cases:
+        dims = len(sp)
+        x = torch.randn(N, cin, *sp, device="cuda", generator=g)
+        w = torch.randn(cout, cin, *([k] * dims), device="cuda", generator=g) / math.sqrt(cin * k**dims)
+        b = torch.randn(cout, device="cuda", generator=g) * 0.3
+        plan = _plan(torch.bfloat16)
+        xa = _act(x, torch.bfloat16)
+        use_res = res and cin == cout
+        y = plan.conv(pack_conv(w, b, [cin], torch.bfloat16), [xa], residual=xa if use_res else None, dims=dims, stats=True)
+        gamma = 1 + 0.1 * torch.randn(cout, device="cuda", generator=g)
+        beta = 0.1 * torch.randn(cout, device="cuda", generator=g)
+        o = plan.groupnorm([y], gamma, beta, silu=True)
+        plan.run()
+        torch.cuda.synchronize()
+        xr = _rt(x, torch.bfloat16)
+        ref = _ref_conv(xr, _rt(w, torch.bfloat16), b) + (xr if use_res else 0)
+        yn = _to_nchw(y, dims)
+        tag = f"N={N} sp={sp} {cin}->{cout} k{k} res={use_res} [{plan.op_names()[0]}]"
+        assert rel_l2(yn, ref) < 5e-3, tag
+        flat = yn.reshape(N, cout, -1).double()
+        st = y.stats.reshape(N, y.stats_parts, cout, 2).double().sum(1)
+        assert rel_l2(st[..., 1], (flat * flat).sum(-1)) < 1e-4, tag
+        assert float((st[..., 0] - flat.sum(-1)).abs().max()) < 1e-3 * float(flat.abs().sum(-1).max()), tag
+        assert rel_l2(_to_nchw(o, dims), F.silu(F.group_norm(yn, 32, gamma, beta, eps=1e-5))) < 4e-3, tag
