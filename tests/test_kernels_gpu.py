@@ -355,9 +355,10 @@ def test_conv_epilogue_statistics_feed_groupnorm(case, dtype):
                                          (1, 129, 3, 64), (1, 600, 2, 64), (5, 32, 3, 64), (9, 16, 2, 64), (2, 20, 2, 64)])
 def test_attention_matches_reference_formula(N, T, heads, d, dtype):
     """bf16 with d in {64, 128}: T in {16, 32} packed tcgen05 kernel (128 / T pairs per tile; 12, 15 and 18 pairs leave a
-    ragged last CTA), 32 < T <= 512: tcgen05 kernel (tq_attn_sm100.cu,
-    ragged T exercises the TMA zero fill and the key mask, T = 300 the 256 + 128 key split, 129 the half-empty
-    softmax split); everything else (fp32, d = 32, T > 512): FFMA kernel."""
+    ragged last CTA), 32 < T <= 128: per-block tcgen05 kernel, 128 < T <= 512: multi-block kernel with P in tensor
+    memory (tq_attn_sm100.cu; ragged T exercises the TMA zero fill and the key mask, T = 300 the 256 + 128 key split
+    and O at column Tk / 4, 129 the half-empty softmax split and a second query block of one row, 256 x d = 128 O beside
+    S); everything else (fp32, d = 32, T > 512): FFMA kernel."""
     from tqdne_b200.engine import Act
 
     g = torch.Generator(device="cuda").manual_seed(T)
