@@ -16,7 +16,7 @@ from tqdne_b200.engine import Act, Plan, pack_conv  # noqa: E402
 dev = torch.device("cuda")
 
 
-def bench(N, sp, cin, cout, k, *, res=False, emb=False, stats=False, block_n=0, cta_group=0, reps=20):
+def bench(N, sp, cin, cout, k, *, res=False, emb=False, stats=False, block_n=0, cta_group=0, reps=20, f32_out=False):
     dims = len(sp)
     H, W = (sp if dims == 2 else (1, sp[0]))
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -29,7 +29,7 @@ def bench(N, sp, cin, cout, k, *, res=False, emb=False, stats=False, block_n=0, 
     pc = pack_conv(w, b, [cin], torch.bfloat16)
     for _ in range(reps):
         plan.conv(pc, [xa], residual=xa if (res and cin == cout) else None, emb=e, emb_ld=cout if emb else 0, dims=dims,
-                  stats=stats, block_n=block_n, cta_group=cta_group)
+                  stats=stats, block_n=block_n, cta_group=cta_group, out_dtype=torch.float32 if f32_out else None)
     name = [n for n in plan.op_names() if "igemm" in n][0]
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
@@ -50,10 +50,11 @@ def bench(N, sp, cin, cout, k, *, res=False, emb=False, stats=False, block_n=0, 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "one":
-        # one N H W cin cout k res emb stats bn cg   (H = 1 -> 1D)
+        # one N H W cin cout k res emb stats bn cg [f32_out]   (H = 1 -> 1D)
         a = [int(v) for v in sys.argv[2:]]
         sp = (a[1], a[2]) if a[1] > 1 else (a[2],)
-        bench(a[0], sp, a[3], a[4], a[5], res=bool(a[6]), emb=bool(a[7]), stats=bool(a[8]), block_n=a[9], cta_group=a[10], reps=6)
+        bench(a[0], sp, a[3], a[4], a[5], res=bool(a[6]), emb=bool(a[7]), stats=bool(a[8]), block_n=a[9], cta_group=a[10], reps=6,
+              f32_out=len(a) > 11 and bool(a[11]))
         sys.exit(0)
     shapes = [(256, (32, 32), 128, 128, 3), (64, (128, 128), 64, 64, 3), (256, (16, 16), 256, 256, 3),
               (256, (4, 4), 512, 512, 3), (256, (8, 8), 512, 512, 3)]

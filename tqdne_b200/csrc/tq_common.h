@@ -88,7 +88,28 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, long lon
     x ^= x >> 15;
     x *= 0x846CA68Bu;
     x ^= x >> 16;
-    return (float)(x >> 8) * (1.f / 16777216.f) < p ? 0.f : keep_scale;
+    // (float)(x >> 8) * 2^-24 < p, decided on the integers (both conversions are exact, so this is the same decision
+    // bit for bit; the int -> float conversion runs on the quarter-rate XU pipe and was 1/4 of the hash's cost)
+    const unsigned int thr = (unsigned int)ceilf(p * 16777216.f);
+    return (x >> 8) < thr ? 0.f : keep_scale;
+}
+// the same decisions for 8 consecutive elements idx0 .. idx0 + 7 (idx0 a multiple of 8, so the low word never carries):
+// the 64-bit index arithmetic and the seed folding are done once per vector, m[j] = 0 or keep_scale
+__device__ __forceinline__ void dropout_scale8(unsigned long long seed, long long idx0, float p, float keep_scale, float (&m)[8]) {
+    const unsigned int base = (unsigned int)idx0 * 0x9E3779B1u + (unsigned int)seed;
+    const unsigned int hi = (unsigned int)(seed >> 32) + (unsigned int)((unsigned long long)idx0 >> 32);
+    const unsigned int thr = (unsigned int)ceilf(p * 16777216.f);
+    const unsigned int thr8 = thr >= 0x1000000u ? 0xFFFFFFFFu : thr << 8;   // (x >> 8) < thr  <=>  x < thr * 256
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        unsigned int x = (base + (unsigned int)j * 0x9E3779B1u) ^ hi;
+        x ^= x >> 16;
+        x *= 0x7FEB352Du;
+        x ^= x >> 15;
+        x *= 0x846CA68Bu;
+        x ^= x >> 16;
+        m[j] = x < thr8 ? 0.f : keep_scale;
+    }
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

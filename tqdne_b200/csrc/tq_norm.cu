@@ -224,8 +224,10 @@ __device__ __forceinline__ void emit8(const Raw8<T>& r, const float (&a)[8], con
         }
     }
     if constexpr (DROP) {
+        float mk[8];
+        dropout_scale8(dr.seed, idx0, dr.p, dr.keep, mk);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= dropout_scale(dr.seed, idx0 + j, dr.p, dr.keep);
+        for (int j = 0; j < 8; ++j) v[j] *= mk[j];
     }
     store8(dst, v);
 }

@@ -48,6 +48,8 @@ template <typename T> struct Vec8;
 template <> struct Vec8<__nv_bfloat16> {
     using Raw = uint4;
     static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+    // coherent (L2) load: for data this kernel has written itself -- the read-only path may hold a stale line
+    static __device__ __forceinline__ Raw ldraw_cg(const __nv_bfloat16* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
     static __device__ __forceinline__ void cvt(const Raw& u, float (&v)[8]) {
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -81,6 +83,9 @@ template <> struct Vec8<float> {
     struct Raw { float4 a, b; };
     static __device__ __forceinline__ Raw ldraw(const float* p) {
         return Raw{__ldg(reinterpret_cast<const float4*>(p)), __ldg(reinterpret_cast<const float4*>(p) + 1)};
+    }
+    static __device__ __forceinline__ Raw ldraw_cg(const float* p) {
+        return Raw{__ldcg(reinterpret_cast<const float4*>(p)), __ldcg(reinterpret_cast<const float4*>(p) + 1)};
     }
     static __device__ __forceinline__ void cvt(const Raw& r, float (&v)[8]) {
         v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
@@ -305,15 +310,17 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_cluster_kernel(const GnBwdParam
     const int c0 = vi * 8;
     group_stats(p, n, cpg, gstat);
     __syncthreads();
-    float ga[8], be[8], mu[8], rs[8];
+    // per channel: xh = x rs + nmr,  v = xh gamma + beta = x gs + bs   (nmr = -mu rs, gs = gamma rs, bs = beta + gamma nmr)
+    float rs[8], nmr[8], gs[8], bs[8];
     if (on) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int g = (c0 + j) / cpg;
-            ga[j] = __ldg(p.gamma + c0 + j);
-            be[j] = __ldg(p.beta + c0 + j);
-            mu[j] = gstat[2 * g];
+            const float ga = __ldg(p.gamma + c0 + j), be = __ldg(p.beta + c0 + j);
             rs[j] = gstat[2 * g + 1];
+            nmr[j] = -gstat[2 * g] * rs[j];
+            gs[j] = ga * rs[j];
+            bs[j] = fmaf(ga, nmr[j], be);
         }
     }
     const int per = (p.P + nchunks - 1) / nchunks;
@@ -325,14 +332,15 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_cluster_kernel(const GnBwdParam
     const float dkeep = drop ? 1.f / (1.f - p.drop_p) : 1.f;
     // dv = dL/dv of one vector (dropout mask and the SiLU derivative applied to dy), xh = normalised input
     auto grad8 = [&](const float (&xv)[8], const float (&dv)[8], int pix, float (&xh)[8], float (&d)[8]) {
-        const long long idx0 = ((long long)n * p.P + pix) * Ct + c0;
+        float mk[8];
+        if (drop) dropout_scale8(dseed, ((long long)n * p.P + pix) * Ct + c0, p.drop_p, dkeep, mk);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            xh[j] = (xv[j] - mu[j]) * rs[j];
+            xh[j] = fmaf(xv[j], rs[j], nmr[j]);
             float dd = dv[j];
-            if (drop) dd *= dropout_scale(dseed, idx0 + j, p.drop_p, dkeep);
+            if (drop) dd *= mk[j];
             if (p.silu) {
-                const float v = fmaf(xh[j], ga[j], be[j]);
+                const float v = fmaf(xv[j], gs[j], bs[j]);
                 const float sg = sigmoid_f<T>(v);
                 dd *= sg * fmaf(v, 1.f - sg, 1.f);
             }
@@ -363,6 +371,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_cluster_kernel(const GnBwdParam
                     A[j] += d[j];
                     B[j] = fmaf(d[j], xh[j], B[j]);
                 }
+                Vec8<T>::store(s.dx + (long long)(pix + u * lanes) * s.C, d);   // parked for phase 2 (see there)
             }
         }
         for (; pix < p1; pix += lanes) {
@@ -375,6 +384,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_cluster_kernel(const GnBwdParam
                 A[j] += d[j];
                 B[j] = fmaf(d[j], xh[j], B[j]);
             }
+            Vec8<T>::store(s.dx + (long long)pix * s.C, d);
         }
     }
 #pragma unroll
@@ -422,22 +432,31 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_cluster_kernel(const GnBwdParam
     }
     cluster_sync_all();   // nobody leaves (or reuses `part`) while a peer may still read its shared memory; also orders gm
     // ---------------------------------------------------------------- phase 2: dx over the same chunk (L2-resident re-read)
-    float M1[8], M2[8], S[8] = {};
+    // The kernel is bound by its arithmetic, not by HBM (dropout hash + SiLU derivative: ~30 instructions per element),
+    // so phase 1 parks dv -- dy with the mask and the activation derivative applied -- in the dx buffer, in the tensor's
+    // own precision, and phase 2 reads it back (the same thread reads what it wrote; coherent load) instead of
+    // evaluating the hash and the sigmoid a second time.
+    // dx = rs (gamma d - M1 - xh M2) [+ add] = gs d - rs M1 - xh (rs M2)
+    float rM1[8], rM2[8], S[8] = {};
+    const bool want_sum = p.dx_sum != nullptr || p.dbias0 != nullptr || p.dbias1 != nullptr;
     if (on) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int g = (c0 + j) / cpg;
-            M1[j] = gm[2 * g];
-            M2[j] = gm[2 * g + 1];
+            rM1[j] = rs[j] * gm[2 * g];
+            rM2[j] = rs[j] * gm[2 * g + 1];
         }
         const bool has_add = s.add != nullptr;
-        auto emit = [&](const float (&xv)[8], const float (&dv)[8], const float (&ad)[8], int pix) {
-            float xh[8], d[8], out[8];
-            grad8(xv, dv, pix, xh, d);
+        auto emit = [&](const float (&xv)[8], const float (&d)[8], const float (&ad)[8], int pix) {
+            float out[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                out[j] = rs[j] * (fmaf(ga[j], d[j], -M1[j]) - xh[j] * M2[j]) + ad[j];
-                S[j] += out[j];
+                const float xh = fmaf(xv[j], rs[j], nmr[j]);
+                out[j] = fmaf(-xh, rM2[j], fmaf(gs[j], d[j], ad[j] - rM1[j]));
+            }
+            if (want_sum) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) S[j] += out[j];
             }
             Vec8<T>::store(s.dx + (long long)pix * s.C, out);
         };
@@ -447,7 +466,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_cluster_kernel(const GnBwdParam
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
                 rx[u] = Vec8<T>::ldraw(s.x + (long long)(pix + u * lanes) * s.C);
-                rd[u] = Vec8<T>::ldraw(dyb + (long long)(pix + u * lanes) * Ct);
+                rd[u] = Vec8<T>::ldraw_cg(s.dx + (long long)(pix + u * lanes) * s.C);
                 if (has_add) ra[u] = Vec8<T>::ldraw(s.add + (long long)(pix + u * lanes) * s.C);
             }
 #pragma unroll
@@ -462,12 +481,12 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_cluster_kernel(const GnBwdParam
         for (; pix < p1; pix += lanes) {
             float xv[8], dv[8], ad[8] = {};
             Vec8<T>::load(s.x + (long long)pix * s.C, xv);
-            Vec8<T>::load(dyb + (long long)pix * Ct, dv);
+            Vec8<T>::cvt(Vec8<T>::ldraw_cg(s.dx + (long long)pix * s.C), dv);
             if (has_add) Vec8<T>::load(s.add + (long long)pix * s.C, ad);
             emit(xv, dv, ad, pix);
         }
     }
-    if (p.dx_sum != nullptr || p.dbias0 != nullptr || p.dbias1 != nullptr) {
+    if (want_sum) {
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 8; ++j) red[threadIdx.x * 17 + j] = on ? S[j] : 0.f;

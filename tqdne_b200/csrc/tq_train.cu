@@ -175,8 +175,10 @@ __global__ void __launch_bounds__(256) dropout_apply_kernel(const __nv_bfloat16*
     float v[8];
     ld8(src + i * 8, v);
     const float ks = 1.f / (1.f - p);
+    float mk[8];
+    dropout_scale8(seed, i * 8, p, ks, mk);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= dropout_scale(seed, i * 8 + j, p, ks);
+    for (int j = 0; j < 8; ++j) v[j] *= mk[j];
     st8(dst + i * 8, v);
 }
 
