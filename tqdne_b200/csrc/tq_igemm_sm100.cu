@@ -828,12 +828,24 @@ int launch_igemm_o(const IgemmParams& p, int grid, bool f32, cudaStream_t st) {
     return f32 ? launch_igemm<BN, CG, true>(p, grid, st) : launch_igemm<BN, CG, false>(p, grid, st);
 }
 
-// cycles per 64-deep K slice per SM: the larger of the tensor-pipe time (2*BN) and the shared-memory traffic
-// (operand fill + operand read at 128 B/clk): the model behind the automatic (BN, CG) choice
-long long slice_cycles(int bn, int cg) {
-    const long long mma = 2LL * bn;
-    const long long smem = (A_BYTES + (long long)(bn / cg) * BK * 2) / 64;
-    return mma > smem ? mma : smem;
+// The automatic (BN, CG = 2) choice: cost = c0 + rounds * (slices * a + e) in SM cycles, fitted to the forced-tile sweep
+// of every convolution of a latent denoiser call (tools/tile_sweep.py, profiles/r2_tile_sweep_latent.txt):
+//   a   cycles per 64-deep K slice: the tensor pipe at N = 256 / 128 (2 * BN: per FLOP the two are equally efficient since
+//       two slices share a stage at N <= 128), the mbarrier handshake floor at N = 64
+//   e   per-round cost that does not overlap the next tile's mainloop (accumulator hand-over, epilogue tail)
+//   c0  per launch: pipeline fill and the last epilogue, which nothing overlaps
+// The model it replaces charged N = 128 slices for their shared-memory traffic (384 cycles) and 700 cycles per round: it kept
+// the 16 x 16 level of the latent UNet on 256-wide tiles (256 tiles on 74 clusters = 4 rounds at 86 %) where 128-wide tiles
+// (512 tiles, 7 rounds at 99 %) measure 17 % faster.
+struct TileCost { long long a, e, c0; };
+TileCost tile_cost(int bn) {
+    if (bn >= 256) return {516, 2900, 12800};
+    if (bn >= 128) return {265, 2450, 10150};
+    return {200, 1500, 8750};
+}
+long long conv_cost(int bn, long long rounds, long long slices) {
+    const TileCost c = tile_cost(bn);
+    return c.c0 + rounds * (slices * c.a + c.e);
 }
 
 }  // namespace
@@ -892,7 +904,7 @@ int build_conv_sm100(std::vector<Op>& ops, const tq_conv_desc& d) {
             const long long tiles = m_groups * ((d.cout_pad + cand - 1) / cand) * d.num_classes;
             const long long clusters = sms / cg;
             const long long rounds = (tiles + clusters - 1) / clusters;
-            const long long cost = rounds * ((long long)d.num_slices * slice_cycles(cand, cg) + 700);
+            const long long cost = conv_cost(cand, rounds, d.num_slices);
             if (best < 0 || cost < best) {
                 best = cost;
                 bn_tile = cand;
