@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 15
+#define TQ_ABI_VERSION 16
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -250,6 +250,22 @@ int tq_dropout_apply(const void* src, void* dst, int64_t n, uint64_t seed, float
  * bwd [Cs][k*Op] = master[co][k-1-t][ci_off+ci] (input-gradient operand: taps flipped, in / out transposed).      */
 int tq_repack_conv_weights(const float* master, void* fwd, void* bwd, int32_t Op, int32_t k, int32_t Ip, int32_t ci_off,
                            int32_t Cs, void* stream);
+/* All operand copies of a model in ONE launch (the per-convolution calls above are ~170 launches of 2-5 us each, a
+ * serial chain even inside a CUDA graph: 0.68 ms of a 14.7 ms training step).  Fill `jobs` (pointers = device addresses,
+ * one job per copy: exactly one of fwd / bwd set), call tq_repack_batch_prepare on the HOST array -- it assigns every job
+ * its range of thread blocks and returns their total (-1 on a bad job) -- copy the array to device memory and launch
+ * tq_repack_batch_run with that device copy after every optimiser step.                                               */
+typedef struct {
+    const float* master;   /* fp32 [Op][k][Ip] */
+    void* fwd;             /* bf16 [Op][k*Ip] or NULL */
+    void* bwd;             /* bf16 [Cs][k*Op] or NULL */
+    int32_t Op, k, Ip, ci_off, Cs;
+    int32_t block0;        /* filled by tq_repack_batch_prepare: first thread block of this job */
+    int32_t nblocks;       /*                                     and how many it owns          */
+    int32_t pad_;
+} tq_repack_job;
+int64_t tq_repack_batch_prepare(tq_repack_job* jobs_host, int32_t n_jobs);
+int     tq_repack_batch_run(const tq_repack_job* jobs_device, int32_t n_jobs, int64_t total_blocks, void* stream);
 int tq_adam_ema_step(float* param, const float* grad, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2,
                      float eps, int64_t step, float ema_decay, float grad_scale, void* stream);
 

@@ -856,6 +856,26 @@ def test_training_helper_kernels_match_torch():
     _lib.check(lib.tq_repack_conv_weights(m.data_ptr(), fwd.data_ptr(), bwd.data_ptr(), Op, k, Ip, off, Cs, st), "repack")
     assert torch.equal(fwd, m.reshape(Op, -1).to(bf))
     assert torch.equal(bwd, m[:, :, off:off + Cs].flip(1).permute(2, 1, 0).reshape(Cs, -1).to(bf))
+    # the same copies (and two more shapes: ragged 32 x 32 tiles, k = 1) through the one-launch job table
+    import ctypes as C
+    shapes = [(Op, k, Ip, off, Cs), (64, 3, 64, 0, 64), (192, 1, 320, 64, 72)]
+    ms = [torch.randn(o, kk, i, device="cuda", generator=g) for o, kk, i, _, _ in shapes]
+    fws = [torch.zeros(o, kk * i, device="cuda", dtype=bf) for o, kk, i, _, _ in shapes]
+    bws = [torch.zeros(cs, kk * o, device="cuda", dtype=bf) for o, kk, _, _, cs in shapes]
+    jobs = (_lib.TqRepackJob * (2 * len(shapes)))()
+    for n, ((o, kk, i, of, cs), mm, fw, bw) in enumerate(zip(shapes, ms, fws, bws)):
+        a, b2 = jobs[2 * n], jobs[2 * n + 1]
+        a.master, a.fwd, a.bwd, a.Op, a.k, a.Ip, a.ci_off, a.Cs = mm.data_ptr(), fw.data_ptr(), None, o, kk, i, 0, 0
+        b2.master, b2.fwd, b2.bwd, b2.Op, b2.k, b2.Ip, b2.ci_off, b2.Cs = mm.data_ptr(), None, bw.data_ptr(), o, kk, i, of, cs
+    total = lib.tq_repack_batch_prepare(jobs, len(jobs))
+    assert total == sum(j.nblocks for j in jobs) > 0 and jobs[0].block0 == 0
+    tab = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).cuda()
+    _lib.check(lib.tq_repack_batch_run(tab.data_ptr(), len(jobs), total, st), "repack batch")
+    for (o, kk, i, of, cs), mm, fw, bw in zip(shapes, ms, fws, bws):
+        assert torch.equal(fw, mm.reshape(o, -1).to(bf))
+        assert torch.equal(bw, mm[:, :, of:of + cs].flip(1).permute(2, 1, 0).reshape(cs, -1).to(bf))
+    bad = (_lib.TqRepackJob * 1)()
+    assert lib.tq_repack_batch_prepare(bad, 1) == -1   # no master, neither copy requested
 
 
 def test_groupnorm_fused_dropout_forward_and_backward_agree():

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 15  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 16  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -101,6 +101,12 @@ class TqGnBwdDesc(C.Structure):
                 ("dbias0", C.c_void_p), ("dbias1", C.c_void_p)]
 
 
+class TqRepackJob(C.Structure):
+    _fields_ = [("master", C.c_void_p), ("fwd", C.c_void_p), ("bwd", C.c_void_p),
+                ("Op", C.c_int32), ("k", C.c_int32), ("Ip", C.c_int32), ("ci_off", C.c_int32), ("Cs", C.c_int32),
+                ("block0", C.c_int32), ("nblocks", C.c_int32), ("pad_", C.c_int32)]
+
+
 # name -> (restype, argtypes): every symbol include/tqdne_b200.h declares
 _VP, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 SIGNATURES = {
@@ -135,6 +141,8 @@ SIGNATURES = {
     "tq_edm_loss": (C.c_int, [_VP, _I32, _VP, _VP, _VP, _VP, _VP, _I64, _I64, _I32, _I32, _F, _VP]),
     "tq_dropout_mask": (C.c_int, [_VP, _I64, C.c_uint64, _F, _VP]),
     "tq_repack_conv_weights": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "tq_repack_batch_prepare": (_I64, [C.POINTER(TqRepackJob), _I32]),
+    "tq_repack_batch_run": (C.c_int, [_VP, _I32, _I64, _VP]),
     "tq_dropout_apply": (C.c_int, [_VP, _VP, _I64, C.c_uint64, _F, _VP]),
     "tq_adam_ema_step": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _I64, _F, _F, _VP]),
     "tq_edm_precondition": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _I32, _F, _VP, _F, _VP]),

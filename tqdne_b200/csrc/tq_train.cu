@@ -207,6 +207,52 @@ __global__ void __launch_bounds__(256) repack_bwd_kernel(const float* __restrict
     }
 }
 
+// Every operand copy of a model in one launch: block b finds its job by binary search over the jobs' first blocks
+// (tq_repack_batch_prepare), then does what the two kernels above do -- a forward job casts 2048 consecutive elements per
+// block (8 per thread), a backward job transposes one 32 x 32 (co, ci) tile of one tap through shared memory.
+__global__ void __launch_bounds__(256) repack_batch_kernel(const tq_repack_job* __restrict__ jobs, int n_jobs) {
+    __shared__ float tile[32][33];
+    int lo = 0, hi = n_jobs - 1;
+    const int b = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].block0 <= b) lo = mid;
+        else hi = mid - 1;
+    }
+    const tq_repack_job j = jobs[lo];
+    const int local = b - j.block0;
+    if (j.fwd != nullptr) {
+        const long long n = (long long)j.Op * j.k * j.Ip;   // a multiple of 8 (Ip is padded to 64)
+        const long long i = ((long long)local * 256 + threadIdx.x) * 8;
+        if (i < n) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(j.master + i));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(j.master + i) + 1);
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
+            uint4 o;
+            o.x = *reinterpret_cast<const unsigned int*>(&p0); o.y = *reinterpret_cast<const unsigned int*>(&p1);
+            o.z = *reinterpret_cast<const unsigned int*>(&p2); o.w = *reinterpret_cast<const unsigned int*>(&p3);
+            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(j.fwd) + i) = o;
+        }
+        return;
+    }
+    const int tiles_ci = (j.Cs + 31) / 32, tiles_co = (j.Op + 31) / 32;
+    const int t = local / (tiles_ci * tiles_co);
+    const int r0 = local % (tiles_ci * tiles_co);
+    const int co0 = (r0 / tiles_ci) * 32, ci0 = (r0 % tiles_ci) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(j.bwd);
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        tile[r][tx] = (co < j.Op && ci < j.Cs) ? __ldg(j.master + ((long long)co * j.k + (j.k - 1 - t)) * j.Ip + j.ci_off + ci) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        if (ci < j.Cs && co < j.Op) dst[((long long)ci * j.k + t) * j.Op + co] = __float2bfloat16_rn(tile[tx][r]);
+    }
+}
+
 // Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) + EMA lerp (ema.py:24-28), one pass over flat fp32 arrays
 __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ ema, long long n, float lr, float b1,
@@ -323,6 +369,36 @@ int tq_repack_conv_weights(const float* master, void* fwd, void* bwd, int32_t Op
         TQ_CUDA(cudaGetLastError());
         count_launch();
     }
+    return 0;
+}
+
+int64_t tq_repack_batch_prepare(tq_repack_job* jobs, int32_t n_jobs) {
+    if (jobs == nullptr || n_jobs <= 0) { set_error("repack_batch_prepare: no jobs"); return -1; }
+    long long total = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        tq_repack_job& j = jobs[i];
+        const bool one = (j.fwd != nullptr) != (j.bwd != nullptr);
+        if (!j.master || !one || j.Op <= 0 || j.k <= 0 || j.Ip <= 0 || j.Ip % 8 != 0 || j.ci_off < 0 ||
+            (j.bwd != nullptr && (j.Cs <= 0 || j.ci_off + j.Cs > j.Ip))) {
+            set_error("repack_batch_prepare: bad job %d", i);
+            return -1;
+        }
+        long long nb;
+        if (j.fwd) nb = ((long long)j.Op * j.k * j.Ip + 2047) / 2048;
+        else nb = (long long)((j.Cs + 31) / 32) * ((j.Op + 31) / 32) * j.k;
+        if (total + nb > 0x7fffffffLL) { set_error("repack_batch_prepare: too many blocks"); return -1; }
+        j.block0 = (int32_t)total;
+        j.nblocks = (int32_t)nb;
+        total += nb;
+    }
+    return total;
+}
+
+int tq_repack_batch_run(const tq_repack_job* jobs_device, int32_t n_jobs, int64_t total_blocks, void* stream) {
+    TQ_CHECK(jobs_device && n_jobs > 0 && total_blocks > 0 && total_blocks <= 0x7fffffffLL, "repack_batch_run: bad arguments");
+    repack_batch_kernel<<<(unsigned)total_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_device, n_jobs);
+    TQ_CUDA(cudaGetLastError());
+    count_launch();
     return 0;
 }
 

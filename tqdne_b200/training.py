@@ -490,37 +490,36 @@ class TrainStep1D:
     # ------------------------------------------------------------------------------------------ running
     @torch.no_grad()
     def refresh_weights(self):
-        """bf16 operand copies (forward, and tap-flipped / transposed for the input gradient) from the fp32 masters: ~170
-        small launches with static arguments, replayed as one CUDA graph from the third call on."""
-        def launch_all():
+        """bf16 operand copies (forward, and tap-flipped / transposed for the input gradient) from the fp32 masters: ONE
+        launch over a device-resident job table (`tq_repack_batch_run`; the ~170 per-convolution launches it replaces were
+        a 0.68 ms serial chain even as a CUDA graph).  `TQ_REPACK_BATCH=0` keeps the per-convolution calls."""
+        if os.environ.get("TQ_REPACK_BATCH", "1") == "0":
             st = self._st()
             for wv, fwd, bwd, coff, Cs in self.repack:
                 Op, k, Ip = wv.shape
                 _lib.check(self.lib.tq_repack_conv_weights(wv.data_ptr(), fwd.data_ptr() if fwd is not None else None,
                                                            bwd.data_ptr() if bwd is not None else None, Op, k, Ip, coff, Cs, st),
                            "repack_conv_weights")
-
-        g = self.__dict__.get("_repack_graph")
-        if os.environ.get("TQ_TRAIN_GRAPH", "1") == "0" or g is False:
-            launch_all()
-        elif g is None:
-            self._repack_calls = getattr(self, "_repack_calls", 0) + 1
-            if self._repack_calls <= 2:
-                launch_all()
-            else:
-                try:
-                    g = torch.cuda.CUDAGraph()
-                    torch.cuda.synchronize(self.dev)
-                    with torch.cuda.graph(g):
-                        launch_all()
-                    self._repack_graph = g
-                    g.replay()
-                except Exception:  # noqa: BLE001
-                    self._repack_graph = False
-                    torch.cuda.synchronize(self.dev)
-                    launch_all()
         else:
-            g.replay()
+            tab = self.__dict__.get("_repack_table")
+            if tab is None:
+                entries = []
+                for wv, fwd, bwd, coff, Cs in self.repack:
+                    Op, k, Ip = wv.shape
+                    if fwd is not None:
+                        entries.append((wv.data_ptr(), fwd.data_ptr(), None, Op, k, Ip, 0, 0))
+                    if bwd is not None:
+                        entries.append((wv.data_ptr(), None, bwd.data_ptr(), Op, k, Ip, coff, Cs))
+                jobs = (_lib.TqRepackJob * len(entries))()
+                for j, (m, f, b, Op, k, Ip, coff, Cs) in zip(jobs, entries):
+                    j.master, j.fwd, j.bwd, j.Op, j.k, j.Ip, j.ci_off, j.Cs = m, f, b, Op, k, Ip, coff, Cs
+                total = self.lib.tq_repack_batch_prepare(jobs, len(entries))
+                if total <= 0:
+                    raise RuntimeError("repack_batch_prepare: " + self.lib.tq_last_error().decode(errors="replace"))
+                dev_jobs = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.dev)
+                tab = self._repack_table = (dev_jobs, len(entries), int(total))
+            dev_jobs, n, total = tab
+            _lib.check(self.lib.tq_repack_batch_run(dev_jobs.data_ptr(), n, total, self._st()), "repack_batch_run")
         self.copies_version = self.store.version
 
     # training progress is shared by every tape of the model (see _Store)
