@@ -9,3 +9,7 @@ compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test
 compute-sanitizer --tool racecheck --racecheck-report hazard --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "$SEL" 2>&1 | tail -8
 compute-sanitizer --tool racecheck --racecheck-report hazard --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "groupnorm_silu_backward and bf16" 2>&1 | tail -6
 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "griffinlim_kernel_matches_oracle or groupnorm_silu_backward" 2>&1 | tail -6
+# later in round 2: the multi-block attention kernel (P in tensor memory), the one-launch operand repack, the GroupNorm
+# backward that parks dv in the dx buffer
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "(attention_matches_reference_formula and bf16) or training_helper_kernels or fused_dropout" 2>&1 | tail -6
+compute-sanitizer --tool racecheck --racecheck-report hazard --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "attention_matches_reference_formula and bf16 and (508 or 300 or 256)" 2>&1 | tail -6
