@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 16
+#define TQ_ABI_VERSION 17
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -137,6 +137,10 @@ typedef struct {
     /* training only (bf16): y = dropout(act(GroupNorm(x))), nn.Dropout of ResBlock.out_layers (tqdne/unet.py:100-108).
      * The decision of element i is hash(*drop_seed + site, i) < drop_p; NULL / 0 = no dropout (every sampling plan).   */
     const uint64_t* drop_seed; float drop_p; int32_t drop_site;
+    /* FiLM, ResBlock(use_scale_shift_norm=True) (tqdne/unet.py:135-139): y = act(GroupNorm(x) * (1 + scale) + shift) with
+     * scale[n][c] = film[n * film_ld + c], shift[n][c] = film[n * film_ld + C0 + C1 + c] (fp32; the two halves of the
+     * block's embedding projection, th.chunk(emb_out, 2, dim=1)).  NULL = plain GroupNorm.                            */
+    const float* film; int32_t film_ld;
 } tq_gn_desc;
 int tq_plan_add_groupnorm(tq_plan* p, const tq_gn_desc* d);
 /* fp32 scratch floats `ws` must hold for this op on the current device (0 = none needed), < 0 on bad arguments */

@@ -29,11 +29,18 @@ def _res_block(sd, p, x, emb):
     """ResBlock._forward (tqdne/unet.py:131-143) and the embedding-free blocks.ResBlock (blocks.py:256-260)."""
     h = _conv(F.silu(_gn(x, sd[p + "in_layers.0.weight"], sd[p + "in_layers.0.bias"])),
               sd[p + "in_layers.2.weight"], sd[p + "in_layers.2.bias"])
+    film = None
     if emb is not None:
         e = F.linear(F.silu(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"])
-        h = h + e[(...,) + (None,) * (h.dim() - 2)]
-    h = _conv(F.silu(_gn(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"])),
-              sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"])
+        e = e[(...,) + (None,) * (h.dim() - 2)]
+        if e.shape[1] == 2 * h.shape[1]:   # use_scale_shift_norm: the projection is 2 * out_channels wide (unet.py:95)
+            film = torch.chunk(e, 2, dim=1)
+        else:
+            h = h + e
+    hn = _gn(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"])
+    if film is not None:
+        hn = hn * (1 + film[0]) + film[1]   # unet.py:135-139
+    h = _conv(F.silu(hn), sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"])
     if p + "skip_connection.weight" in sd:
         x = _conv(x, sd[p + "skip_connection.weight"], sd[p + "skip_connection.bias"])
     return x + h
@@ -199,30 +206,33 @@ def sampling_sigmas(num_steps: int):
     return torch.cat([s, torch.zeros_like(s[:1])])
 
 
-def denoise(sd, cfg, x, sigma, cond, prefix="unet."):
-    """LightningEDM.forward (edm.py:105-113): D = c_out * F(c_in x, 0.25 ln sigma, cond) + c_skip x."""
+def denoise(sd, cfg, x, sigma, cond, prefix="unet.", cond_sample=None):
+    """LightningEDM.forward (edm.py:105-113): D = c_out * F(c_in x [cat cond_sample], 0.25 ln sigma, cond) + c_skip x."""
     ex = (...,) + (None,) * (x.dim() - 1)
     c_in = 1 / (sigma**2 + SIGMA_DATA**2) ** 0.5
     c_out = sigma * SIGMA_DATA / (sigma**2 + SIGMA_DATA**2) ** 0.5
     c_skip = SIGMA_DATA**2 / (sigma**2 + SIGMA_DATA**2)
-    out = unet_forward(sd, cfg, x * c_in[ex], 0.25 * sigma.log(), cond, prefix)
+    inp = x * c_in[ex]
+    if cond_sample is not None:
+        inp = torch.cat((inp, cond_sample), dim=1)   # edm.py:109
+    out = unet_forward(sd, cfg, inp, 0.25 * sigma.log(), cond, prefix)
     return out * c_out[ex] + c_skip[ex] * x
 
 
-def heun_sample(sd, cfg, eps, sigmas, cond, prefix="unet.", trace=None):
+def heun_sample(sd, cfg, eps, sigmas, cond, prefix="unet.", trace=None, cond_sample=None):
     """LightningEDM.sample_deterministically (edm.py:171-196): fp64 state, fp32 denoiser, NFE = 2N-1."""
     n = len(sigmas) - 1
     x_next = eps
     for i in range(n):
         s, s_next = sigmas[i], sigmas[i + 1]
         x = x_next
-        pred = denoise(sd, cfg, x.float(), s.repeat(len(x)), cond, prefix).double()
+        pred = denoise(sd, cfg, x.float(), s.repeat(len(x)), cond, prefix, cond_sample).double()
         if trace is not None:
             trace.append(pred)
         d = (x - pred) / s
         x_next = x + d * (s_next - s)
         if i < n - 1:
-            pred2 = denoise(sd, cfg, x_next.float(), s_next.repeat(len(x)), cond, prefix).double()
+            pred2 = denoise(sd, cfg, x_next.float(), s_next.repeat(len(x)), cond, prefix, cond_sample).double()
             if trace is not None:
                 trace.append(pred2)
             d2 = (x_next - pred2) / s_next

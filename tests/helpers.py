@@ -25,7 +25,12 @@ def arch():
 def unet_cfg(kind):
     a = arch()
     return {"latent2d": a.get_2d_unet_config(CFG, 8, 8), "1d": a.get_1d_unet_config(CFG, 6, 6),
-            "pixel2d": a.get_2d_unet_config(CFG, 3, 3)}[kind]
+            "pixel2d": a.get_2d_unet_config(CFG, 3, 3),
+            # signal-conditioned variants: cond_sample supplies the second half of the input channels (edm.py:109)
+            "1d_condsample": a.get_1d_unet_config(CFG, 12, 6), "latent2d_condsample": a.get_2d_unet_config(CFG, 16, 8),
+            # FiLM ResBlocks (use_scale_shift_norm, unet.py:135-139)
+            "latent2d_film": dict(a.get_2d_unet_config(CFG, 8, 8), use_scale_shift_norm=True),
+            "1d_film": dict(a.get_1d_unet_config(CFG, 6, 6), use_scale_shift_norm=True)}[kind]
 
 
 def seeded(module, seed):

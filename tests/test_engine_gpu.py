@@ -37,7 +37,8 @@ def _unet(kind, seed, mode):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("kind,name", [("latent2d", "unet_latent2d"), ("1d", "unet_1d"), ("pixel2d", "unet_pixel2d")])
+@pytest.mark.parametrize("kind,name", [("latent2d", "unet_latent2d"), ("1d", "unet_1d"), ("pixel2d", "unet_pixel2d"),
+                                       ("latent2d_film", "unet_film_2d"), ("1d_film", "unet_film_1d")])
 def test_unet_forward_matches_reference_golden(kind, name, mode):
     g = golden(name)
     net = _unet(kind, g["seed"], mode)
@@ -183,6 +184,33 @@ def test_stochastic_sampler_matches_reference_golden(name, kind, mode):
     edm.max_positions_per_pass = shape[-1] if len(shape) == 3 else 1024   # one sample per pass
     b = edm.sample(shape, cond=cond, generator=torch.Generator(device="cuda").manual_seed(3))
     assert bool(torch.isfinite(a).all()) and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,kind", [("edm_condsample_1d", "1d_condsample"), ("edm_condsample_2d", "latent2d_condsample")])
+def test_signal_conditioned_sampler_matches_reference_golden(name, kind, mode):
+    """cond_sample (reference edm.py:109: th.cat((c_in * sample, cond_sample), dim=1) in front of the UNet at every
+    denoiser call) against the reference's own sample_deterministically.  The engine keeps the conditioning signal in a
+    tensor of its own and the stem convolution reads it as a second concat segment."""
+    import tqdne_b200 as tq
+
+    g = golden(name)
+    edm = tq.LightningEDM(unet_cfg(kind), {}, num_sampling_steps=int(g["steps"]))
+    seeded(edm, g["seed"]).cuda().set_engine_precision(mode)
+    cs, cond = g["cond_sample"].cuda(), g["cond"].cuda()
+    out = edm.sample_deterministically(g["eps"].cuda(), g["sigmas"], cs, cond)
+    assert out.dtype == torch.float64 and out.shape == g["sample"].shape
+    err = rel_l2(out.cpu(), g["sample"])
+    assert err < (TOL["fp32"] if mode == "fp32" else BF16_CHAIN["sample_1d_3step"]), err
+    # the public entry points take it too: sample() (explicit noise = eps / sigma_0) and the single denoiser call
+    noise = (g["eps"] / g["sigmas"][0].double()).cuda()
+    via_sample = edm.sample(tuple(g["eps"].shape), cond_sample=cs, cond=cond, noise=noise)
+    assert rel_l2(via_sample.double().cpu(), out.cpu()) < 1e-6
+    x = g["eps"].float().cuda()
+    sig = torch.full((x.shape[0],), 2.0, device="cuda")
+    D = edm(x, sig, cs, cond)
+    D0 = edm(x, sig, torch.zeros_like(cs), cond)
+    assert bool(torch.isfinite(D).all()) and rel_l2(D0, D) > 1e-4
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])

@@ -15,7 +15,8 @@ def _sd(module, seed):
     return seeded_state_dict(shapes_of(module), seed)
 
 
-@pytest.mark.parametrize("kind,name", [("latent2d", "unet_latent2d"), ("1d", "unet_1d"), ("pixel2d", "unet_pixel2d")])
+@pytest.mark.parametrize("kind,name", [("latent2d", "unet_latent2d"), ("1d", "unet_1d"), ("pixel2d", "unet_pixel2d"),
+                                       ("latent2d_film", "unet_film_2d"), ("1d_film", "unet_film_1d")])
 def test_unet_restatement_matches_reference(kind, name):
     import tqdne_b200 as tq
 
@@ -273,3 +274,21 @@ def test_kernel_fft_network_model_is_exact():
     L = np.arange(32)
     kk = np.stack([(L & 15) + 16 * p + 64 * (L >> 4) for p in range(4)], 1)
     assert np.abs(griffinlim_ref.kernel_model_fft128_dif(x) - X[kk]).max() < 1e-12
+
+
+@pytest.mark.parametrize("name,kind", [("edm_condsample_1d", "1d_condsample"), ("edm_condsample_2d", "latent2d_condsample")])
+def test_signal_conditioned_sampler_restatement_matches_reference(name, kind):
+    """LightningEDM.sample_deterministically with cond_sample (edm.py:109,171-196): the conditioning signal is concatenated
+    to the scaled state in front of the UNet at every call."""
+    import tqdne_b200 as tq
+
+    g = golden(name)
+    cfg = unet_cfg(kind)
+    sd = _sd(tq.LightningEDM(cfg, {}), g["seed"])
+    with torch.no_grad():
+        out = torch_ref.heun_sample(sd, cfg, g["eps"], g["sigmas"], g["cond"], cond_sample=g["cond_sample"])
+    assert out.dtype == torch.float64 and rel_l2(out, g["sample"]) < TOL
+    with torch.no_grad():   # the conditioning signal matters: zeros in its place give another sample
+        other = torch_ref.heun_sample(sd, cfg, g["eps"], g["sigmas"], g["cond"], cond_sample=torch.zeros_like(g["cond_sample"]))
+    assert rel_l2(other, g["sample"]) > 1e-3
+

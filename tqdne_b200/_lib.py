@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 16  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 17  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -69,6 +69,7 @@ class TqGnDesc(C.Structure):
         ("stats0", C.c_void_p), ("stats1", C.c_void_p),
         ("parts0", C.c_int32), ("parts1", C.c_int32),
         ("drop_seed", C.c_void_p), ("drop_p", C.c_float), ("drop_site", C.c_int32),
+        ("film", C.c_void_p), ("film_ld", C.c_int32),
     ]
 
 

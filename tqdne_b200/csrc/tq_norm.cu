@@ -38,7 +38,21 @@ struct GnParams {
     const unsigned long long* drop_seed;  // training only: dropout after the activation (nullptr = none)
     float drop_p;
     int drop_site;
+    const float* film;  // FiLM (use_scale_shift_norm): row n = [scale[Ct] | shift[Ct]] of sample n, or nullptr
+    int film_ld;
 };
+
+// y = GroupNorm(x) * (1 + scale[n][c]) + shift[n][c] (ResBlock with use_scale_shift_norm, tqdne/unet.py:135-139): folded into
+// the per-channel affine of this block's sample before the activation
+__device__ __forceinline__ void film8(const GnParams& p, int n, int c0, int Ct, float (&a)[8], float (&b)[8]) {
+    const float* row = p.film + (long long)n * p.film_ld + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float sc = 1.f + __ldcg(row + j), sh = __ldcg(row + Ct + j);
+        a[j] *= sc;
+        b[j] = fmaf(b[j], sc, sh);
+    }
+}
 
 template <typename T>
 __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
@@ -322,6 +336,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(c
     const bool halve = sizeof(T) == 2 && p.silu;   // see emit8
     if (v0.on) {
         affine8(gstat, cpg, v0.cvec0, g4, b4, a, b);
+        if (p.film) film8(p, n, v0.cvec0, Ct, a, b);
         if (halve) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { a[j] *= 0.5f; b[j] *= 0.5f; }
@@ -343,6 +358,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_kernel(c
             b4[0] = __ldg(reinterpret_cast<const float4*>(p.beta + v1.cvec0));
             b4[1] = __ldg(reinterpret_cast<const float4*>(p.beta + v1.cvec0) + 1);
             affine8(gstat, cpg, v1.cvec0, g4, b4, a, b);
+            if (p.film) film8(p, n, v1.cvec0, Ct, a, b);
             if (halve) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { a[j] *= 0.5f; b[j] *= 0.5f; }
@@ -450,6 +466,7 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d) {
     const bool drop = d.drop_seed != nullptr && d.drop_p > 0.f;
     TQ_CHECK(!drop || (!f32 && d.drop_p < 1.f), "groupnorm: fused dropout is built for bf16 and p < 1");
     p->drop_seed = reinterpret_cast<const unsigned long long*>(d.drop_seed); p->drop_p = d.drop_p; p->drop_site = d.drop_site;
+    p->film = d.film; p->film_ld = d.film_ld;
     ap.launch = [p, grid, f32, smem, drop](cudaStream_t s) -> int {
         if (f32) TQ_CUDA(launch_pdl(gn_apply_kernel<float, false>, grid, dim3(256), smem, s, *p));
         else if (drop) TQ_CUDA(launch_pdl(gn_apply_kernel<__nv_bfloat16, true>, grid, dim3(256), smem, s, *p));

@@ -173,16 +173,19 @@ class LightningEDM(LightningModule):
         `noise` (optional, engine extension): explicit unit-variance fp64 noise of the (latent) shape; when
         omitted, noise is drawn with the reference's draw order so that equal seeds give equal noise.
         """
-        if cond_sample is not None:
-            raise NotImplementedError("tqdne_b200: cond_sample (signal-conditioned sampling) is not used by any shipped "
-                                      "tqdne config and is not lowered yet")
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("tqdne_b200: LightningEDM.sample needs the module on a CUDA device (no CPU path)")
         with device_guard(dev):
-            return self._sample(tuple(shape), cond, noise, generator, dev)
+            return self._sample(tuple(shape), cond, noise, generator, dev, cond_sample)
 
-    def _sample(self, shape, cond, noise, generator, dev):
+    def _sample(self, shape, cond, noise, generator, dev, cond_sample=None):
+        if cond_sample is not None:
+            # signal-conditioned sampling: cond_sample rides along as extra UNet input channels, fixed over the calls
+            require_cuda(cond_sample, "cond_sample")
+            if self.autoencoder:   # reference: encoded BEFORE the dummy encode (edm.py:151-152), one randn_like draw
+                mean, log_std = torch.chunk(self.autoencoder.encoder(cond_sample), 2, dim=1)
+                cond_sample = mean + torch.randn(mean.shape, device=dev, dtype=mean.dtype, generator=generator) * torch.exp(log_std)
         if self.autoencoder:
             shape = self.latent_shape(shape)
             if noise is None and self.compat_rng:
@@ -213,7 +216,8 @@ class LightningEDM(LightningModule):
                 i1 = min(N, i0 + micro)
                 c = cond[i0:i1] if cond is not None else None
                 nz = [z[i0:i1] for z in churn] if churn is not None else None
-                outs.append(self._sample_chunk(eps[i0:i1].contiguous(), sigmas, c, noises=nz))
+                cs = cond_sample[i0:i1] if cond_sample is not None else None
+                outs.append(self._sample_chunk(eps[i0:i1].contiguous(), sigmas, c, noises=nz, cond_sample=cs))
             x = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)   # fp64 channels-last [N, P, C]
             C_ = shape[1]
             if not self.autoencoder:
@@ -228,16 +232,23 @@ class LightningEDM(LightningModule):
         is ordered after / before the caller's current stream."""
         return _SideStream(self)
 
-    def _sample_chunk(self, eps: torch.Tensor, sigmas: torch.Tensor, cond, noises=None) -> torch.Tensor:
+    def _sample_chunk(self, eps: torch.Tensor, sigmas: torch.Tensor, cond, noises=None, cond_sample=None) -> torch.Tensor:
         """Deterministic / stochastic Heun loop on one micro-batch; returns the fp64 channels-last state.
         `noises`: per-step unit normal fp64 tensors of eps.shape for the stochastic sampler (drawn here when None)."""
         lib = _lib.lib()
         n, C_ = eps.shape[0], eps.shape[1]
         spatial = tuple(eps.shape[2:])
         NP = n * math.prod(spatial)
-        plan = get_unet_plan(self.unet, n, spatial, uniform_t=True)
+        cc = 0
+        if cond_sample is not None:
+            cc = cond_sample.shape[1]
+            assert C_ + cc == self.unet.in_channels and tuple(cond_sample.shape[2:]) == spatial, \
+                "cond_sample must supply the UNet input channels beyond the sampled state, at the state's size"
+        plan = get_unet_plan(self.unet, n, spatial, uniform_t=True, cond_channels=cc)
         if self.use_cuda_graph:
             plan.plan.enable_graph(True)
+        if cond_sample is not None:
+            plan.set_cond_sample(cond_sample)
         if cond is not None:
             require_cuda(cond, "cond")
         assert (cond is not None) == (self.unet.cond_features is not None), \
@@ -331,12 +342,13 @@ class LightningEDM(LightningModule):
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     # reference API: the two samplers are also callable on their own with explicit eps (edm.py:171-230)
-    def _run_sampler(self, eps, sigmas, cond, deterministic: bool, noises=None):
+    def _run_sampler(self, eps, sigmas, cond, deterministic: bool, noises=None, cond_sample=None):
         keep = self.deterministic_sampling
         self.deterministic_sampling = deterministic
         try:
             with device_guard(eps.device), self._engine_stream():
-                x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond, noises=noises)
+                x = self._sample_chunk(eps.to(torch.float64).contiguous(), sigmas.to("cpu"), cond, noises=noises,
+                                       cond_sample=cond_sample)
                 out = nhwc_to_nchw(x, eps.shape[0], eps.shape[1], tuple(eps.shape[2:]), eps.shape[1], torch.float64)
         finally:
             self.deterministic_sampling = keep
@@ -345,19 +357,17 @@ class LightningEDM(LightningModule):
 
     @torch.no_grad()
     def sample_deterministically(self, eps, sigmas, cond_sample=None, cond=None):
-        assert cond_sample is None, "cond_sample is not lowered"
-        return self._run_sampler(eps, sigmas, cond, True)
+        return self._run_sampler(eps, sigmas, cond, True, cond_sample=cond_sample)
 
     @torch.no_grad()
     def sample_stochastically(self, eps, sigmas, cond_sample=None, cond=None, noises=None, generator=None):
         """reference: edm.py:198-230.  Engine extensions: `noises` = the per-step unit normal draws (one fp64 tensor of
         eps.shape per Heun step, what the reference takes from th.randn_like), else drawn from `generator`."""
-        assert cond_sample is None, "cond_sample is not lowered"
         if noises is None:
             noises = [torch.randn(eps.shape, device=eps.device, dtype=torch.float64, generator=generator)
                       for _ in range(self.num_sampling_steps)]
         assert len(noises) == self.num_sampling_steps, "one noise tensor per Heun step"
-        return self._run_sampler(eps, sigmas, cond, False, noises=noises)
+        return self._run_sampler(eps, sigmas, cond, False, noises=noises, cond_sample=cond_sample)
 
     @torch.no_grad()
     def evaluate(self, batch):

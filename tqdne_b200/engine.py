@@ -380,7 +380,9 @@ class Plan:
         return out
 
     def groupnorm(self, srcs: list[Act], gamma: torch.Tensor, beta: torch.Tensor, silu: bool, *, drop_seed: torch.Tensor | None = None,
-                  drop_p: float = 0.0, drop_site: int = 0) -> Act:
+                  drop_p: float = 0.0, drop_site: int = 0, film: torch.Tensor | None = None, film_ld: int = 0) -> Act:
+        """`film`: fp32 view whose row n holds [scale | shift] of sample n (2 * C values, row stride `film_ld`):
+        y = act(GroupNorm(x) * (1 + scale) + shift), ResBlock(use_scale_shift_norm=True)."""
         a0 = srcs[0]
         a1 = srcs[1] if len(srcs) > 1 else None
         Ct = a0.C + (a1.C if a1 else 0)
@@ -396,6 +398,10 @@ class Plan:
         d.eps = GN_EPS
         d.silu = 1 if silu else 0
         d.y = out.t.data_ptr()
+        if film is not None:
+            assert film.dtype == torch.float32 and film_ld >= 2 * Ct
+            d.film, d.film_ld = film.data_ptr(), film_ld
+            self.keep.append(film)
         if drop_seed is not None and drop_p > 0:      # training only: dropout fused behind the activation
             d.drop_seed, d.drop_p, d.drop_site = drop_seed.data_ptr(), drop_p, drop_site
             self.keep.append(drop_seed)

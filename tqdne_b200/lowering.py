@@ -75,9 +75,16 @@ class Lowerer:
         gn2, conv2 = blk.out_layers[0], blk.out_layers[3]
         h0 = plan.groupnorm(srcs, gn1.weight, gn1.bias, silu=True)
         e = emb[:, emb_off:] if emb is not None else None
-        h1 = self.conv(conv1, [h0], emb=e, emb_ld=emb_ld, stats=True)
-        plan.release(h0)
-        h2 = plan.groupnorm([h1], gn2.weight, gn2.bias, silu=True)
+        if getattr(blk, "use_scale_shift_norm", False):
+            # FiLM (unet.py:135-139): h = out_norm(conv1(h0)) * (1 + scale) + shift, (scale, shift) = the two halves of the
+            # block's 2 * C embedding columns -- folded into the second norm's per-sample affine, not added after conv1
+            h1 = self.conv(conv1, [h0], stats=True)
+            plan.release(h0)
+            h2 = plan.groupnorm([h1], gn2.weight, gn2.bias, silu=True, film=e, film_ld=emb_ld)
+        else:
+            h1 = self.conv(conv1, [h0], emb=e, emb_ld=emb_ld, stats=True)
+            plan.release(h0)
+            h2 = plan.groupnorm([h1], gn2.weight, gn2.bias, silu=True)
         plan.release(h1)
         skip = blk.skip_connection
         if isinstance(skip, nn.Identity):
@@ -127,7 +134,12 @@ class Lowerer:
 class UNetPlan:
     """One denoiser call for a fixed (batch, spatial size, dtype): F = UNet(xin, t, cond)."""
 
-    def __init__(self, model: U.UNetModel, N: int, spatial: tuple, act_dtype: torch.dtype, uniform_t: bool):
+    def __init__(self, model: U.UNetModel, N: int, spatial: tuple, act_dtype: torch.dtype, uniform_t: bool,
+                 cond_channels: int = 0):
+        """`cond_channels` > 0: the trailing input channels of the UNet are a conditioning signal that stays fixed over
+        the denoiser calls of a sample() (LightningEDM.forward: th.cat((sample_in, cond_sample), dim=1), edm.py:109).  It
+        lives in a tensor of its own (`xcond`) and the stem convolution reads it as a second concat segment, so the
+        sampler kernels keep writing a state-only `xin`."""
         dev = next(model.parameters()).device
         require_cuda(next(model.parameters()), "UNetModel parameters")
         self.N, self.spatial, self.act_dtype, self.uniform_t = N, tuple(spatial), act_dtype, uniform_t
@@ -141,8 +153,17 @@ class UNetPlan:
         f32 = dict(device=dev, dtype=torch.float32)
         rows_t = 1 if uniform_t else N
         self.t = torch.zeros(rows_t, **f32)
-        self.cin_pad = (model.in_channels + 63) // 64 * 64
+        assert 0 <= cond_channels < model.in_channels
+        self.cond_channels = cond_channels
+        state_channels = model.in_channels - cond_channels
+        self.cin_pad = (state_channels + 63) // 64 * 64
         self.xin = Act(torch.zeros(N * H * W * self.cin_pad, device=dev, dtype=act_dtype), N, H, W, self.cin_pad)
+        self.xcond = None
+        stem_srcs, stem_segments = [self.xin], [state_channels]
+        if cond_channels:
+            cpad = (cond_channels + 63) // 64 * 64
+            self.xcond = Act(torch.zeros(N * H * W * cpad, device=dev, dtype=act_dtype), N, H, W, cpad)
+            stem_srcs, stem_segments = [self.xin, self.xcond], [state_channels, cond_channels]
 
         # ---- conditioning prologue (constant over the NFE calls of one sample()): cond_mlp ----
         self.cond = None
@@ -203,8 +224,8 @@ class UNetPlan:
                         plan.release(cur[0])
                 elif isinstance(layer, B.Upsample):
                     o = low.upsample(layer, cur[0], fi)
-                elif isinstance(layer, (nn.Conv1d, nn.Conv2d)):
-                    o = low.conv(layer, cur, segments=[layer.weight.shape[1]], stats=True)
+                elif isinstance(layer, (nn.Conv1d, nn.Conv2d)):   # the stem
+                    o = low.conv(layer, cur, segments=stem_segments, stats=True)
                 else:
                     raise NotImplementedError(f"tqdne_b200: cannot lower {type(layer).__name__}")
                 cur = [o]
@@ -215,7 +236,7 @@ class UNetPlan:
         hs: list[Act] = []
         h = None
         for i, blk in enumerate(model.input_blocks):
-            h = run_seq(blk, [self.xin] if i == 0 else [h], free_inputs=False)
+            h = run_seq(blk, stem_srcs if i == 0 else [h], free_inputs=False)
             hs.append(h)
         h = run_seq(model.middle_block, [h], free_inputs=False)
         for blk in model.output_blocks:
@@ -238,6 +259,11 @@ class UNetPlan:
             self.cond.copy_(cond.to(torch.float32))
             self.cond_plan.run()
 
+    def set_cond_sample(self, cond_sample: torch.Tensor) -> None:
+        """[N, cond_channels, ...] -> the channels-last second stem source (once per sample(), not per call)."""
+        assert self.xcond is not None and cond_sample.shape[1] == self.cond_channels
+        self.xcond.t.copy_(nchw_to_nhwc(cond_sample.to(torch.float32), self.act_dtype, self.xcond.C).view(-1))
+
     def set_t(self, t: torch.Tensor) -> None:
         self.t.copy_(t.to(torch.float32).reshape(-1)[: self.t.numel()])
 
@@ -256,7 +282,8 @@ def _act_dtype_of(model: nn.Module) -> torch.dtype:
     return dt
 
 
-def get_unet_plan(model: U.UNetModel, N: int, spatial: tuple, uniform_t: bool, act_dtype: torch.dtype | None = None) -> UNetPlan:
+def get_unet_plan(model: U.UNetModel, N: int, spatial: tuple, uniform_t: bool, act_dtype: torch.dtype | None = None,
+                  cond_channels: int = 0) -> UNetPlan:
     c = _cache(model)
     stamp = _param_stamp(model)
     if c.get("stamp") != stamp:
@@ -264,10 +291,10 @@ def get_unet_plan(model: U.UNetModel, N: int, spatial: tuple, uniform_t: bool, a
         c = _cache(model)
         c["stamp"] = stamp
     act_dtype = act_dtype or getattr(model, "engine_dtype", None) or _act_dtype_of(model)
-    key = ("unet", N, tuple(spatial), act_dtype, uniform_t)
+    key = ("unet", N, tuple(spatial), act_dtype, uniform_t, cond_channels)
     p = c["plans"].get(key)
     if p is None:
-        p = UNetPlan(model, N, spatial, act_dtype, uniform_t)
+        p = UNetPlan(model, N, spatial, act_dtype, uniform_t, cond_channels)
         c["plans"][key] = p
     return p
 

@@ -137,6 +137,9 @@ class TrainStep1D:
         self.lib = _lib.lib()
         self.lr0, self.max_steps, self.eta_min, self.ema_decay, self.betas, self.eps = lr, max_steps, eta_min, ema_decay, betas, eps
         first_res = next(m for m in model.modules() if isinstance(m, U.ResBlock))
+        if first_res.use_scale_shift_norm:
+            raise NotImplementedError("tqdne_b200: the training tape covers the shipped ResBlock (embedding added after conv1); "
+                                      "use_scale_shift_norm models sample on the engine and train with the reference package")
         self.p_drop = float(first_res.out_layers[2].p) if dropout is None else float(dropout)
         self.sigma_data = float(edm.edm.sigma_data)
         # dropout inside the GroupNorm kernels of both passes (default) or as separate multiply passes (A/B switch)

@@ -29,13 +29,11 @@ class ResBlock(TimestepBlock):
                  use_scale_shift_norm=False, dims=2, use_checkpoint=False):
         super().__init__()
         out_channels = out_channels or channels
-        if use_scale_shift_norm:
-            raise NotImplementedError("tqdne_b200: use_scale_shift_norm (FiLM) is off in every shipped tqdne config "
-                                      "and is not lowered")
         self.use_conv, self.use_checkpoint, self.use_scale_shift_norm = use_conv, use_checkpoint, use_scale_shift_norm
         self.in_layers = nn.Sequential(
             normalization(channels), nn.SiLU(), conv_nd(dims, channels, out_channels, kernel_size, padding="same"))
-        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, out_channels))
+        self.emb_layers = nn.Sequential(
+            nn.SiLU(), nn.Linear(emb_channels, 2 * out_channels if use_scale_shift_norm else out_channels))
         self.out_layers = nn.Sequential(
             normalization(out_channels), nn.SiLU(), nn.Dropout(p=dropout),
             zero_module(conv_nd(dims, out_channels, out_channels, kernel_size, padding="same")))
