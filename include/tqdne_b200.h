@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 17
+#define TQ_ABI_VERSION 18
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -149,10 +149,12 @@ int64_t tq_groupnorm_ws_floats(const tq_gn_desc* d);
 /* ---- attention core -------------------------------------------------------------------------- *
  * Replaces: QKVAttention.forward (tqdne/blocks.py:156-190).  qkv:[N,T,3*heads*d] channels-last
  * with channel = third*(heads*d) + head*d + c, out:[N,T,heads*d];
- * w = softmax_fp32((q*s)^T (k*s)), s = d^-1/4, out = w v.                                         */
+ * w = softmax_fp32((q*s)^T (k*s)), s = d^-1/4, out = w v.
+ * `causal` != 0: key s > query t is masked out before the softmax (use_causal_mask, blocks.py:181-186; FFMA kernels). */
 typedef struct {
     int32_t dtype; int32_t N, T, heads, d;
     const void* qkv; void* out;
+    int32_t causal;
 } tq_attn_desc;
 int tq_plan_add_attention(tq_plan* p, const tq_attn_desc* d);
 

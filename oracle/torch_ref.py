@@ -46,8 +46,9 @@ def _res_block(sd, p, x, emb):
     return x + h
 
 
-def _attention(sd, p, x, heads):
-    """AttentionBlock._forward + QKVAttention.forward (tqdne/blocks.py:139-145,156-190)."""
+def _attention(sd, p, x, heads, causal=False):
+    """AttentionBlock._forward + QKVAttention.forward (tqdne/blocks.py:139-145,156-190); `causal` = use_causal_mask
+    (:181-186)."""
     b, c = x.shape[:2]
     spatial = x.shape[2:]
     qkv = _conv(_gn(x, sd[p + "norm.weight"], sd[p + "norm.bias"]), sd[p + "qkv.weight"], sd[p + "qkv.bias"])
@@ -58,7 +59,10 @@ def _attention(sd, p, x, heads):
     s = 1 / math.sqrt(math.sqrt(d))
     q = (q * s).reshape(b * heads, d, t)
     k = (k * s).reshape(b * heads, d, t)
-    w = torch.softmax(torch.einsum("bct,bcs->bts", q, k).float(), dim=-1).to(q.dtype)
+    w = torch.einsum("bct,bcs->bts", q, k)
+    if causal:
+        w = w.masked_fill(torch.tril(torch.ones(t, t)).unsqueeze(0) == 0, -torch.inf)
+    w = torch.softmax(w.float(), dim=-1).to(q.dtype)
     a = torch.einsum("bts,bcs->bct", w, v.reshape(b * heads, d, t)).reshape(b, c, *spatial)
     return x + _conv(a, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
 
@@ -72,6 +76,7 @@ def _upsample(sd, p, x):
 def unet_forward(sd: dict, cfg: dict, x, timesteps, cond=None, prefix: str = ""):
     """UNetModel.forward (tqdne/unet.py:360-398) with the topology of UNetModel.__init__ (unet.py:188-358)."""
     heads = cfg.get("num_heads", 1)
+    causal = bool(cfg.get("use_causal_mask", False)) and not cfg.get("flash_attention", True)   # blocks.py:136-139
     mult = cfg.get("channel_mult", (1, 2, 4, 8))
     nres = cfg["num_res_blocks"]
     att = cfg.get("attention_resolutions", (8, 16, 32))
@@ -95,7 +100,7 @@ def unet_forward(sd: dict, cfg: dict, x, timesteps, cond=None, prefix: str = "")
         for _ in range(nres):
             h = _res_block(sub, f"input_blocks.{idx}.0.", h, emb)
             if ds in att:
-                h = _attention(sub, f"input_blocks.{idx}.1.", h, heads)
+                h = _attention(sub, f"input_blocks.{idx}.1.", h, heads, causal)
             hs.append(h)
             idx += 1
         if level != len(mult) - 1:
@@ -104,7 +109,7 @@ def unet_forward(sd: dict, cfg: dict, x, timesteps, cond=None, prefix: str = "")
             idx += 1
             ds *= 2
     h = _res_block(sub, "middle_block.0.", h, emb)
-    h = _attention(sub, "middle_block.1.", h, heads)
+    h = _attention(sub, "middle_block.1.", h, heads, causal)
     h = _res_block(sub, "middle_block.2.", h, emb)
     idx = 0
     for level in reversed(range(len(mult))):
@@ -113,7 +118,7 @@ def unet_forward(sd: dict, cfg: dict, x, timesteps, cond=None, prefix: str = "")
             h = _res_block(sub, f"output_blocks.{idx}.0.", h, emb)
             j = 1
             if ds in att:
-                h = _attention(sub, f"output_blocks.{idx}.{j}.", h, heads)
+                h = _attention(sub, f"output_blocks.{idx}.{j}.", h, heads, causal)
                 j += 1
             if level and i == nres:
                 h = _upsample(sub, f"output_blocks.{idx}.{j}.", h)

@@ -30,7 +30,10 @@ def unet_cfg(kind):
             "1d_condsample": a.get_1d_unet_config(CFG, 12, 6), "latent2d_condsample": a.get_2d_unet_config(CFG, 16, 8),
             # FiLM ResBlocks (use_scale_shift_norm, unet.py:135-139)
             "latent2d_film": dict(a.get_2d_unet_config(CFG, 8, 8), use_scale_shift_norm=True),
-            "1d_film": dict(a.get_1d_unet_config(CFG, 6, 6), use_scale_shift_norm=True)}[kind]
+            "1d_film": dict(a.get_1d_unet_config(CFG, 6, 6), use_scale_shift_norm=True),
+            # causal attention mask (blocks.py:181-186)
+            "1d_causal": dict(a.get_1d_unet_config(CFG, 6, 6), use_causal_mask=True),
+            "latent2d_causal": dict(a.get_2d_unet_config(CFG, 8, 8), use_causal_mask=True)}[kind]
 
 
 def seeded(module, seed):

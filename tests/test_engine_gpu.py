@@ -38,7 +38,8 @@ def _unet(kind, seed, mode):
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("kind,name", [("latent2d", "unet_latent2d"), ("1d", "unet_1d"), ("pixel2d", "unet_pixel2d"),
-                                       ("latent2d_film", "unet_film_2d"), ("1d_film", "unet_film_1d")])
+                                       ("latent2d_film", "unet_film_2d"), ("1d_film", "unet_film_1d"),
+                                       ("1d_causal", "unet_causal_1d"), ("latent2d_causal", "unet_causal_2d")])
 def test_unet_forward_matches_reference_golden(kind, name, mode):
     g = golden(name)
     net = _unet(kind, g["seed"], mode)

@@ -381,6 +381,34 @@ def test_attention_matches_reference_formula(N, T, heads, d, dtype):
     assert rel_l2(got, a) < (4e-3 if dtype == torch.bfloat16 else 3e-6)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("N,T,heads,d", [(2, 16, 2, 128), (1, 27, 2, 64), (2, 100, 2, 64), (1, 508, 2, 64), (1, 130, 1, 32)])
+def test_causal_attention_matches_reference_formula(N, T, heads, d, dtype):
+    """use_causal_mask (tqdne/blocks.py:181-186): scores of keys behind the query are filled with -inf before the fp32
+    softmax.  Off in every shipped config; both modes run it on the FFMA kernels (tq_attn.cu)."""
+    from tqdne_b200.engine import Act
+
+    g = torch.Generator(device="cuda").manual_seed(100 + T)
+    C = heads * d
+    qkv = torch.randn(N, T, 3 * C, device="cuda", generator=g)
+    plan = _plan(dtype)
+    out = plan.attention(Act(qkv.to(dtype).reshape(-1), N, 1, T, 3 * C), heads, causal=True)
+    assert "causal" in plan.op_names()[-1] and "attention_tc" not in plan.op_names()[-1]
+    plan.run()
+    torch.cuda.synchronize()
+    x = _rt(qkv, dtype).permute(0, 2, 1)
+    q, k, v = x.chunk(3, dim=1)
+    s = 1 / math.sqrt(math.sqrt(d))
+    w = torch.einsum("bct,bcs->bts", (q * s).reshape(N * heads, d, T), (k * s).reshape(N * heads, d, T))
+    mask = torch.tril(torch.ones(T, T, device="cuda")).unsqueeze(0).expand(w.size(0), -1, -1)
+    w = torch.softmax(w.masked_fill(mask == 0, -torch.inf).float(), dim=-1)
+    a = torch.einsum("bts,bcs->bct", w, v.reshape(N * heads, d, T)).reshape(N, C, T)
+    got = out.t.float().reshape(N, T, C).permute(0, 2, 1)
+    assert rel_l2(got, a) < (4e-3 if dtype == torch.bfloat16 else 3e-6)
+    # the first query sees only itself: its output is v[0]
+    assert rel_l2(got[:, :, 0], v.reshape(N, C, T)[:, :, 0]) < (4e-3 if dtype == torch.bfloat16 else 1e-6)
+
+
 def test_embedding_mlp_kernels():
     plan = _plan(torch.bfloat16)
     g = torch.Generator(device="cuda").manual_seed(1)

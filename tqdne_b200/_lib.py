@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 17  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 18  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -78,6 +78,7 @@ class TqAttnDesc(C.Structure):
         ("dtype", C.c_int32),
         ("N", C.c_int32), ("T", C.c_int32), ("heads", C.c_int32), ("d", C.c_int32),
         ("qkv", C.c_void_p), ("out", C.c_void_p),
+        ("causal", C.c_int32),
     ]
 
 

@@ -49,8 +49,6 @@ class QKVAttention(EngineOnly):
 
     def __init__(self, n_heads, use_causal_mask=False):
         super().__init__()
-        if use_causal_mask:
-            raise NotImplementedError("tqdne_b200: causal attention mask is not lowered (off in all shipped configs)")
         self.n_heads = n_heads
         self.use_causal_mask = use_causal_mask
 
@@ -65,9 +63,10 @@ class AttentionBlock(EngineOnly):
         self.use_checkpoint = use_checkpoint
         self.norm = normalization(channels)
         self.qkv = conv_nd(dims, channels, channels * 3, 1)
-        # the reference's flash_attention=True branch needs flash-attn v1 and is dead code;
-        # both settings lower to the same kernel here
-        self.attention = QKVAttention(num_heads, use_causal_mask=use_causal_mask)
+        # the reference's flash_attention=True branch needs flash-attn v1 and is dead code; both settings
+        # lower to the same kernels here.  Like the reference, only the flash_attention=False core takes the causal mask
+        # (blocks.py:136-139: QKVFlashAttention is built without it).
+        self.attention = QKVAttention(num_heads, use_causal_mask=use_causal_mask and not flash_attention)
         self.proj_out = zero_module(conv_nd(dims, channels, channels, 1))
 
 

@@ -1,7 +1,8 @@
 // tq_attn.cu -- attention core, channels-last, fp32 math with online softmax.
 // Reference: QKVAttention.forward (tqdne/blocks.py:156-190): q,k,v = qkv.chunk(3, dim=1), heads split
-// inside each third, w = softmax_fp32((q*s)^T (k*s)) with s = d^-1/4, a = w v.  No mask (use_causal_mask is
-// off in every shipped config, tqdne/architectures.py:35,76).
+// inside each third, w = softmax_fp32((q*s)^T (k*s)) with s = d^-1/4, a = w v.  The optional causal mask
+// (use_causal_mask, blocks.py:181-186: key s > query t -> -inf; off in every shipped config) is handled by these FFMA
+// kernels only: a causal attention never takes the tensor-core kernels of tq_attn_sm100.cu.
 //
 // One CTA = (sample, head, 16 queries); 4 warps x 4 queries.  K/V are staged in shared memory in
 // 64-key blocks (row pitch d+1 floats: conflict-free both for "lane = key" score dots and
@@ -24,6 +25,7 @@ struct AttnParams {
     const void* qkv;
     void* out;
     int N, T, heads, d;
+    int causal;
 };
 
 __device__ __forceinline__ float ld_f(const float* p) { return __ldg(p); }
@@ -66,7 +68,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
         for (int j = 0; j < DPL; ++j) acc[i][j] = 0.f;
     }
 
-    for (int k0 = 0; k0 < p.T; k0 += KBLK) {
+    // causal: keys beyond the last query of this CTA contribute nothing
+    const int k_end = p.causal ? min(p.T, qb * QB + QB) : p.T;
+    for (int k0 = 0; k0 < k_end; k0 += KBLK) {
         __syncthreads();
         for (int i = tid; i < KBLK * D; i += 128) {
             const int s = i / D, c = i % D;
@@ -83,6 +87,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
 #pragma unroll
         for (int qi = 0; qi < 4; ++qi) {
             const float* q = Qs + (warp * 4 + qi) * D;
+            const int k_lim = p.causal ? min(p.T, qb * QB + warp * 4 + qi + 1) : p.T;   // keys [0, k_lim) are visible
             float sc[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
                 const float* kr = Ks + s * PITCH;
 #pragma unroll 8
                 for (int c = 0; c < D; ++c) a = fmaf(q[c], kr[c], a);
-                sc[j] = (k0 + s < p.T) ? a : -INFINITY;
+                sc[j] = (k0 + s < k_lim) ? a : -INFINITY;
             }
             float bm = fmaxf(sc[0], sc[1]);
 #pragma unroll
@@ -210,11 +215,12 @@ __global__ void __launch_bounds__(128) attention_small_kernel(const AttnParams p
     __syncthreads();
     if (tid < Tn) {
         float* pr = Ps + tid * (Tp + 1);
+        const int k_lim = p.causal ? tid + 1 : Tn;   // causal: query tid sees keys 0 .. tid
         float m = -INFINITY;
-        for (int k = 0; k < Tn; ++k) m = fmaxf(m, pr[k]);
+        for (int k = 0; k < k_lim; ++k) m = fmaxf(m, pr[k]);
         float l = 0.f;
         for (int k = 0; k < Tn; ++k) {
-            const float e = expf(pr[k] - m);
+            const float e = k < k_lim ? expf(pr[k] - m) : 0.f;
             pr[k] = e;
             l += e;
         }
@@ -273,15 +279,16 @@ int build_attention(std::vector<Op>& ops, const tq_attn_desc& d) {
     {
         // T > 32 in bf16 runs on the tensor cores; TQ_ATTN_SIMT=1 keeps the FFMA kernel (A/B and cross-check)
         const char* simt = getenv("TQ_ATTN_SIMT");
-        if (attention_tc_supported(d) && !(simt && simt[0] == '1')) return build_attention_tc(ops, d);
+        if (!d.causal && attention_tc_supported(d) && !(simt && simt[0] == '1')) return build_attention_tc(ops, d);
     }
     auto p = std::make_shared<AttnParams>();
     p->qkv = d.qkv; p->out = d.out; p->N = d.N; p->T = d.T; p->heads = d.heads; p->d = d.d;
+    p->causal = d.causal ? 1 : 0;
     const bool f32 = d.dtype == TQ_F32;
     const int dd = d.d;
     Op op;
     char nm[64];
-    snprintf(nm, sizeof nm, "attention<%s,d=%d> T=%d", f32 ? "f32" : "bf16", dd, d.T);
+    snprintf(nm, sizeof nm, "attention<%s,d=%d> T=%d%s", f32 ? "f32" : "bf16", dd, d.T, d.causal ? " causal" : "");
     op.name = nm;
     op.launch = [p, f32, dd](cudaStream_t st) -> int {
         if (f32) {

@@ -431,13 +431,14 @@ class Plan:
         self.keep += [g, b, a0.t, out.t] + ([a1.t] if a1 else [])
         return out
 
-    def attention(self, qkv: Act, heads: int) -> Act:
+    def attention(self, qkv: Act, heads: int, causal: bool = False) -> Act:
         Cc = qkv.C // 3
         out = self.new_act(qkv.N, qkv.H, qkv.W, Cc)
         d = _lib.TqAttnDesc()
         d.dtype = self.tq_dtype
         d.N, d.T, d.heads, d.d = qkv.N, qkv.P, heads, Cc // heads
         d.qkv, d.out = qkv.t.data_ptr(), out.t.data_ptr()
+        d.causal = 1 if causal else 0
         _lib.check(self.lib.tq_plan_add_attention(self.h, C.byref(d)), "plan_add_attention")
         self.op_meta.append(("attention", 4 * qkv.N * qkv.P * qkv.P * Cc, 0))
         self.keep += [qkv.t, out.t]

@@ -107,7 +107,7 @@ class Lowerer:
         qkv = self.conv(blk.qkv, [g])
         plan.release(g)
         heads = blk.num_heads
-        a = plan.attention(qkv, heads)
+        a = plan.attention(qkv, heads, causal=bool(getattr(blk.attention, "use_causal_mask", False)))
         self.flops += 4 * x.N * x.P * x.P * x.C  # QK^T and PV, 2*MAC each
         plan.release(qkv)
         out = self.conv(blk.proj_out, [a], residual=x, stats=True)

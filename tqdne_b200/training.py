@@ -284,6 +284,9 @@ class TrainStep1D:
             return out
 
         def attention(blk, x: Act) -> Act:
+            if blk.attention.use_causal_mask:
+                raise NotImplementedError("tqdne_b200: the attention backward has no causal mask; train this model with "
+                                          "the reference package")
             g = self._gn(blk.norm, [x], False)
             self.nodes.append(("gn", blk.norm, [x], g, False))
             qkv = self._conv(blk.qkv, [g], [g.C], stats=False)
