@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 18
+#define TQ_ABI_VERSION 19
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -176,6 +176,11 @@ typedef struct {
 int tq_plan_add_linear(tq_plan* p, const tq_linear_desc* d);
 /* feat[M, 2*half] = [sin(2*pi*t*W), cos(2*pi*t*W)],  t:[M] read from device                      */
 int tq_plan_add_fourier(tq_plan* p, const float* t, const float* W, int32_t M, int32_t half, float* feat);
+/* The conv-less resamplers of conv_resample=False models, channels-last x:[N,H,W,C] (H = 1 for 1-D), C % 8 == 0:
+ * mode 0 = nn.AvgPool{1,2}d(kernel 2, stride 2) (tqdne/blocks.py:104) -> y:[N,H/2,W/2,C] (odd sizes floor, like torch);
+ * mode 1 = F.interpolate(scale_factor=2, mode="nearest") (blocks.py:59-62) -> y:[N,2H,2W,C].                        */
+int tq_plan_add_resample2(tq_plan* p, int32_t dtype, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                          int32_t mode);
 /* y[N, C] = mean over the P positions of x[N, P, ld] (fp32 channels-last, first C channels).
  * Replaces: th.mean(h, dim=spatial) in LithningClassifier.embed (tqdne/classifier.py:51-53).      */
 int tq_plan_add_spatial_mean(tq_plan* p, const float* x, int32_t N, int32_t P, int32_t C, int32_t ld, float* y);

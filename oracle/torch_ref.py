@@ -68,9 +68,19 @@ def _attention(sd, p, x, heads, causal=False):
 
 
 def _upsample(sd, p, x):
-    """Upsample.forward: nearest x2 then conv (tqdne/blocks.py:59-65)."""
+    """Upsample.forward: nearest x2 then conv -- no conv when the layer was built with use_conv=False, i.e. has no
+    parameters (tqdne/blocks.py:59-65)."""
     x = F.interpolate(x, scale_factor=2, mode="nearest")
+    if p + "conv.weight" not in sd:
+        return x
     return _conv(x, sd[p + "conv.weight"], sd[p + "conv.bias"])
+
+
+def _downsample(sd, p, x):
+    """Downsample.forward: stride-2 conv, or the parameter-free average pool of use_conv=False (tqdne/blocks.py:93-108)."""
+    if p + "op.weight" not in sd:
+        return (F.avg_pool1d if x.dim() == 3 else F.avg_pool2d)(x, 2, 2)
+    return _conv(x, sd[p + "op.weight"], sd[p + "op.bias"], stride=2)
 
 
 def unet_forward(sd: dict, cfg: dict, x, timesteps, cond=None, prefix: str = ""):
@@ -89,6 +99,9 @@ def unet_forward(sd: dict, cfg: dict, x, timesteps, cond=None, prefix: str = "")
     emb = F.linear(F.silu(F.linear(emb, g("time_mlp.0.weight"), g("time_mlp.0.bias"))), g("time_mlp.2.weight"),
                    g("time_mlp.2.bias"))
     if cfg.get("cond_features") is not None:
+        if cfg.get("cond_emb_scale") is not None:   # unet.py:386-387 (runs for one conditioning feature only, blocks.py:23)
+            hc = cond[:, None] * g("cond_embed.W")[None, :] * 2 * torch.pi
+            cond = torch.cat([torch.sin(hc), torch.cos(hc)], dim=-1).view(cond.shape[0], -1)
         emb = emb + F.linear(F.silu(F.linear(cond, g("cond_mlp.0.weight"), g("cond_mlp.0.bias"))),
                              g("cond_mlp.2.weight"), g("cond_mlp.2.bias"))
 
@@ -104,7 +117,7 @@ def unet_forward(sd: dict, cfg: dict, x, timesteps, cond=None, prefix: str = "")
             hs.append(h)
             idx += 1
         if level != len(mult) - 1:
-            h = _conv(h, g(f"input_blocks.{idx}.0.op.weight"), g(f"input_blocks.{idx}.0.op.bias"), stride=2)
+            h = _downsample(sub, f"input_blocks.{idx}.0.", h)
             hs.append(h)
             idx += 1
             ds *= 2

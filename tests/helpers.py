@@ -33,7 +33,12 @@ def unet_cfg(kind):
             "1d_film": dict(a.get_1d_unet_config(CFG, 6, 6), use_scale_shift_norm=True),
             # causal attention mask (blocks.py:181-186)
             "1d_causal": dict(a.get_1d_unet_config(CFG, 6, 6), use_causal_mask=True),
-            "latent2d_causal": dict(a.get_2d_unet_config(CFG, 8, 8), use_causal_mask=True)}[kind]
+            "latent2d_causal": dict(a.get_2d_unet_config(CFG, 8, 8), use_causal_mask=True),
+            # conv_resample=False: average-pool Downsample, conv-less nearest Upsample (blocks.py:59-64,104)
+            "1d_pool": dict(a.get_1d_unet_config(CFG, 6, 6), conv_resample=False),
+            "latent2d_pool": dict(a.get_2d_unet_config(CFG, 8, 8), conv_resample=False),
+            # Fourier-embedded conditioning, one feature (unet.py:217-219,386-387)
+            "1d_condembed": dict(a.get_1d_unet_config(CFG, 6, 6), cond_features=1, cond_emb_scale=0.5)}[kind]
 
 
 def seeded(module, seed):

@@ -39,7 +39,9 @@ def _unet(kind, seed, mode):
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("kind,name", [("latent2d", "unet_latent2d"), ("1d", "unet_1d"), ("pixel2d", "unet_pixel2d"),
                                        ("latent2d_film", "unet_film_2d"), ("1d_film", "unet_film_1d"),
-                                       ("1d_causal", "unet_causal_1d"), ("latent2d_causal", "unet_causal_2d")])
+                                       ("1d_causal", "unet_causal_1d"), ("latent2d_causal", "unet_causal_2d"),
+                                       ("1d_pool", "unet_poolresample_1d"), ("latent2d_pool", "unet_poolresample_2d"),
+                                       ("1d_condembed", "unet_condembed_1d")])
 def test_unet_forward_matches_reference_golden(kind, name, mode):
     g = golden(name)
     net = _unet(kind, g["seed"], mode)

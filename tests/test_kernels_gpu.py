@@ -409,6 +409,32 @@ def test_causal_attention_matches_reference_formula(N, T, heads, d, dtype):
     assert rel_l2(got[:, :, 0], v.reshape(N, C, T)[:, :, 0]) < (4e-3 if dtype == torch.bfloat16 else 1e-6)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("N,H,W,C", [(2, 1, 64, 64), (3, 1, 37, 128), (2, 16, 16, 64), (1, 7, 10, 72)])
+def test_conv_less_resamplers_match_torch(N, H, W, C, dtype):
+    """conv_resample=False: nn.AvgPool{1,2}d(2, 2) (odd sizes floor) and F.interpolate(scale_factor=2, "nearest")."""
+    from tqdne_b200.engine import Act
+
+    g = torch.Generator(device="cuda").manual_seed(N * 100 + W)
+    x = _rt(torch.randn(N, H, W, C, device="cuda", generator=g), dtype)
+    plan = _plan(dtype)
+    xa = Act(x.to(dtype).reshape(-1), N, H, W, C)
+    down, up = plan.resample2(xa, "avg_pool"), plan.resample2(xa, "nearest")
+    plan.run()
+    torch.cuda.synchronize()
+    xn = x.permute(0, 3, 1, 2)   # [N, C, H, W]
+    if H == 1:
+        rd = F.avg_pool1d(xn[:, :, 0], 2, 2)[:, :, None]
+        ru = F.interpolate(xn[:, :, 0], scale_factor=2, mode="nearest")[:, :, None]
+    else:
+        rd, ru = F.avg_pool2d(xn, 2, 2), F.interpolate(xn, scale_factor=2, mode="nearest")
+    assert (down.H, down.W) == tuple(rd.shape[2:]) and (up.H, up.W) == tuple(ru.shape[2:])
+    got_d = down.t.float().reshape(N, down.H, down.W, C).permute(0, 3, 1, 2)
+    got_u = up.t.float().reshape(N, up.H, up.W, C).permute(0, 3, 1, 2)
+    assert torch.equal(got_u, ru)
+    assert rel_l2(got_d, rd) < (3e-3 if dtype == torch.bfloat16 else 1e-7)
+
+
 def test_embedding_mlp_kernels():
     plan = _plan(torch.bfloat16)
     g = torch.Generator(device="cuda").manual_seed(1)

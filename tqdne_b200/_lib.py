@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 18  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 19  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -131,6 +131,7 @@ SIGNATURES = {
     "tq_plan_add_attention": (C.c_int, [_VP, C.POINTER(TqAttnDesc)]),
     "tq_plan_add_linear": (C.c_int, [_VP, C.POINTER(TqLinearDesc)]),
     "tq_plan_add_fourier": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
+    "tq_plan_add_resample2": (C.c_int, [_VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, _I32]),
     "tq_plan_add_spatial_mean": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     "tq_gn_silu_backward": (C.c_int, [C.POINTER(TqGnBwdDesc), _VP]),
     "tq_attention_backward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),

@@ -38,10 +38,11 @@ class Downsample(EngineOnly):
         super().__init__()
         self.channels, self.out_channels = channels, out_channels or channels
         self.use_conv, self.dims = use_conv, dims
-        if not use_conv:
-            raise NotImplementedError("tqdne_b200: average-pool Downsample (conv_resample=False) is not lowered; "
-                                      "every shipped tqdne config uses conv_resample=True")
-        self.op = conv_nd(dims, self.channels, self.out_channels, kernel_size, stride=2, padding=kernel_size // 2)
+        if use_conv:
+            self.op = conv_nd(dims, self.channels, self.out_channels, kernel_size, stride=2, padding=kernel_size // 2)
+        else:   # conv_resample=False: parameter-free average pool (reference: blocks.py:102-104)
+            assert self.channels == self.out_channels
+            self.op = nn.AvgPool1d(2, 2) if dims == 1 else nn.AvgPool2d(2, 2)
 
 
 class QKVAttention(EngineOnly):

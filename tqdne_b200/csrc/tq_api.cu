@@ -193,6 +193,11 @@ int tq_plan_add_fourier(tq_plan* p, const float* t, const float* W, int32_t M, i
     drop_graph(p);
     return build_fourier(p->ops, t, W, M, half, feat);
 }
+int tq_plan_add_resample2(tq_plan* p, int32_t dtype, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t mode) {
+    TQ_CHECK(p != nullptr, "null argument");
+    drop_graph(p);
+    return build_resample2(p->ops, dtype, x, y, N, H, W, C, mode);
+}
 int tq_plan_add_spatial_mean(tq_plan* p, const float* x, int32_t N, int32_t P, int32_t C, int32_t ld, float* y) {
     TQ_CHECK(p != nullptr, "null argument");
     drop_graph(p);

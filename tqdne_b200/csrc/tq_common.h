@@ -143,6 +143,7 @@ bool attention_tc_supported(const tq_attn_desc& d);
 int build_attention_tc(std::vector<Op>& ops, const tq_attn_desc& d);
 int build_linear(std::vector<Op>& ops, const tq_linear_desc& d);
 int build_fourier(std::vector<Op>& ops, const float* t, const float* W, int M, int half, float* feat);
+int build_resample2(std::vector<Op>& ops, int dtype, const void* x, void* y, int N, int H, int W, int C, int mode);
 int build_spatial_mean(std::vector<Op>& ops, const float* x, int N, int P, int C, int ld, float* y);
 
 }  // namespace tq

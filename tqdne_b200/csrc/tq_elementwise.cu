@@ -368,6 +368,87 @@ int build_fourier(std::vector<Op>& ops, const float* t, const float* W, int M, i
     return 0;
 }
 
+// conv_resample=False resamplers on channels-last tensors (tqdne/blocks.py:59-64: F.interpolate(scale_factor=2, "nearest");
+// blocks.py:104: AvgPool{1,2}d(kernel 2, stride 2)).  One thread per 8 channels of an OUTPUT position; fp32 averaging.
+template <typename T>
+__device__ __forceinline__ void load_vec8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load_vec8<float>(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load_vec8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        v[2 * k] = __low2float(b2);
+        v[2 * k + 1] = __high2float(b2);
+    }
+}
+// mode 0: average pool (Ho = H / 2 unless H == 1, Wo = W / 2), mode 1: nearest x2 (Ho = 2 H unless H == 1, Wo = 2 W)
+template <typename T>
+__global__ void __launch_bounds__(256) resample2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C,
+                                                        int Ho, int Wo, int mode) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int cv = C >> 3;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)N * Ho * Wo * cv) return;
+    const int c0 = (int)(i % cv) * 8;
+    long long r = i / cv;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float o[8];
+    if (mode == 1) {
+        const int yi = H == 1 ? 0 : yo >> 1, xi = xo >> 1;
+        load_vec8<T>(x + (((long long)n * H + yi) * W + xi) * C + c0, o);
+    } else {
+        const int ny = H == 1 ? 1 : 2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        for (int dy = 0; dy < ny; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                float v[8];
+                load_vec8<T>(x + (((long long)n * H + (ny * yo + dy)) * W + (2 * xo + dx)) * C + c0, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] += v[j];
+            }
+        const float inv = 1.f / (float)(2 * ny);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] *= inv;
+    }
+    store_group8<T>(y + (((long long)n * Ho + yo) * Wo + xo) * C + c0, o);
+}
+
+int build_resample2(std::vector<Op>& ops, int dtype, const void* x, void* y, int N, int H, int W, int C, int mode) {
+    TQ_CHECK(dtype == TQ_BF16 || dtype == TQ_F32, "resample2: bad dtype");
+    TQ_CHECK(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "resample2: bad arguments (C must be a multiple of 8)");
+    TQ_CHECK(mode == 0 || mode == 1, "resample2: mode must be 0 (average pool) or 1 (nearest x2)");
+    TQ_CHECK(mode == 1 || (W >= 2 && (H == 1 || H >= 2)), "resample2: average pool needs at least two positions per axis");
+    const int Ho = H == 1 ? 1 : (mode == 1 ? 2 * H : H / 2), Wo = mode == 1 ? 2 * W : W / 2;
+    const long long threads = (long long)N * Ho * Wo * (C / 8);
+    Op op;
+    op.name = mode == 1 ? "nearest_upsample2" : "avg_pool2";
+    op.small = threads * 8 * 4 < 40e6;
+    op.launch = [=](cudaStream_t st) -> int {
+        if (dtype == TQ_F32)
+            TQ_CUDA(launch_pdl(resample2_kernel<float>, dim3(blocks_for(threads, 256)), dim3(256), 0, st, static_cast<const float*>(x),
+                               static_cast<float*>(y), N, H, W, C, Ho, Wo, mode));
+        else
+            TQ_CUDA(launch_pdl(resample2_kernel<__nv_bfloat16>, dim3(blocks_for(threads, 256)), dim3(256), 0, st,
+                               static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), N, H, W, C, Ho, Wo, mode));
+        TQ_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    };
+    ops.push_back(std::move(op));
+    return 0;
+}
+
 // mean over the positions of a channels-last fp32 tensor: y[n][c] = mean_p x[n][p][c]   (row stride ld >= C)
 // one CTA per (sample, 32-channel slab): 8 position lanes x 32 channels, coalesced 128 B rows, smem tree at the end
 __global__ void __launch_bounds__(256) spatial_mean_kernel(const float* __restrict__ x, int P, int C, int ld, float* __restrict__ y) {

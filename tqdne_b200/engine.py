@@ -466,6 +466,20 @@ class Plan:
         self.op_meta.append(("fourier", 0, 0))
         self.keep += [t, Wf, feat]
 
+    def resample2(self, x: Act, mode: str) -> Act:
+        """'avg_pool' (nn.AvgPool{1,2}d(2, 2)) or 'nearest' (F.interpolate x2): the conv-less resamplers of conv_resample=False.
+        The result carries no GroupNorm statistics: the consuming norm runs its own statistics pass."""
+        up = mode == "nearest"
+        Ho = 1 if x.H == 1 else (2 * x.H if up else x.H // 2)
+        Wo = 2 * x.W if up else x.W // 2
+        out = self.new_act(x.N, Ho, Wo, x.C)
+        _lib.check(self.lib.tq_plan_add_resample2(self.h, self.tq_dtype, x.t.data_ptr(), out.t.data_ptr(), x.N, x.H, x.W, x.C,
+                                                  1 if up else 0), "plan_add_resample2")
+        esz = x.t.element_size()
+        self.op_meta.append(("resample2", 0, (x.N * x.P + out.N * out.P) * x.C * esz))
+        self.keep += [x.t, out.t]
+        return out
+
     def spatial_mean(self, x: torch.Tensor, N: int, P: int, Cc: int, ld: int, y: torch.Tensor):
         _lib.check(self.lib.tq_plan_add_spatial_mean(self.h, x.data_ptr(), N, P, Cc, ld, y.data_ptr()), "plan_add_spatial_mean")
         self.op_meta.append(("spatial_mean", 0, 4 * N * P * Cc))

@@ -117,11 +117,16 @@ class Lowerer:
         return out
 
     def downsample(self, blk: B.Downsample, x: Act) -> Act:
+        if not blk.use_conv:   # conv_resample=False: nn.AvgPool{1,2}d(2, 2) (blocks.py:104)
+            return self.plan.resample2(x, "avg_pool")
         return self.conv(blk.op, [x], stats=True)
 
     def upsample(self, blk: B.Upsample, x: Act, free_input: bool) -> Act:
-        if not blk.use_conv:
-            raise NotImplementedError("tqdne_b200: Upsample(use_conv=False) is not lowered")
+        if not blk.use_conv:   # conv_resample=False: F.interpolate(scale_factor=2, mode="nearest") alone (blocks.py:59-62)
+            out = self.plan.resample2(x, "nearest")
+            if free_input:
+                self.plan.release(x)
+            return out
         out = self.conv(blk.conv, [x], upsample=True, stats=True)
         if free_input:
             self.plan.release(x)
@@ -175,7 +180,12 @@ class UNetPlan:
             c1 = torch.empty(N, E, **f32)
             cemb = torch.empty(N, E, **f32)
             l0, l2 = model.cond_mlp[0], model.cond_mlp[2]
-            cp.linear(self.cond, l0.weight.detach().float().contiguous(), l0.bias.detach().float().contiguous(), N, y=c1)
+            cin = self.cond
+            if getattr(model, "cond_embed", None) is not None:
+                # Fourier-embedded conditioning (unet.py:386-387): one feature per sample -> [N, model_channels]
+                cin = torch.empty(N, mc, **f32)
+                cp.fourier(self.cond.view(-1), model.cond_embed.W.detach().float().contiguous(), N, cin)
+            cp.linear(cin, l0.weight.detach().float().contiguous(), l0.bias.detach().float().contiguous(), N, y=c1)
             cp.linear(c1, l2.weight.detach().float().contiguous(), l2.bias.detach().float().contiguous(), N, act_in=True,
                       y=cemb)
             self.cond_plan = cp

@@ -304,6 +304,8 @@ class TrainStep1D:
                     o = resblock(layer, cur)
                 elif isinstance(layer, B.AttentionBlock):
                     o = attention(layer, cur[0])
+                elif isinstance(layer, (B.Downsample, B.Upsample)) and not layer.use_conv:
+                    raise NotImplementedError("tqdne_b200: the training tape covers conv_resample=True models only")
                 elif isinstance(layer, B.Downsample):
                     o = self._conv(layer.op, [cur[0]], [cur[0].C], stride=2, stats=True)
                     self.nodes.append(("conv", layer.op, [cur[0]], o, dict(stride=2)))

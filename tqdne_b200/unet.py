@@ -61,10 +61,15 @@ class UNetModel(nn.Module):
         self.time_mlp = nn.Sequential(nn.Linear(model_channels, emb_dim), nn.SiLU(), nn.Linear(emb_dim, emb_dim))
         self.cond_features = cond_features
         if cond_features is not None:
-            if cond_emb_scale is not None:
-                raise NotImplementedError("tqdne_b200: Fourier-embedded conditioning (cond_emb_scale) is unused by the "
-                                          "shipped configs and is not lowered")
             self.cond_embed = None
+            if cond_emb_scale is not None:
+                # reference unet.py:217-219, 386-387.  GaussianFourierProjection.forward broadcasts x[:, None] * W[None, :]
+                # (blocks.py:23): with a [N, F] conditioning tensor that only runs for F = 1, so that is what is lowered.
+                if cond_features != 1:
+                    raise NotImplementedError("tqdne_b200: cond_emb_scale with more than one conditioning feature does not run "
+                                              "in the reference either (GaussianFourierProjection broadcasts [N, 1, F] * [1, C/2])")
+                self.cond_embed = GaussianFourierProjection(model_channels, cond_emb_scale)
+                cond_features = cond_features * model_channels
             self.cond_mlp = nn.Sequential(nn.Linear(cond_features, emb_dim), nn.SiLU(), nn.Linear(emb_dim, emb_dim))
 
         def res(cin, cout):
