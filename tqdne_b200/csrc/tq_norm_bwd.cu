@@ -19,6 +19,9 @@
 // bf16).  mu / rstd come from the per-(sample, channel) sums the FORWARD conv epilogue left behind (tq_conv_desc.stats).
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "tq_common.h"
 #include "tq_gnstats.cuh"
 #include "tq_ptx.cuh"
@@ -520,6 +523,10 @@ int launch_gn_bwd_cluster(const GnBwdParams& p, int chunks, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (chunks > 8) {
+        static PerDeviceOnce np;
+        if (np.first()) TQ_CUDA(cudaFuncSetAttribute(gn_bwd_cluster_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
     TQ_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_cluster_kernel<T>, p));
     return 0;
 }
@@ -563,6 +570,7 @@ extern "C" int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream) {
         if (cl > 8) cl = 8;
         if (cl < 1) cl = 1;
         while (cl & (cl - 1)) cl &= cl - 1;   // power of two
+        if (const char* e = getenv("TQ_GN_BWD_CL")) cl = std::max(1, std::min(std::min(16, max_chunks), atoi(e)));   // experiments
         p.chunks = cl;
         if (d->dtype == TQ_F32) {
             if (launch_gn_bwd_cluster<float>(p, cl, st)) return 1;
