@@ -303,8 +303,13 @@ def test_engine_fails_loudly_off_gpu_and_on_unsupported_options():
         net(torch.zeros(1, 8, 32, 32), torch.zeros(1), torch.zeros(1, 5))
     with pytest.raises(AssertionError):
         net.cuda()(torch.zeros(1, 8, 32, 32, device="cuda"), torch.zeros(1, device="cuda"), None)
+    # the one option that still raises is the one the reference cannot run either (blocks.py:23 broadcast)
     with pytest.raises(NotImplementedError):
-        tq.UNetModel(**(unet_cfg("latent2d") | {"use_scale_shift_norm": True}))
+        tq.UNetModel(**(unet_cfg("latent2d") | {"cond_emb_scale": 0.5}))
+    # ... and the training tape, which covers the shipped ResBlock / resamplers / attention only
+    edm = tq.LightningEDM(unet_cfg("1d_film"), {}).cuda()
+    with pytest.raises(NotImplementedError):
+        edm.training_step({"signal": torch.zeros(2, 6, 512, device="cuda"), "cond": torch.zeros(2, 5, device="cuda")}, 0)
 
 
 def test_launch_accounting_counts_native_kernels():
