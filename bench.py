@@ -346,20 +346,28 @@ def kernel_breakdown(edm, batch, iters=3):
     scale = graph_ms / sum(a["ms"] for a in agg.values())   # exact closure (the floor above can leave a few microseconds)
     for a in agg.values():
         a["ms"] *= scale
-    return agg, graph_ms, op_sum
+    return agg, graph_ms, op_sum, names
 
 
-def source_sha16(*rel_paths) -> str:
-    """Hash of the kernel sources a committed ncu capture belongs to: a capture is only quoted while it matches HEAD."""
+def source_sha16(*rel_paths, extra: str = "") -> str:
+    """Hash that ties a committed ncu capture to what it measured: the kernel sources plus `extra`."""
     import hashlib
 
     h = hashlib.sha256()
     for rp in rel_paths:
         h.update((ROOT / rp).read_bytes())
+    h.update(extra.encode())
     return h.hexdigest()[:16]
 
 
-IGEMM_SOURCES = ("tqdne_b200/csrc/tq_igemm_sm100.cu", "tqdne_b200/csrc/tq_ptx.cuh", "tqdne_b200/engine.py", "tqdne_b200/lowering.py")
+# The DRAM capture of the igemm launches belongs to (a) the kernel's sources and (b) the launches the lowering asked for:
+# every igemm op name carries its tile shape, tile count, K slices and stage kind, so the list of names of the plan is the
+# fingerprint of (b) -- an edit of engine.py / lowering.py that does not change a single convolution keeps the capture valid.
+IGEMM_SOURCES = ("tqdne_b200/csrc/tq_igemm_sm100.cu", "tqdne_b200/csrc/tq_ptx.cuh")
+
+
+def igemm_fingerprint(op_names) -> str:
+    return source_sha16(*IGEMM_SOURCES, extra="\n".join(n for n in op_names if n.startswith("igemm_sm100")))
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -703,7 +711,7 @@ def run_engine(args) -> None:
         "wall_ms_per_step": wall_ms / args.steps,
     }
     if rank == 0 and world == 1:
-        agg, graph_ms, op_sum_ms = kernel_breakdown(edm, hi - lo)
+        agg, graph_ms, op_sum_ms, plan_op_names = kernel_breakdown(edm, hi - lo)
         tot_ms = graph_ms
         conv = agg.get("igemm_sm100") or agg.get("igemm_simt")
         ach = conv["flops"] / (conv["ms"] / 1e3) / 1e12
@@ -722,7 +730,7 @@ def run_engine(args) -> None:
         tfile = ROOT / "profiles" / "igemm_dram_traffic.json"
         if tfile.exists():
             tj = json.loads(tfile.read_text())
-            if tj.get("launches") == conv["launches"] and tj.get("source_sha16") == source_sha16(*IGEMM_SOURCES):
+            if tj.get("launches") == conv["launches"] and tj.get("source_sha16") == igemm_fingerprint(plan_op_names):
                 line["roofline"]["traffic"] = tj["bytes_per_launch"]
                 line["roofline"]["traffic_unit"] = "DRAM bytes per launch (read + write), ncu --set full, " + tj.get("capture", "")
             else:

@@ -29,6 +29,9 @@ with torch.cuda.stream(s):
         p.set_cond(torch.from_numpy(cond_grid(B)).cuda())
         p.t.fill_(0.3)
         run = p.plan.run
+        # the launches this capture belongs to (bench.igemm_fingerprint): travels back with the csv
+        Path("gpurun_out").mkdir(exist_ok=True)
+        Path(f"gpurun_out/r2_ops_unet_b{B}.names.txt").write_text("\n".join(p.plan.op_names()) + "\n")
     elif what == "decoder":
         p = get_coder_plan(edm.autoencoder.decoder, "decoder", B, (32, 32))
         p.xin.t.normal_()

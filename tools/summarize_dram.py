@@ -1,7 +1,8 @@
 """ncu csv (dram__bytes_read.sum, dram__bytes_write.sum, gpu__time_duration.sum per launch) -> JSON for bench.py's
 roofline.traffic: DRAM bytes per launch of the dominant kernel, averaged over the launches of one denoiser call.
 
-    python tools/summarize_dram.py gpurun_out/igemm_dram.csv profiles/r1_igemm_dram_traffic.json
+    python tools/summarize_dram.py profiles/r2_igemm_dram_unet_b256.csv profiles/igemm_dram_traffic.json \
+        profiles/r2_ops_unet_b256.names.txt        # op names of the captured plan (tools/profile_call.py writes them)
 """
 import collections
 import csv
@@ -16,7 +17,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-3, 
         "msecond": 1e3, "ms": 1e3}
 
 
-def main(src, dst):
+def main(src, dst, names_file):
     lines = [l for l in open(src) if not l.startswith("==")]
     per = collections.defaultdict(dict)
     for r in csv.DictReader(io.StringIO("".join(lines))):
@@ -27,11 +28,11 @@ def main(src, dst):
     rd = sum(p.get("dram__bytes_read.sum", 0.0) for p in per.values())
     wr = sum(p.get("dram__bytes_write.sum", 0.0) for p in per.values())
     us = sum(p.get("gpu__time_duration.sum", 0.0) for p in per.values())
-    from bench import IGEMM_SOURCES, source_sha16
+    from bench import igemm_fingerprint
 
     # the hash ties the capture to the kernel sources it was taken from: bench.py quotes `traffic` only while it matches
     out = {"kernel": "igemm_sm100_kernel (all launches of one latent-UNet denoiser call, batch 256, bf16)", "launches": n,
-           "source_sha16": source_sha16(*IGEMM_SOURCES), "capture": Path(src).name,
+           "source_sha16": igemm_fingerprint(Path(names_file).read_text().split("\n")), "capture": Path(src).name,
            "dram_read_bytes": rd, "dram_write_bytes": wr, "bytes_per_launch": (rd + wr) / max(n, 1),
            "ncu_time_us": us, "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum ({src}); cold cache per launch"}
     json.dump(out, open(dst, "w"), indent=1)
@@ -39,4 +40,4 @@ def main(src, dst):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], sys.argv[3])
