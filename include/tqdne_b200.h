@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TQ_ABI_VERSION 19
+#define TQ_ABI_VERSION 20
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
 
@@ -155,7 +155,12 @@ typedef struct {
     int32_t dtype; int32_t N, T, heads, d;
     const void* qkv; void* out;
     int32_t causal;
+    /* optional (training): [N][heads][T] fp32, L_i = log2 sum_j 2^(s_ij d^-1/2 log2 e) of every query row, the statistic
+     * tq_attention_backward otherwise recomputes.  Written by the multi-block tensor-core kernel (bf16, d in {64, 128},
+     * 128 < T <= 512); tq_attention_writes_lse(d) tells whether the kernel chosen for `d` does.                         */
+    float* lse;
 } tq_attn_desc;
+int32_t tq_attention_writes_lse(const tq_attn_desc* d);
 int tq_plan_add_attention(tq_plan* p, const tq_attn_desc* d);
 
 /* ---- small dense layers in fp32 (embedding MLPs) ---------------------------------------------- *
@@ -232,9 +237,11 @@ int tq_gn_silu_backward(const tq_gn_bwd_desc* d, void* stream);
  * Replaces: autograd through QKVAttention.forward (tqdne/blocks.py:156-190).  Same layouts as tq_attn_desc:
  * qkv [N,T,3*heads*d] (forward input), out [N,T,heads*d] (forward output), dout = gradient of out, all bf16;
  * writes dqkv [N,T,3*heads*d] bf16.  ws: 2*N*heads*T floats of scratch (row log-sum-exp and D_i).
+ * `lse_given` != 0: ws[0 .. N*heads*T) already holds the log-sum-exp the forward wrote (tq_attn_desc.lse = ws) and the
+ * kernel skips recomputing it (one S = Q K^T over all keys and two softmax passes per query block).
  * tcgen05 kernels; head dim 64, 32 < T <= 512 (the 1D UNet's attention blocks).                          */
 int tq_attention_backward(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws, int32_t N,
-                          int32_t T, int32_t heads, int32_t d, void* stream);
+                          int32_t T, int32_t heads, int32_t d, int32_t lse_given, void* stream);
 
 /* ---- small kernels of the training step ------------------------------------------ *
  * tq_rows_op: rows of a channels-last bf16 tensor [N, L, C]; L_dst = rows of dst per sample.

@@ -822,10 +822,27 @@ def test_attention_backward_matches_autograd(N, T, heads):
     dout = _rt(torch.randn(N, T, C, device="cuda", generator=g), dt)
     plan = _plan(dt)
     qa = Act(qkv.to(dt).reshape(-1), N, 1, T, 3 * C)
-    out = plan.attention(qa, heads)
+    ws = torch.full((2 * N * heads * T,), float("nan"), device="cuda")
+    out = plan.attention(qa, heads, lse=ws)
+    # the multi-block forward kernel (T > 128) leaves the rows' log-sum-exp for the backward; other shapes recompute it
+    assert out.lse_written == (T > 128)
     plan.run()
-    dqkv = attention_backward(qa, out, Act(dout.to(dt).reshape(-1), N, 1, T, C), heads)
+    da = Act(dout.to(dt).reshape(-1), N, 1, T, C)
+    dqkv = attention_backward(qa, out, da, heads, lse=ws if out.lse_written else None)
     torch.cuda.synchronize()
+    if out.lse_written:
+        # the handed-over statistic equals the one the backward computes for itself (exact fp32 sums on both sides), and
+        # both routes give the same gradient
+        from tqdne_b200 import _lib as L
+        from tqdne_b200.engine import current_stream_ptr
+
+        own = attention_backward(qa, out, da, heads, lse=None)
+        ws2 = torch.empty_like(ws)
+        L.check(L.lib().tq_attention_backward(qa.t.data_ptr(), out.t.data_ptr(), da.t.data_ptr(), torch.empty_like(qa.t).data_ptr(),
+                                              ws2.data_ptr(), N, T, heads, d, 0, current_stream_ptr()), "attention_backward")
+        torch.cuda.synchronize()
+        assert float((ws[: N * heads * T] - ws2[: N * heads * T]).abs().max()) < 2e-4
+        assert rel_l2(own.t.float(), dqkv.t.float()) < 2e-3
     x = qkv.double().permute(0, 2, 1).clone().requires_grad_(True)   # [N, 3C, T] like the reference
     q, k, v = x.chunk(3, dim=1)
     s = 1 / math.sqrt(math.sqrt(d))

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 TQ_BF16, TQ_F32, TQ_F64 = 0, 1, 2
-ABI_VERSION = 19  # TQ_ABI_VERSION of include/tqdne_b200.h
+ABI_VERSION = 20  # TQ_ABI_VERSION of include/tqdne_b200.h
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("TQDNE_B200_LIB", _HERE / "libtqdne_b200.so"))
@@ -79,6 +79,7 @@ class TqAttnDesc(C.Structure):
         ("N", C.c_int32), ("T", C.c_int32), ("heads", C.c_int32), ("d", C.c_int32),
         ("qkv", C.c_void_p), ("out", C.c_void_p),
         ("causal", C.c_int32),
+        ("lse", C.c_void_p),
     ]
 
 
@@ -129,12 +130,13 @@ SIGNATURES = {
     "tq_plan_add_groupnorm": (C.c_int, [_VP, C.POINTER(TqGnDesc)]),
     "tq_groupnorm_ws_floats": (_I64, [C.POINTER(TqGnDesc)]),
     "tq_plan_add_attention": (C.c_int, [_VP, C.POINTER(TqAttnDesc)]),
+    "tq_attention_writes_lse": (_I32, [C.POINTER(TqAttnDesc)]),
     "tq_plan_add_linear": (C.c_int, [_VP, C.POINTER(TqLinearDesc)]),
     "tq_plan_add_fourier": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
     "tq_plan_add_resample2": (C.c_int, [_VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, _I32]),
     "tq_plan_add_spatial_mean": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     "tq_gn_silu_backward": (C.c_int, [C.POINTER(TqGnBwdDesc), _VP]),
-    "tq_attention_backward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
+    "tq_attention_backward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "tq_sample_channel_sums": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _I32, _VP]),
     "tq_conv1d_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _I32, _I32, _I32, _VP]),
     "tq_conv2d_wgrad": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),

@@ -101,16 +101,21 @@ def sample_channel_sums(dy: Act, out: torch.Tensor | None = None, out_ld: int = 
     return out
 
 
-def attention_backward(qkv: Act, out: Act, dout: Act, heads: int) -> Act:
+def attention_backward(qkv: Act, out: Act, dout: Act, heads: int, lse: torch.Tensor | None = None) -> Act:
     """d(qkv) [N, T, 3C] of the attention core (QKVAttention.forward, blocks.py:156-190) from the forward's input / output
-    and the gradient of its output; bf16, head dim 64, 32 < T <= 512."""
+    and the gradient of its output; bf16, head dim 64, 32 < T <= 512.  `lse`: the 2 * N * heads * T float scratch whose first
+    half the FORWARD kernel filled with the rows' log-sum-exp (Plan.attention(lse=...) with out.lse_written): the backward
+    then skips recomputing it."""
     N, T, C3 = qkv.N, qkv.H * qkv.W, qkv.C
     Cc = C3 // 3
     assert out.C == Cc and dout.C == Cc and qkv.t.dtype == torch.bfloat16
     dqkv = torch.empty_like(qkv.t)
-    ws = torch.empty(2 * N * heads * T, device=qkv.t.device, dtype=torch.float32)
+    given = lse is not None
+    ws = lse if given else torch.empty(2 * N * heads * T, device=qkv.t.device, dtype=torch.float32)
+    assert ws.numel() >= 2 * N * heads * T and ws.dtype == torch.float32
     _lib.check(_lib.lib().tq_attention_backward(qkv.t.data_ptr(), out.t.data_ptr(), dout.t.data_ptr(), dqkv.data_ptr(),
-                                                ws.data_ptr(), N, T, heads, Cc // heads, current_stream_ptr()), "attention_backward")
+                                                ws.data_ptr(), N, T, heads, Cc // heads, 1 if given else 0, current_stream_ptr()),
+               "attention_backward")
     return Act(dqkv, N, qkv.H, qkv.W, C3)
 
 

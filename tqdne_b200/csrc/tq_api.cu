@@ -188,6 +188,7 @@ int tq_plan_add_linear(tq_plan* p, const tq_linear_desc* d) {
     drop_graph(p);
     return build_linear(p->ops, *d);
 }
+int32_t tq_attention_writes_lse(const tq_attn_desc* d) { return d != nullptr && attention_writes_lse(*d) ? 1 : 0; }
 int tq_plan_add_fourier(tq_plan* p, const float* t, const float* W, int32_t M, int32_t half, float* feat) {
     TQ_CHECK(p != nullptr, "null argument");
     drop_graph(p);

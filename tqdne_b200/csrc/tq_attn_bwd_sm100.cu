@@ -39,6 +39,7 @@ struct AttnBwdParams {
     float* dsum;               // [N][heads][T] D_i
     int N, T, heads, Tk;
     float scale, scale_log2;   // d^-1/2, d^-1/2 * log2(e)
+    int lse_given;             // lse[] was written by the forward kernel: pass 1 of the dQ kernel is skipped
 };
 
 __device__ __forceinline__ void tma3(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2) {
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
         }
     }
     uint32_t mma_phase = 0;
-    // ---- pass 1: S over all keys -> row max / sum
-    if (warp == 0) {
+    // ---- pass 1: S over all keys -> row max / sum (skipped when the forward kernel left the log-sum-exp behind)
+    if (warp == 0 && !p.lse_given) {
         mbar_wait(bar_ld, 0);
         tc_fence_after();
         if (elect_one()) {
@@ -148,10 +149,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
     const uint32_t t_row = tmem + (uint32_t((warp & 3) * 32) << 16);
     const int t = qb * BLK + row;
     const float sc = p.scale_log2;
+    float Lreg;
+    if (p.lse_given) {
+        mbar_wait(bar_ld, 0);   // (every thread: the pass-2 MMAs and the D_i loads below need nothing else from pass 1)
+        Lreg = t < p.T ? __ldg(p.lse + ((long long)n * p.heads + h) * p.T + t) : 0.f;
+    } else {
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
-    float Lreg;
     {
         const int cols = Tk / 2, col0 = half * cols;
         float m = -INFINITY;
@@ -184,6 +189,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
         __syncthreads();
         Lreg = m * sc + log2f(l);   // L_i in the log2 domain: P_ij = 2^(s_ij c - L_i); both threads of a row agree bitwise
     }
+    }
     // D_i = sum_c dO_ic O_ic (this thread: half of the 64 channels of its row)
     float Dreg;
     {
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
     const float L = Lreg, Dm = Dreg;
     if (half == 0 && t < p.T) {
         const long long o = ((long long)n * p.heads + h) * p.T + t;
-        p.lse[o] = L;
+        if (!p.lse_given) p.lse[o] = L;
         p.dsum[o] = Dm;
     }
     // ---- pass 2: key blocks of 128
@@ -442,7 +448,7 @@ int encode_rows(CUtensorMap* m, const void* ptr, int N, int T, int ld, const cha
 using namespace tq;
 
 extern "C" int tq_attention_backward(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws, int32_t N,
-                                     int32_t T, int32_t heads, int32_t d, void* stream) {
+                                     int32_t T, int32_t heads, int32_t d, int32_t lse_given, void* stream) {
     TQ_CHECK(qkv && out && dout && dqkv && ws, "attention_backward: null pointer");
     TQ_CHECK(d == D, "attention_backward: head dim 64 only (the 1D UNet); got %d", d);
     TQ_CHECK(N > 0 && heads > 0 && T > 32 && T <= 512, "attention_backward: 32 < T <= 512");
@@ -457,6 +463,7 @@ extern "C" int tq_attention_backward(const void* qkv, const void* out, const voi
     p.lse = ws;
     p.dsum = ws + (size_t)N * heads * T;
     p.N = N; p.T = T; p.heads = heads; p.Tk = (T + BLK - 1) / BLK * BLK;
+    p.lse_given = lse_given ? 1 : 0;
     p.scale = 1.f / sqrtf((float)D);
     p.scale_log2 = p.scale * 1.4426950408889634f;
     const int blocks = (T + BLK - 1) / BLK;

@@ -283,6 +283,7 @@ struct AttnMultiParams {
     int N, T, heads, Tk;
     int qsplit;        // CTAs per (sample, head): each takes a contiguous range of the query blocks
     float scale_log2;
+    float* lse;        // optional [N][heads][T]: log2-domain log-sum-exp of the scaled scores, for the backward pass
 };
 
 template <int D>
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attention_tc_multi_kernel(const
     extern __shared__ uint8_t smem_raw[];
     __shared__ float red_max[2][kQB];
     __shared__ float red_sum[2][kQB];
+    __shared__ float red_lx[2][kQB];   // unrounded row sums (only when the log-sum-exp is written out)
     __shared__ __align__(8) uint64_t bars[5];   // q[0], q[1], k, v, mma
     __shared__ uint32_t tmem_slot;
 
@@ -427,7 +429,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attention_tc_multi_kernel(const
         __syncthreads();
         m = fmaxf(red_max[0][row], red_max[1][row]);
         const float msc = m * sc;
-        float l = 0.f;
+        float l = 0.f, lx = 0.f;   // lx: the same sum before the bf16 rounding (what the backward's exact softmax needs)
+        const bool want_lse = p.lse != nullptr;
         auto exp_chunk = [&](const uint32_t (&r)[32], int c) {
             const int lim = p.T - (col0 + c);
             uint32_t pk[16];
@@ -438,6 +441,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attention_tc_multi_kernel(const
                     const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), sc, -msc));
                     const __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
                     l += __low2float(b2) + __high2float(b2);  // the row sum of the weights the MMA really applies
+                    if (want_lse) lx += e0 + e1;
                     pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
                 }
             } else {
@@ -447,6 +451,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attention_tc_multi_kernel(const
                     const float e1 = (2 * j + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), sc, -msc)) : 0.f;
                     const __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
                     l += __low2float(b2) + __high2float(b2);
+                    if (want_lse) lx += e0 + e1;
                     pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
                 }
             }
@@ -465,6 +470,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attention_tc_multi_kernel(const
             tmem_ld_wait();
         }
         red_sum[half][row] = l;
+        if (want_lse) red_lx[half][row] = lx;
         tmem_st_wait();
         tc_fence_before();
         __syncthreads();
@@ -492,6 +498,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) attention_tc_multi_kernel(const
         {
             const float inv = 1.f / (red_sum[0][row] + red_sum[1][row]);
             const int t = qb * kQB + row;
+            if (want_lse && half == 0 && t < p.T)   // L_i = m c + log2 sum_j 2^((s_ij - m) c): P_ij = 2^(s_ij c - L_i)
+                p.lse[((long long)n * p.heads + h) * p.T + t] = msc + log2f(red_lx[0][row] + red_lx[1][row]);
             constexpr int OC = D / 2;  // output channels per thread
             __nv_bfloat16* o = p.out + ((long long)n * p.T + t) * C + h * D + half * OC;
 #pragma unroll
@@ -784,6 +792,13 @@ bool attention_tc_supported(const tq_attn_desc& d) {
     return attn_tc_smem(Tk, d.d) <= 224 * 1024;  // + ~2 KB of static shared memory
 }
 
+// does the kernel build_attention picks for `d` write tq_attn_desc.lse?  (only the multi-block kernel does)
+bool attention_writes_lse(const tq_attn_desc& d) {
+    const char* simt = getenv("TQ_ATTN_SIMT");
+    if (d.causal || (simt && simt[0] == '1') || !attention_tc_supported(d) || d.T <= 32) return false;
+    return attn_multi_ok((d.T + 127) / 128 * 128, d.d);
+}
+
 int build_attention_tc(std::vector<Op>& ops, const tq_attn_desc& d) {
     auto enc = encode_fn();
     TQ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -824,6 +839,7 @@ int build_attention_tc(std::vector<Op>& ops, const tq_attn_desc& d) {
         auto q = std::make_shared<AttnMultiParams>();
         q->map = p->map; q->out = p->out; q->N = d.N; q->T = d.T; q->heads = d.heads; q->Tk = p->Tk;
         q->scale_log2 = p->scale_log2;
+        q->lse = d.lse;
         // CTAs per (sample, head): all query blocks in one CTA (K / V loaded once) unless that leaves SMs idle
         const int qblocks = (d.T + kQB - 1) / kQB;
         int qsplit = 1;

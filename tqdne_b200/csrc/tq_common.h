@@ -140,6 +140,7 @@ int build_groupnorm(std::vector<Op>& ops, const tq_gn_desc& d);
 int build_attention(std::vector<Op>& ops, const tq_attn_desc& d);
 // tcgen05 attention (tq_attn_sm100.cu): bf16, head dim 64 / 128, 32 < T <= 512, all keys resident in shared memory
 bool attention_tc_supported(const tq_attn_desc& d);
+bool attention_writes_lse(const tq_attn_desc& d);
 int build_attention_tc(std::vector<Op>& ops, const tq_attn_desc& d);
 int build_linear(std::vector<Op>& ops, const tq_linear_desc& d);
 int build_fourier(std::vector<Op>& ops, const float* t, const float* W, int M, int half, float* feat);

@@ -431,7 +431,9 @@ class Plan:
         self.keep += [g, b, a0.t, out.t] + ([a1.t] if a1 else [])
         return out
 
-    def attention(self, qkv: Act, heads: int, causal: bool = False) -> Act:
+    def attention(self, qkv: Act, heads: int, causal: bool = False, lse: torch.Tensor | None = None) -> Act:
+        """`lse` (training): fp32 [N * heads * T] the kernel fills with the rows' log-sum-exp for the backward pass, when the
+        kernel chosen for this shape can (`out.lse_written`)."""
         Cc = qkv.C // 3
         out = self.new_act(qkv.N, qkv.H, qkv.W, Cc)
         d = _lib.TqAttnDesc()
@@ -439,6 +441,12 @@ class Plan:
         d.N, d.T, d.heads, d.d = qkv.N, qkv.P, heads, Cc // heads
         d.qkv, d.out = qkv.t.data_ptr(), out.t.data_ptr()
         d.causal = 1 if causal else 0
+        out.lse_written = False
+        if lse is not None and int(self.lib.tq_attention_writes_lse(C.byref(d))) == 1:
+            assert lse.dtype == torch.float32 and lse.numel() >= qkv.N * heads * qkv.P
+            d.lse = lse.data_ptr()
+            out.lse_written = True
+            self.keep.append(lse)
         _lib.check(self.lib.tq_plan_add_attention(self.h, C.byref(d)), "plan_add_attention")
         self.op_meta.append(("attention", 4 * qkv.N * qkv.P * qkv.P * Cc, 0))
         self.keep += [qkv.t, out.t]

@@ -291,8 +291,11 @@ class TrainStep1D:
             self.nodes.append(("gn", blk.norm, [x], g, False))
             qkv = self._conv(blk.qkv, [g], [g.C], stats=False)
             self.nodes.append(("conv", blk.qkv, [g], qkv, {}))
-            a = self._plan(self.fwd).attention(qkv, blk.num_heads)
-            self.nodes.append(("attn", blk, [qkv], a, None))
+            # scratch of the backward kernels (row log-sum-exp, D_i): the forward kernel fills the first half when it can
+            ws = torch.empty(2 * qkv.N * blk.num_heads * qkv.W, device=self.dev, dtype=torch.float32)
+            self._keep.append(ws)
+            a = self._plan(self.fwd).attention(qkv, blk.num_heads, lse=ws)
+            self.nodes.append(("attn", blk, [qkv], a, ws))
             out = self._conv(blk.proj_out, [a], [a.C], residual=x, stats=True)
             self.nodes.append(("conv", blk.proj_out, [a], out, dict(residual=x)))
             return out
@@ -459,11 +462,10 @@ class TrainStep1D:
                 qkv, da = srcs[0], grad[id(out)]
                 dqkv = self._new(N, qkv.W, qkv.C)
                 heads = mod.num_heads
-                ws = torch.empty(2 * N * heads * qkv.W, device=self.dev, dtype=torch.float32)
-                self._keep.append(ws)
-                self._direct(ops, lambda qkv=qkv, out=out, da=da, dqkv=dqkv, ws=ws, heads=heads: _lib.check(
+                ws, given = extra, 1 if getattr(out, "lse_written", False) else 0
+                self._direct(ops, lambda qkv=qkv, out=out, da=da, dqkv=dqkv, ws=ws, heads=heads, given=given: _lib.check(
                     lib.tq_attention_backward(qkv.t.data_ptr(), out.t.data_ptr(), da.t.data_ptr(), dqkv.t.data_ptr(), ws.data_ptr(),
-                                              N, qkv.W, heads, qkv.C // 3 // heads, self._st()), "attention_backward"))
+                                              N, qkv.W, heads, qkv.C // 3 // heads, given, self._st()), "attention_backward"))
                 grad[id(qkv)] = dqkv
             elif kind == "mul":
                 dy = grad[id(out)]
