@@ -17,6 +17,8 @@
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include <memory>
 
 #include "tq_common.h"
@@ -180,19 +182,49 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad1d_kernel(const __grid_con
     }
 }
 
-// db[co] = sum over positions of dY: one CTA per 256 positions, 64 channels per warp-row; fp32 atomics
+// db[co] = sum over positions of dY.  Thread = (8-channel vector of a slab of <= 32 vectors, row lane), 16 B loads, four
+// rows in flight; the grid is a fixed ~2 blocks per SM walking the rows with a stride, because what bounded the version
+// this replaces (one block per 256 rows) was its ONE fp32 atomic per channel and block: ~2 000 serialised atomics per address.
+constexpr int BG_VEC = 32;   // vectors (of 8 channels) per block slab
 __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long long rows, int cout,
                                                         float* __restrict__ db) {
-    const int c = blockIdx.y * 64 + (threadIdx.x & 63);
-    const int rl = threadIdx.x >> 6;  // 4 row lanes
-    const long long r0 = (long long)blockIdx.x * 256, r1 = min(rows, r0 + 256);
-    float a = 0.f;
-    if (c < cout)
-        for (long long r = r0 + rl; r < r1; r += 4) a += __bfloat162float(dy[r * cout + c]);
-    __shared__ float red[4][64];
-    red[rl][threadIdx.x & 63] = a;
+    __shared__ float red[256 * 9];
+    const int cv = cout >> 3;                       // 16 B vectors per row (cout % 8 == 0)
+    const int v0 = blockIdx.y * BG_VEC, cvb = min(BG_VEC, cv - v0);
+    const int lanes = 256 / cvb;                    // >= 8 row lanes
+    const int vi = threadIdx.x % cvb, rl = threadIdx.x / cvb;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    auto add8 = [&](const uint4& u) {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+            a[2 * k] += __low2float(b2);
+            a[2 * k + 1] += __high2float(b2);
+        }
+    };
+    if (rl < lanes) {
+        const __nv_bfloat16* base = dy + (long long)(v0 + vi) * 8;
+        const long long step = (long long)gridDim.x * lanes;
+        long long r = (long long)blockIdx.x * lanes + rl;
+        for (; r + 3 * step < rows; r += 4 * step) {
+            uint4 u[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const uint4*>(base + (r + q * step) * cout));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) add8(u[q]);
+        }
+        for (; r < rows; r += step) add8(__ldg(reinterpret_cast<const uint4*>(base + r * cout)));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 9 + j] = rl < lanes ? a[j] : 0.f;
     __syncthreads();
-    if (rl == 0 && c < cout) atomicAdd(db + c, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+    for (int o = threadIdx.x; o < cvb * 8; o += 256) {
+        const int v2 = o >> 3, j = o & 7;
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += red[(l * cvb + v2) * 9 + j];
+        atomicAdd(db + (v0 + v2) * 8 + j, t);
+    }
 }
 
 // out[n][c] += sum over the P positions of sample n of dy[n][p][c]: the gradient of a per-sample, per-channel additive
@@ -279,7 +311,10 @@ extern "C" int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* 
     count_launch();
     if (db) {
         const long long rows = (long long)N * L;
-        bias_grad_kernel<<<dim3((unsigned)((rows + 255) / 256), (cout + 63) / 64), 256, 0, st>>>(
+        TQ_CHECK(cout % 8 == 0 && cout <= 2048, "conv1d_wgrad: bias gradient needs cout %% 8 == 0 and cout <= 2048");
+        const int cv = cout / 8, slabs = (cv + BG_VEC - 1) / BG_VEC;
+        const int gx = std::max(1, std::min((int)((rows + 63) / 64), 2 * device_sm_count() / slabs));
+        bias_grad_kernel<<<dim3((unsigned)gx, (unsigned)slabs), 256, 0, st>>>(
             static_cast<const __nv_bfloat16*>(dy), rows, cout, db);
         TQ_CUDA(cudaGetLastError());
         count_launch();
