@@ -159,6 +159,7 @@ class Act:
     C: int
     stats: torch.Tensor | None = None   # [N, parts, C, 2] fp32 per-(sample, tile, channel) sum / sum of squares (conv epilogue)
     stats_parts: int = 1
+    lse_written: bool = False           # attention output: the kernel also left the rows' log-sum-exp in the caller's buffer
 
     @property
     def P(self) -> int:
@@ -441,7 +442,6 @@ class Plan:
         d.N, d.T, d.heads, d.d = qkv.N, qkv.P, heads, Cc // heads
         d.qkv, d.out = qkv.t.data_ptr(), out.t.data_ptr()
         d.causal = 1 if causal else 0
-        out.lse_written = False
         if lse is not None and int(self.lib.tq_attention_writes_lse(C.byref(d))) == 1:
             assert lse.dtype == torch.float32 and lse.numel() >= qkv.N * heads * qkv.P
             d.lse = lse.data_ptr()
