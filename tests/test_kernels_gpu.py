@@ -564,6 +564,28 @@ def test_griffinlim_kernel_matches_oracle(monkeypatch):
     assert w32.dtype == np.float32 and e32 < max(20 * numpy32, 1e-4)
 
 
+@pytest.mark.parametrize("frames", [6, 12, 40, 128])
+def test_griffinlim_other_frame_counts_and_both_cta_shapes(frames, monkeypatch):
+    """Frame counts besides the reference's 128: 6 frames = a signal shorter than two windows (the kernel then keeps one
+    window-sum entry per sample), 12 / 40 = the compact window-sum table with a short interior; each through the two-CTA 8-warp
+    kernel (the fp64 default) and the one-CTA 16-warp kernel (TQ_GL_WARPS16=1), against the NumPy oracle and each other."""
+    from oracle import griffinlim_ref
+    from tqdne_b200.representation import LogSpectrogram
+
+    g = torch.Generator().manual_seed(frames)
+    rep = torch.tanh(torch.randn(2, 3, 128, frames, generator=g) * 0.5)
+    ref = griffinlim_ref.logspec_inverse(rep.numpy(), n_iter=12, precision="fp64")
+    ls = LogSpectrogram(stft_channels=256, hop_size=32)
+    ls.n_iter = 12
+    w8 = ls.invert_representation(rep.cuda())
+    monkeypatch.setenv("TQ_GL_WARPS16", "1")
+    w16 = ls.invert_representation(rep.cuda())
+    assert w8.shape == ref.shape == (2, 3, 32 * (frames - 1))
+    assert rel_l2(w8, ref) < 1e-9 and rel_l2(w16, ref) < 1e-9
+    # same arithmetic per frame, and a sample's overlapping frames are added in round order in both shapes: bit-identical
+    assert np.array_equal(w8, w16)
+
+
 def test_griffinlim_full_iterations_and_golden():
     from oracle import griffinlim_ref
     from tests.helpers import golden

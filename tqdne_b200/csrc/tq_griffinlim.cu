@@ -313,8 +313,10 @@ __global__ void __launch_bounds__(GL_THREADS) logspec_forward_kernel(const float
 //   * 1 / window-sum-of-squares is a per-sample table in shared memory.
 namespace fused {
 
-constexpr int FW = 16;          // warps per CTA
-constexpr int FTHREADS = FW * 32;
+// Warps per CTA (template parameter FWT of the kernel): 16 with one CTA per SM, or -- fp64, where the signal buffers leave
+// room for it -- 8 with TWO CTAs per SM: the same 16 warps per SM, but an item is half as wide, so the 768 items of a batch
+// of 256 fill the last wave better (5.19 waves of 148 one-CTA slots was 6 rounds) and one CTA's frame-round barriers are
+// covered by the other's work.  What makes two CTAs fit is the window-sum table below instead of a per-sample array.
 constexpr int EX = 152;         // per-warp exchange buffer (complex elements): >= 152 (transposes), >= 129 (spectrum)
 
 template <typename R> __device__ __forceinline__ Cx<R> cmul(Cx<R> a, Cx<R> b) { return Cx<R>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
@@ -415,28 +417,45 @@ __device__ __forceinline__ Cx<R> unit_times(R ar, R ai, R sv) {
     return Cx<R>{ar / den * sv, ai / den * sv};
 }
 
+// 1 / (window sum of squares) of padded sample n, 0 outside the kept range [NFFT/2, len - NFFT/2).  Away from the ends all
+// NFFT/HOP frames cover a sample and the sum depends on n mod HOP only; the first / last NFFT/2 kept samples have their own
+// entries: table = [HOP interior | NFFT/2 head | NFFT/2 tail].  (Needs len >= 2 NFFT; shorter signals use WSS_FULL.)
+constexpr int WSS_TAB = HOP + NFFT;
+template <typename R>
+__device__ __forceinline__ R inv_wss_at(const R* tab, int n, int len, bool full) {
+    if (full) return tab[n];
+    if (n < NFFT / 2 || n >= len - NFFT / 2) return (R)0;
+    if (n < NFFT) return tab[HOP + n - NFFT / 2];
+    if (n >= len - NFFT) return tab[HOP + NFFT / 2 + n - (len - NFFT)];
+    return tab[n & (HOP - 1)];
+}
+
 template <typename R>
 struct Smem {
     R* ya;        // signal buffers (padded length)
     R* yb;
-    R* inv_wss;   // 1 / window sum of squares per padded sample (0 outside the kept range)
+    R* inv_wss;   // window-sum table (WSS_TAB entries), or one entry per padded sample (`full`)
     R* win;       // periodic Hann, 256
     Cx<R>* tw128; // TW_ELEMS: the conflict-free stage tables of fft128
     Cx<R>* tw256; // 129 (+pad)
     Cx<R>* ex;    // FW x EX
 };
 
-template <typename R>
-__global__ void __launch_bounds__(FTHREADS, sizeof(R) == 4 ? 2 : 1) griffinlim_fused_kernel(const GlParams p) {
+template <typename R, int FWT>
+__global__ void __launch_bounds__(FWT * 32, (sizeof(R) == 4 || FWT == 8) ? 2 : 1) griffinlim_fused_kernel(const GlParams p) {
+    constexpr int FTHREADS = FWT * 32;
+    constexpr int FW = FWT;
     extern __shared__ __align__(16) unsigned char gl_smem[];
     const int frames = p.frames;
     const int len = NFFT + HOP * (frames - 1);
     const int len4 = (len + 3) & ~3;
+    const bool wss_full = len < 2 * NFFT;
+    const int wss_n = wss_full ? len4 : WSS_TAB;
     Smem<R> sm;
     sm.ya = reinterpret_cast<R*>(gl_smem);
     sm.yb = sm.ya + len4;
     sm.inv_wss = sm.yb + len4;
-    sm.win = sm.inv_wss + len4;
+    sm.win = sm.inv_wss + wss_n;
     sm.tw128 = reinterpret_cast<Cx<R>*>(sm.win + NFFT);
     sm.tw256 = sm.tw128 + TW_ELEMS;
     sm.ex = sm.tw256 + 132;
@@ -466,7 +485,10 @@ __global__ void __launch_bounds__(FTHREADS, sizeof(R) == 4 ? 2 : 1) griffinlim_f
         sm.yb[i] = 0;
     }
     __syncthreads();
-    for (int n = tid; n < len4; n += FTHREADS) {
+    for (int i = tid; i < wss_n; i += FTHREADS) {
+        // the padded sample this entry stands for (interior entries: any sample with all NFFT / HOP frames over it)
+        int n = i;
+        if (!wss_full) n = i < HOP ? NFFT + i : (i < HOP + NFFT / 2 ? NFFT / 2 + (i - HOP) : len - NFFT + (i - HOP - NFFT / 2));
         R v = 0;
         if (n >= NFFT / 2 && n < len - NFFT / 2) {
             R wss = 0;
@@ -479,7 +501,7 @@ __global__ void __launch_bounds__(FTHREADS, sizeof(R) == 4 ? 2 : 1) griffinlim_f
             }
             v = wss > r_tiny<R>() ? (R)1 / wss : (R)1;
         }
-        sm.inv_wss[n] = v;
+        sm.inv_wss[i] = v;
     }
     // S = exp(((rep + 1) / 2) * (log_max - log_clip) + log_clip), Nyquist row = 0
     const float* rep = p.rep + (size_t)item * 128 * frames;
@@ -625,7 +647,7 @@ __global__ void __launch_bounds__(FTHREADS, sizeof(R) == 4 ? 2 : 1) griffinlim_f
         }
         // ---- divide by the window sum of squares (centre padding -> 0), clear the consumed buffer, swap
         for (int n = tid; n < len4; n += FTHREADS) {
-            ynext[n] *= sm.inv_wss[n];
+            ynext[n] *= inv_wss_at<R>(sm.inv_wss, n, len, wss_full);
             ycur[n] = 0;
         }
         __syncthreads();
@@ -639,10 +661,11 @@ __global__ void __launch_bounds__(FTHREADS, sizeof(R) == 4 ? 2 : 1) griffinlim_f
 }
 
 template <typename R>
-size_t smem_bytes(int frames) {
+size_t smem_bytes(int frames, int warps) {
     const int len = NFFT + HOP * (frames - 1);
     const int len4 = (len + 3) & ~3;
-    return sizeof(R) * (3 * (size_t)len4 + NFFT) + sizeof(Cx<R>) * (TW_ELEMS + 132 + (size_t)FW * EX);
+    const size_t wss_n = len < 2 * NFFT ? (size_t)len4 : (size_t)WSS_TAB;
+    return sizeof(R) * (2 * (size_t)len4 + wss_n + NFFT) + sizeof(Cx<R>) * (TW_ELEMS + 132 + (size_t)warps * EX);
 }
 
 }  // namespace fused
@@ -680,15 +703,22 @@ extern "C" int tq_logspec_griffinlim(const float* rep, const double* phase0, voi
     const char* legacy = getenv("TQ_GL_LEGACY");
     const bool use_legacy = legacy && legacy[0] == '1';
     if (!use_legacy && precision == TQ_F32) {
-        const size_t smem = fused::smem_bytes<float>(frames);
+        const size_t smem = fused::smem_bytes<float>(frames, 16);
         TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");
-        TQ_CUDA(cudaFuncSetAttribute(fused::griffinlim_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused::griffinlim_fused_kernel<float><<<items, fused::FTHREADS, smem, st>>>(p);
+        TQ_CUDA(cudaFuncSetAttribute(fused::griffinlim_fused_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fused::griffinlim_fused_kernel<float, 16><<<items, 512, smem, st>>>(p);
     } else if (!use_legacy) {
-        const size_t smem = fused::smem_bytes<double>(frames);
-        TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");
-        TQ_CUDA(cudaFuncSetAttribute(fused::griffinlim_fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused::griffinlim_fused_kernel<double><<<items, fused::FTHREADS, smem, st>>>(p);
+        // fp64: two 8-warp CTAs per SM when both fit (2 x (smem + 1 KB reserved) <= 228 KB), else one 16-warp CTA
+        const size_t smem8 = fused::smem_bytes<double>(frames, 8), smem16 = fused::smem_bytes<double>(frames, 16);
+        const char* w16 = getenv("TQ_GL_WARPS16");
+        if (2 * (smem8 + 1024) <= 228 * 1024 && !(w16 && w16[0] == '1')) {
+            TQ_CUDA(cudaFuncSetAttribute(fused::griffinlim_fused_kernel<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            fused::griffinlim_fused_kernel<double, 8><<<items, 256, smem8, st>>>(p);
+        } else {
+            TQ_CHECK(smem16 <= 227 * 1024, "griffinlim: too many frames for shared memory");
+            TQ_CUDA(cudaFuncSetAttribute(fused::griffinlim_fused_kernel<double, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            fused::griffinlim_fused_kernel<double, 16><<<items, 512, smem16, st>>>(p);
+        }
     } else if (precision == TQ_F32) {
         const size_t smem = gl_smem_bytes<float>(frames);
         TQ_CHECK(smem <= 227 * 1024, "griffinlim: too many frames for shared memory");
