@@ -1,10 +1,13 @@
 // tq_attn_sm100.cu -- attention core on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), bf16, 32 < T <= 512.
 // Reference: QKVAttention.forward (tqdne/blocks.py:156-190): q,k,v = qkv.chunk(3, dim=1), heads split inside each
-// third, w = softmax_fp32((q*s)^T (k*s)) with s = d^-1/4, a = w v.  No mask (off in every shipped config).
-// Serves the pixel-space 2D UNet (T = 256, d = 128) and the 1D UNet (T = 508 / 512, d = 64); the latent UNet
-// (T = 16) stays on attention_small_kernel and the fp32 parity mode on the FFMA kernel (tcgen05 has no fp32 MMA).
+// third, w = softmax_fp32((q*s)^T (k*s)) with s = d^-1/4, a = w v.  No mask here (a causal attention runs on tq_attn.cu).
+// Three kernels: attention_tc_multi_kernel (128 < T <= 512: the pixel-space 2D UNet, T = 256, d = 128, and the 1D UNet,
+// T = 508 / 512, d = 64 -- K / V resident over a range of query blocks, P kept in tensor memory, optional log-sum-exp output
+// for the training step), attention_tc_kernel (32 < T <= 128 and shapes the multi-block kernel cannot hold) and
+// attention_tc_packed_kernel (T in {16, 32}: the latent UNet).  The fp32 parity mode stays on the FFMA kernels (tcgen05 has
+// no fp32 MMA).
 //
-// One CTA = (sample, head, 128 queries), 256 threads.  All keys of the head are resident, so there is no online
+// attention_tc_kernel: one CTA = (sample, head, 128 queries), 256 threads.  All keys of the head are resident, so there is no online
 // softmax and no rescaling of the accumulator:
 //   TMA      Q [128 x d], K [Tk x d], V [Tk x d] boxes of 128 rows x 64 channels (SWIZZLE_128B) straight out of the
 //            channels-last qkv tensor (rows >= T are zero-filled by the TMA unit), Tk = T rounded up to 128

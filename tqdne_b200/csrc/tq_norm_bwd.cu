@@ -12,7 +12,9 @@
 // its position chunk once for the per-channel sums A, B, the cluster exchanges them through distributed shared memory
 // (fixed rank order: deterministic, no atomics, no scratch memset), and every CTA streams the SAME chunk again for dx -- a
 // re-read that comes out of L2 (a chunk is ~130 KB) instead of HBM: 6 B per element of HBM traffic instead of 10, one launch
-// instead of two + a memset.  The two-kernel version below stays as the fallback / A-B switch (TQ_GN_BWD_2PASS=1).
+// instead of two + a memset.  The kernel is bound by its ARITHMETIC (dropout hash + SiLU derivative, ~57 instructions per
+// element before this was done), so phase 1 parks dv = dy * mask * act'(v) in the dx buffer and phase 2 reads it back instead
+// of evaluating either again.  The two-kernel version below stays as the fallback / A-B switch (TQ_GN_BWD_2PASS=1).
 //
 // HBM-bound, two streaming passes over (x, dy): pass 1 leaves A[n][c] = sum_p dv and B[n][c] = sum_p dv xh in a
 // scratch buffer laid out like the forward statistics; pass 2 forms M1 / M2 from them and writes dx (10 B per element in
