@@ -13,3 +13,6 @@ compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test
 # backward that parks dv in the dx buffer
 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "(attention_matches_reference_formula and bf16) or training_helper_kernels or fused_dropout" 2>&1 | tail -6
 compute-sanitizer --tool racecheck --racecheck-report hazard --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "attention_matches_reference_formula and bf16 and (508 or 300 or 256)" 2>&1 | tail -6
+# end of round 2: the option paths (FiLM, causal mask, pooled resamplers, Fourier-embedded conditioning, cond_sample), the
+# two-CTA Griffin-Lim kernel and the rewritten small training kernels
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_engine_gpu.py tests/test_kernels_gpu.py -m gpu -x -q -k "(unet_forward_matches and (film or causal or pool or condembed) and bf16) or (signal_conditioned and bf16) or causal_attention or resamplers or griffinlim_other_frame or training_helper" 2>&1 | tail -6
