@@ -17,6 +17,8 @@
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include <algorithm>
 
 #include <memory>
@@ -43,6 +45,7 @@ struct WgradParams {
     int b_rows;        // rows of the X halo box
     int b_stage;       // bytes of the X halo buffer rounded up to 1024
     int steps_per_sample, total_steps, steps_per_cta, kchunks, co_tiles, ci_tiles;
+    int probe;         // experiments (TQ_WGRAD_PROBE): 1 = the epilogue reads the accumulators but skips the global reductions
 };
 
 __device__ __forceinline__ void tma_load_3d_wg(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2) {
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad1d_kernel(const __grid_con
                     uint32_t r[32];
                     tmem_ld_32x32(t_row + t * 64 + c, r);
                     tmem_ld_wait();
-                    if (co < p.cout) {
+                    if (co < p.cout && !(p.probe & 1)) {
                         // cin is a multiple of 64: the 32 columns are in range and 16 B aligned -> 8 vector reductions
                         float* dst = p.dw + ((long long)co * p.taps + t) * p.dw_ld + p.ci_off + ci_t * 64 + c;
 #pragma unroll
@@ -296,6 +299,8 @@ extern "C" int tq_conv1d_wgrad(const void* x, const void* dy, float* dw, float* 
     p.co_tiles = (cout + 127) / 128;
     p.ci_tiles = cin / 64;
     const int tiles = p.co_tiles * p.ci_tiles;
+    p.probe = 0;
+    if (const char* e = getenv("TQ_WGRAD_PROBE")) p.probe = atoi(e);
     int kchunks = device_sm_count() / tiles;  // one wave of CTAs: every extra K chunk adds a full tile of fp32 reductions
     if (kchunks > p.total_steps) kchunks = p.total_steps;
     if (kchunks < 1) kchunks = 1;
