@@ -209,6 +209,9 @@ def test_training_tape_graph_replay_equals_eager_passes():
     for _ in range(4):
         losses.append(float(step.forward_backward(x, cond, sigma=sigma, noise=noise)))
         grads.append(step.store.G.clone())
-    assert isinstance(step._graph, torch.cuda.CUDAGraph), "the third pass should have captured the tape"
+    # two graphs: the tape is split where the late gradient bucket is final (the data-parallel step starts its all-reduce there)
+    assert isinstance(step._graph, list) and len(step._graph) == 2 and all(isinstance(g_, torch.cuda.CUDAGraph) for g_ in step._graph), \
+        "the third pass should have captured the tape"
+    assert 0 < step.bwd_split < len(step.bwd) and 0 < step.store.tail_off < step.store.n
     assert abs(losses[3] - losses[1]) < 1e-6 * abs(losses[1]) and abs(losses[2] - losses[1]) < 1e-6 * abs(losses[1])
     assert rel_l2(grads[3], grads[1]) < 1e-5 and rel_l2(grads[2], grads[1]) < 1e-5

@@ -413,8 +413,9 @@ class LightningEDM(LightningModule):
 
         with device_guard(self.device):
             ts = self._train_step(batch)
-            loss = ts.forward_backward(batch["signal"], batch.get("cond"))
-            ts.optimizer_step(dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1)
+            ws = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            loss = ts.forward_backward(batch["signal"], batch.get("cond"), world_size=ws)
+            ts.optimizer_step(ws)
         return loss
 
     def sync_trained_weights(self, ema: bool = False):

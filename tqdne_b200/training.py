@@ -42,6 +42,12 @@ def _pad64(v: int) -> int:
     return (v + 63) // 64 * 64
 
 
+# the gradient all-reduce of everything from this input block on overlaps the backward pass of the blocks before it (index
+# 3 = the first Downsample of the shipped UNets: stem + two top-level ResBlocks remain, the longest-running part of the
+# backward with the fewest parameters)
+TAIL_FROM_INPUT_BLOCK = 3
+
+
 class _Store:
     """Flat fp32 parameter / gradient / Adam / EMA buffers with engine-layout views per parameter."""
 
@@ -65,14 +71,24 @@ class _Store:
         for r in res_blocks:
             add(r.emb_layers[1].bias, r.emb_layers[1].bias.shape, "dense")
         self.emb_b_off = self.items[id(res_blocks[0].emb_layers[1].bias)][0]
-        for mod in model.modules():
-            if isinstance(mod, nn.Conv1d):
-                O, I, k = mod.weight.shape
-                add(mod.weight, (_pad64(O), k, _pad64(I)), "conv_w")
-                add(mod.bias, (_pad64(O),), "conv_b")
-        for p in model.parameters():
-            if p.requires_grad and id(p) not in self.items:
-                add(p, p.shape, "dense")
+        # Everything else in two buckets, each in forward order (convolutions, then the remaining parameters).  The LATE
+        # bucket = the layers whose gradients are final early in the backward pass (from the first Downsample on: the deep
+        # input blocks, the middle block, the output blocks, the head); it sits at the end of the flat buffers so that its
+        # gradient all-reduce is ONE contiguous range that can run while the backward of the first blocks is still going.
+        first = min(TAIL_FROM_INPUT_BLOCK, len(model.input_blocks) - 1)
+        tail_mods = list(model.input_blocks)[first:] + [model.middle_block, model.output_blocks, model.out]
+        tail_ids = {id(p) for m in tail_mods for p in m.parameters()}
+        for tail in (False, True):
+            if tail:
+                self.tail_off = off
+            for mod in model.modules():
+                if isinstance(mod, nn.Conv1d) and (id(mod.weight) in tail_ids) == tail:
+                    O, I, k = mod.weight.shape
+                    add(mod.weight, (_pad64(O), k, _pad64(I)), "conv_w")
+                    add(mod.bias, (_pad64(O),), "conv_b")
+            for p in model.parameters():
+                if p.requires_grad and id(p) not in self.items and (id(p) in tail_ids) == tail:
+                    add(p, p.shape, "dense")
         self.n = off
         z = lambda: torch.zeros(self.n, device=device, dtype=torch.float32)  # noqa: E731
         self.P, self.G, self.M, self.V, self.EMA = z(), z(), z(), z(), z()
@@ -324,7 +340,10 @@ class TrainStep1D:
             return cur[0]
 
         hs, h = [], None
+        first_tail = min(TAIL_FROM_INPUT_BLOCK, len(model.input_blocks) - 1)
         for i, blk in enumerate(model.input_blocks):
+            if i == first_tail:
+                self.tail_node0 = len(self.nodes)   # nodes [tail_node0, end) own the parameters of the late bucket
             h = run_seq(blk, [self.xin] if i == 0 else [h])
             hs.append(h)
         h = run_seq(model.middle_block, [h])
@@ -368,7 +387,12 @@ class TrainStep1D:
                 first_use.setdefault(id(t), i)
         bias_done: set[int] = set()
 
+        self.bwd_split = 0
         for idx in range(len(self.nodes) - 1, -1, -1):
+            if idx == self.tail_node0 - 1:
+                # every gradient of the late bucket is final once the ops recorded so far have run
+                self._cur = None
+                self.bwd_split = len(ops)
             kind, mod, srcs, out, extra = self.nodes[idx]
             if kind == "conv":
                 dy = extra.get("dy") or grad.get(id(out))
@@ -556,9 +580,12 @@ class TrainStep1D:
 
     @torch.no_grad()
     def forward_backward(self, signal: torch.Tensor, cond: torch.Tensor | None, *, sigma: torch.Tensor | None = None,
-                         noise: torch.Tensor | None = None) -> torch.Tensor:
+                         noise: torch.Tensor | None = None, world_size: int = 1) -> torch.Tensor:
         """Loss (0-dim CUDA tensor) and gradients (flat buffer `store.G`) of LightningEDM.step on `signal` [N, C, L].
-        `sigma` / `noise` may be given explicitly (tests); otherwise they are drawn as in edm.py:125-127."""
+        `sigma` / `noise` may be given explicitly (tests); otherwise they are drawn as in edm.py:125-127.
+        `world_size` > 1 (data-parallel step): the all-reduce of the late gradient bucket is started as soon as the backward
+        pass has produced it and runs beside the rest of the backward; optimizer_step(world_size) reduces the remainder and
+        waits for both (TQ_TRAIN_OVERLAP=0: one all-reduce of the whole buffer in optimizer_step, as before)."""
         N, L = self.N, self.L
         assert tuple(signal.shape) == (N, self.cin, L), f"expected signal of shape {(N, self.cin, L)}"
         if self.copies_version != self.store.version:
@@ -577,48 +604,75 @@ class TrainStep1D:
             self.cond.copy_(cond.to(torch.float32))
         self.pass_count += 1
         self.drop_seed.fill_((self.pass_count * 0x9E3779B1) & 0x7FFFFFFFFFFF)   # fresh dropout decisions every pass
-        self._run_tape()
+        self._early_work = None
+        between = None
+        if (world_size > 1 and os.environ.get("TQ_TRAIN_OVERLAP", "1") != "0" and self.bwd_split > 0
+                and 0 < self.store.tail_off < self.store.n):
+            import torch.distributed as dist
+
+            def between():
+                # enqueued behind the first part of the tape (NCCL's stream waits for this stream's work so far), beside the second
+                self._early_work = dist.all_reduce(self.store.G[self.store.tail_off:], async_op=True)
+        self._run_tape(between)
         return self.loss[0]
 
-    def _tape(self):
-        """Everything between the step's inputs and its gradients: ~550 launches with static arguments."""
+    def _tape(self, part: int | None = None):
+        """Everything between the step's inputs and its gradients: ~550 launches with static arguments.  `part` 0 = up to
+        the point where the gradients of the late bucket (store.tail_off ..) are final, 1 = the rest of the backward."""
         N, L = self.N, self.L
-        self.store.G.zero_()
-        self.de_all.zero_()
-        st = self._st()
-        for f in self.fwd:
-            f()
-        _lib.check(self.lib.tq_edm_loss(self.out.t.data_ptr(), self.out.C, self.xn.data_ptr(), self.y.data_ptr(), self.sigma.data_ptr(),
-                                        self.dF.t.data_ptr(), self.loss.data_ptr(), N, L, self.cin, self.cout_pad, self.sigma_data,
-                                        st), "edm_loss")
-        for b in self.bwd:
+        if part in (None, 0):
+            self.store.G.zero_()
+            self.de_all.zero_()
+            st = self._st()
+            for f in self.fwd:
+                f()
+            _lib.check(self.lib.tq_edm_loss(self.out.t.data_ptr(), self.out.C, self.xn.data_ptr(), self.y.data_ptr(),
+                                            self.sigma.data_ptr(), self.dF.t.data_ptr(), self.loss.data_ptr(), N, L, self.cin,
+                                            self.cout_pad, self.sigma_data, st), "edm_loss")
+        lo = 0 if part in (None, 0) else self.bwd_split
+        hi = len(self.bwd) if part in (None, 1) else self.bwd_split
+        for b in self.bwd[lo:hi]:
             b()
 
-    def _run_tape(self):
-        """The tape as ONE CUDA graph (captured on the third pass, after two eager ones): the launches all have static
+    def _run_tape(self, between=None):
+        """The tape as CUDA graphs (captured on the third pass, after two eager ones): the launches all have static
         arguments -- the dropout decisions come from a counter in device memory -- so a replay replaces ~550 host-side ctypes
-        calls.  TQ_TRAIN_GRAPH=0, separate (host-seeded) dropout passes or a capture failure fall back to eager launches."""
+        calls.  Two graphs, split where the late bucket's gradients are final: `between()` (the early gradient all-reduce of a
+        data-parallel step) is called between their launches.  TQ_TRAIN_GRAPH=0, separate (host-seeded) dropout passes or a
+        capture failure fall back to eager launches."""
+        def eager():
+            self._tape(0)
+            if between is not None:
+                between()
+            self._tape(1)
+
         use = os.environ.get("TQ_TRAIN_GRAPH", "1") != "0" and (self.fused_dropout or self.p_drop == 0.0)
         if not use or self._graph is False:
-            return self._tape()
+            return eager()
         if self._graph is None:
             self._eager_passes = getattr(self, "_eager_passes", 0) + 1
             if self._eager_passes <= 2:
-                return self._tape()
+                return eager()
             try:
-                g = torch.cuda.CUDAGraph()
+                graphs = []
                 torch.cuda.synchronize(self.dev)
-                with torch.cuda.graph(g):
-                    self._tape()
-                self._graph = g      # capturing does not execute: the replay below runs this pass
+                for part in (0, 1):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._tape(part)
+                    graphs.append(g)
+                self._graph = graphs      # capturing does not execute: the replays below run this pass
             except Exception as e:  # noqa: BLE001
                 self._graph = False
                 import warnings
 
                 warnings.warn(f"tqdne_b200: CUDA-graph capture of the training tape failed ({e}); running eager")
                 torch.cuda.synchronize(self.dev)
-                return self._tape()
-        self._graph.replay()
+                return eager()
+        self._graph[0].replay()
+        if between is not None:
+            between()
+        self._graph[1].replay()
 
     @torch.no_grad()
     def optimizer_step(self, world_size: int = 1):
@@ -627,7 +681,13 @@ class TrainStep1D:
         if world_size > 1:
             import torch.distributed as dist
 
-            dist.all_reduce(s.G)
+            early = self.__dict__.get("_early_work")
+            if early is not None:
+                dist.all_reduce(s.G[: s.tail_off])   # the early bucket: what the end of the backward pass produced
+                early.wait()
+                self._early_work = None
+            else:
+                dist.all_reduce(s.G)
         lr = self.lr()            # the k-th update runs at the schedule's value after k - 1 scheduler steps (Lightning order)
         self.step_count += 1
         _lib.check(self.lib.tq_adam_ema_step(s.P.data_ptr(), s.G.data_ptr(), s.M.data_ptr(), s.V.data_ptr(), s.EMA.data_ptr(), s.n,
@@ -637,7 +697,7 @@ class TrainStep1D:
         self.refresh_weights()
 
     def training_step(self, batch: dict, world_size: int = 1) -> torch.Tensor:
-        loss = self.forward_backward(batch["signal"], batch.get("cond"))
+        loss = self.forward_backward(batch["signal"], batch.get("cond"), world_size=world_size)
         self.optimizer_step(world_size)
         return loss
 
