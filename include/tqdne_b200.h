@@ -24,6 +24,13 @@
 extern "C" {
 #endif
 
+/* ABI history of round 2 (tq_abi_version() must equal the header the caller was built against):
+ *   13  deterministic GroupNorm statistics: tq_conv_desc.stats_parts, tq_gn_desc.parts0/1, tq_conv_stats_parts,
+ *       tq_groupnorm_ws_floats                      14  t_next / t_value on the sampler kernels
+ *   15  tq_gn_bwd_desc.dbias0/1                      16  tq_repack_batch_prepare / tq_repack_batch_run
+ *   17  tq_gn_desc.film (FiLM ResBlocks)             18  tq_attn_desc.causal
+ *   19  tq_plan_add_resample2                        20  tq_attn_desc.lse, tq_attention_writes_lse,
+ *                                                        tq_attention_backward(..., lse_given, stream)            */
 #define TQ_ABI_VERSION 20
 
 enum { TQ_BF16 = 0, TQ_F32 = 1, TQ_F64 = 2 };
