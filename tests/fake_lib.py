@@ -8,6 +8,8 @@ class FakeLib:
         self.calls = []
         self.convs = []
         self.gns = []
+        self.attns = []
+        self.resamples = []
 
     def __getattr__(self, name):
         def fn(*args):
@@ -31,7 +33,13 @@ class FakeLib:
                     has_emb=bool(d.emb), has_res=bool(d.residual), stats=d.stats, stats_parts=d.stats_parts))
             if name == "tq_plan_add_groupnorm":
                 d = args[1]._obj if hasattr(args[1], "_obj") else args[1].contents
-                self.gns.append(dict(N=d.N, P=d.P, C0=d.C0, C1=d.C1, stats0=d.stats0, stats1=d.stats1, ws=d.ws, parts0=d.parts0, parts1=d.parts1))
+                self.gns.append(dict(N=d.N, P=d.P, C0=d.C0, C1=d.C1, stats0=d.stats0, stats1=d.stats1, ws=d.ws, parts0=d.parts0, parts1=d.parts1,
+                                     film=d.film, film_ld=d.film_ld))
+            if name == "tq_plan_add_attention":
+                d = args[1]._obj if hasattr(args[1], "_obj") else args[1].contents
+                self.attns.append(dict(N=d.N, T=d.T, heads=d.heads, d=d.d, causal=d.causal, lse=d.lse))
+            if name == "tq_plan_add_resample2":
+                self.resamples.append(dict(N=args[4], H=args[5], W=args[6], C=args[7], mode=args[8]))
             if name == "tq_last_error":
                 return b""
             return 0

@@ -91,6 +91,48 @@ def test_1d_unet_and_decoder_lowering(fake):
     assert (d.out.H, d.out.W, d.out.C) == (128, 128, 3)
 
 
+def test_option_lowering(fake):
+    """The module options no shipped config uses, as the lowering hands them to the library: FiLM -> tq_gn_desc.film on the
+    second norm of every ResBlock (and no embedding add on conv1), use_causal_mask -> tq_attn_desc.causal, conv_resample=False
+    -> resample ops instead of convolutions (their consumers' norms run a statistics pass: no conv epilogue behind them),
+    cond_sample -> a second source of the stem convolution, cond_emb_scale -> one more Fourier op."""
+    import tqdne_b200 as tq
+    from tqdne_b200.lowering import UNetPlan
+
+    def lower(kind, **kw):
+        fake.calls.clear(); fake.convs.clear(); fake.gns.clear(); fake.attns.clear(); fake.resamples.clear()
+        net = tq.UNetModel(**unet_cfg(kind)).eval()
+        return net, UNetPlan(net, 2, (32, 32) if "2d" in kind else (512,), torch.bfloat16, uniform_t=True, **kw)
+
+    net, _ = lower("latent2d")
+    base_convs, base_gns = len(fake.convs), len(fake.gns)
+    assert not any(g["film"] for g in fake.gns) and not any(a["causal"] for a in fake.attns) and not fake.resamples
+    n_res = sum(1 for m in net.modules() if type(m).__name__ == "ResBlock")
+
+    lower("latent2d_film")
+    assert sum(1 for g in fake.gns if g["film"]) == n_res and len(fake.gns) == base_gns
+    assert all(g["film_ld"] >= 2 * (g["C0"] + g["C1"]) for g in fake.gns if g["film"])
+    assert sum(1 for c in fake.convs if c["has_emb"]) == 0            # FiLM: conv1 no longer adds the embedding
+
+    lower("latent2d_causal")
+    assert len(fake.attns) == 6 and all(a["causal"] == 1 for a in fake.attns)
+
+    lower("latent2d_pool")
+    assert len(fake.convs) == base_convs - 6                          # 3 stride-2 and 3 post-upsample convolutions are gone
+    assert sorted(r["mode"] for r in fake.resamples) == [0, 0, 0, 1, 1, 1]
+    assert sum(1 for g in fake.gns if not g["stats0"]) >= 6           # norms behind a resampler compute their own statistics
+
+    _, p = lower("latent2d_condsample", cond_channels=8)
+    stem = fake.convs[1]                                               # convs[0] = the embedding GEMM
+    assert stem["num_srcs"] == 2 and p.xcond is not None and p.cin_pad == 64 and p.xcond.C == 64
+    assert len(fake.convs) == base_convs
+
+    lower("1d_condembed")
+    assert sum(1 for c in fake.calls if c == "tq_plan_add_fourier") == 2   # the noise level and the conditioning feature
+    with pytest.raises(NotImplementedError):
+        tq.UNetModel(**(unet_cfg("1d") | {"cond_emb_scale": 0.5}))     # five features: the reference cannot run it either
+
+
 def test_pack_conv_layout():
     from tqdne_b200.engine import pack_conv
 
