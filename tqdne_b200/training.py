@@ -604,6 +604,9 @@ class TrainStep1D:
             self.cond.copy_(cond.to(torch.float32))
         self.pass_count += 1
         self.drop_seed.fill_((self.pass_count * 0x9E3779B1) & 0x7FFFFFFFFFFF)   # fresh dropout decisions every pass
+        stale = self.__dict__.get("_early_work")
+        if stale is not None:
+            stale.wait()   # a pass whose optimizer_step never came: its all-reduce must not run into this pass's G.zero_()
         self._early_work = None
         between = None
         if (world_size > 1 and os.environ.get("TQ_TRAIN_OVERLAP", "1") != "0" and self.bwd_split > 0
