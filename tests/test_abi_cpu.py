@@ -74,3 +74,29 @@ def test_product_path_fails_loudly_without_the_library(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "missing.so")
     with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
         _lib.lib()
+
+
+def test_repack_batch_prepare_is_host_logic(lib_path):
+    """tq_repack_batch_prepare only assigns thread-block ranges to the jobs of the one-launch operand repack: callable
+    without a GPU.  (Pointers are never dereferenced on the host.)"""
+    from tqdne_b200 import _lib
+
+    handle = ctypes.CDLL(str(lib_path))
+    handle.tq_repack_batch_prepare.restype = ctypes.c_int64
+    handle.tq_repack_batch_prepare.argtypes = [ctypes.POINTER(_lib.TqRepackJob), ctypes.c_int32]
+    jobs = (_lib.TqRepackJob * 3)()
+    # forward cast of a [128, 5, 192] master: ceil(128 * 5 * 192 / 2048) blocks; two input-gradient copies: one block per
+    # 32 x 32 (co, ci) tile and tap
+    jobs[0].master, jobs[0].fwd, jobs[0].Op, jobs[0].k, jobs[0].Ip = 0x1000, 0x2000, 128, 5, 192
+    jobs[1].master, jobs[1].bwd, jobs[1].Op, jobs[1].k, jobs[1].Ip, jobs[1].ci_off, jobs[1].Cs = 0x1000, 0x3000, 128, 5, 192, 64, 128
+    jobs[2].master, jobs[2].bwd, jobs[2].Op, jobs[2].k, jobs[2].Ip, jobs[2].ci_off, jobs[2].Cs = 0x1000, 0x4000, 72, 1, 320, 0, 40
+    total = handle.tq_repack_batch_prepare(jobs, 3)
+    want = [-(-128 * 5 * 192 // 2048), 4 * 4 * 5, 2 * 3 * 1]
+    assert [j.nblocks for j in jobs] == want and total == sum(want)
+    assert [j.block0 for j in jobs] == [0, want[0], want[0] + want[1]]
+    jobs[1].fwd = 0x5000                       # both copies in one job: refused
+    assert handle.tq_repack_batch_prepare(jobs, 3) == -1
+    jobs[1].fwd = None
+    jobs[2].Cs = 400                           # source slice beyond the master's input channels: refused
+    assert handle.tq_repack_batch_prepare(jobs, 3) == -1
+
