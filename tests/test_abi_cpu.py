@@ -100,3 +100,27 @@ def test_repack_batch_prepare_is_host_logic(lib_path):
     jobs[2].Cs = 400                           # source slice beyond the master's input channels: refused
     assert handle.tq_repack_batch_prepare(jobs, 3) == -1
 
+
+def test_attention_writes_lse_decision_is_host_logic(lib_path):
+    """Which attention shapes take the multi-block tensor-core kernel -- the one that can leave the rows' log-sum-exp behind
+    for the backward pass -- is decided on the host from the descriptor alone."""
+    from tqdne_b200 import _lib
+
+    handle = ctypes.CDLL(str(lib_path))
+    handle.tq_attention_writes_lse.restype = ctypes.c_int32
+    handle.tq_attention_writes_lse.argtypes = [ctypes.POINTER(_lib.TqAttnDesc)]
+
+    def writes(dtype, T, d, causal=0):
+        desc = _lib.TqAttnDesc()
+        desc.dtype, desc.N, desc.T, desc.heads, desc.d, desc.causal = dtype, 2, T, 4, d, causal
+        desc.qkv, desc.out = 0x10000, 0x20000        # 16 B aligned device addresses (never dereferenced here)
+        return handle.tq_attention_writes_lse(ctypes.byref(desc))
+
+    BF16, F32 = 0, 1
+    assert writes(BF16, 508, 64) == 1 and writes(BF16, 512, 64) == 1 and writes(BF16, 256, 128) == 1   # 1D UNet, pixel UNet
+    assert writes(BF16, 300, 64) == 1                  # 384 keys: O fits beside the packed P
+    assert writes(BF16, 100, 64) == 0 and writes(BF16, 16, 128) == 0    # one query block / the packed small-T kernel
+    assert writes(BF16, 512, 128) == 0                 # K + V of 512 keys x 128 channels do not fit beside two Q buffers
+    assert writes(BF16, 600, 64) == 0 and writes(F32, 508, 64) == 0     # FFMA kernels
+    assert writes(BF16, 508, 64, causal=1) == 0        # a causal attention runs on the FFMA kernels
+
